@@ -1,0 +1,267 @@
+"""Live-reference harness (TEST INFRASTRUCTURE - never imported by the product path).
+
+Imports the unmodified reference (`/root/reference`, package ``src.hydromodel`` and the
+``cases`` drivers) in THIS container, builds the shipped cases exactly as the reference's
+own drivers do, runs ``PreissmannSolver.run`` and records what the parity tests need:
+
+* ``depth`` / ``flow``            - result arrays  (reference ``solver.py:43-44``)
+* ``iters``                       - Newton iterations per time level (``preissmann.py:122-161``;
+                                    the reference only prints them, so we count ``spsolve`` calls)
+* ``storage_stage``               - reservoir stage record (``boundary.py:126-131``)
+* optional per-iteration ``(J.data, R, delta)`` captures via an ``spsolve`` hook.
+
+The reference cannot travel to the GPU box, so everything it produces is committed as small
+fixtures under ``tests/golden/`` by ``oracle/make_golden.py``.
+
+Caveats handled here: matplotlib/openpyxl/geopandas are absent, so
+``matplotlib.pyplot`` is stubbed before the gerd modules are imported; the gerd case uses
+Windows path literals, so ``pandas.read_csv`` is wrapped to normalise ``\\`` and the process
+changes directory to the reference root.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import time
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("PR_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "hydromodel"))
+
+
+_ready = False
+
+
+def setup_reference() -> None:
+    """Make ``src.hydromodel`` and ``cases.*`` importable, with the stubs described above."""
+    global _ready
+    if _ready:
+        return
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    os.chdir(REFERENCE_ROOT)
+
+    # matplotlib is not installed; the gerd helper module imports pyplot at module scope.
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        plt = types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.pyplot"] = plt
+
+    import pandas
+
+    if not getattr(pandas.read_csv, "_pr_wrapped", False):
+        _orig = pandas.read_csv
+
+        def read_csv(path, *a, **k):
+            if isinstance(path, str):
+                path = path.replace("\\", "/")
+            return _orig(path, *a, **k)
+
+        read_csv._pr_wrapped = True
+        pandas.read_csv = read_csv
+    _ready = True
+
+
+# --------------------------------------------------------------------------------------
+# Case builders: each returns an un-run reference PreissmannSolver plus run() kwargs.
+# They restate the reference drivers' *configuration* (not algorithms) because the drivers
+# execute at import time and write result files.
+# --------------------------------------------------------------------------------------
+
+def build_example():
+    """cases/example/main.py:8-57 (config 1)."""
+    setup_reference()
+    from src.hydromodel.boundary import Boundary
+    from src.hydromodel.channel import Channel
+    from src.hydromodel.hydrograph import Hydrograph
+    from src.hydromodel.lumped_storage import LumpedStorage
+    from src.hydromodel.preissmann import PreissmannSolver
+
+    def inflow(t):
+        base, peak = 1000, 10000
+        rise, hold, fall = 3 * 3600, 6 * 3600, 4 * 3600
+        if t <= 0:
+            return base
+        if t < rise:
+            return base + (peak - base) * t / rise
+        if t - rise < hold:
+            return peak
+        if t - rise - hold < fall:
+            return peak - (peak - base) * (t - rise - hold) / fall
+        return base
+
+    us = Boundary(condition="flow_hydrograph", bed_level=5, chainage=0, hydrograph=Hydrograph(function=inflow))
+    ds = Boundary(condition="fixed_depth", initial_depth=5, bed_level=0, chainage=20000)
+    ds.set_lumped_storage(LumpedStorage(surface_area=5000 * 250, min_stage=5, solution_boundaries=(0, 200)))
+    ch = Channel(width=250, initial_flow=us.hydrograph.get_at(0), roughness=0.027,
+                 upstream_boundary=us, downstream_boundary=ds)
+    solver = PreissmannSolver(channel=ch, theta=0.8, time_step=3600, spatial_step=1000, simulation_time=24 * 3600)
+    return solver, dict(tolerance=1e-4, max_iter=100)
+
+
+def build_akbari(peak_flow: float = 200.0, n_nodes_override: int | None = None, **over):
+    """cases/akbari_firoozi/settings.py + main_preissmann.py:5-32 (config 2).
+
+    ``over`` lets the config-5 style clones change length / steps / theta for spot checks.
+    """
+    setup_reference()
+    from math import cos, pi, sin
+
+    from src.hydromodel.boundary import Boundary
+    from src.hydromodel.channel import Channel
+    from src.hydromodel.hydrograph import Hydrograph
+    from src.hydromodel.preissmann import PreissmannSolver
+
+    width = over.get("width", 120)
+    length = over.get("length", 29000)
+    roughness = over.get("roughness", 0.023)
+    S_0 = over.get("S_0", 0.00061)
+    dx = over.get("spatial_step", 1000)
+    duration = over.get("duration", 20 * 3600)
+    theta = over.get("theta", 0.5)
+    dt = over.get("time_step", 3600)
+    tol = over.get("tolerance", 1e-4)
+    Q_b = 100
+
+    def hyd(t):
+        t_b, t_p = 15 * 3600, 5 * 3600
+        if t <= t_p:
+            return peak_flow / 2 * sin(pi * t / t_p - pi / 2) + peak_flow / 2 + Q_b
+        if t <= t_b:
+            return peak_flow / 2 * cos(pi * (t - t_p) / (t_b - t_p)) + peak_flow / 2 + Q_b
+        return Q_b
+
+    us = Boundary(condition="flow_hydrograph", bed_level=S_0 * length, chainage=0, hydrograph=Hydrograph(hyd))
+    ds = Boundary(condition="normal_depth", bed_level=0, chainage=length)
+    ch = Channel(width=width, initial_flow=Q_b, roughness=roughness, upstream_boundary=us,
+                 downstream_boundary=ds, interpolation_method="steady-state")
+    solver = PreissmannSolver(channel=ch, theta=theta, time_step=dt, spatial_step=dx,
+                              simulation_time=duration, regularization=False)
+    return solver, dict(tolerance=tol)
+
+
+def build_gerd(n_main=None, n_fp=None, calibration: bool = False, **over):
+    """cases/gerd_roseires/model.py:10-92 (config 3) / n_calibrate.py:5-17 (config 4 member).
+
+    Restates model.run() up to (not including) ``solver.run`` so the solver object can be
+    flattened, hooked and timed separately.
+    """
+    setup_reference()
+    from cases.gerd_roseires import settings
+    from cases.gerd_roseires.custom_functions import import_hydrograph, import_table, load_trapzoid_xs
+    from cases.gerd_roseires.gerd_discharge import GerdHydrograph
+    from cases.gerd_roseires.roseires_rating_curve import RoseiresRatingCurve
+    from src.hydromodel.boundary import Boundary
+    from src.hydromodel.channel import Channel
+    from src.hydromodel.hydrograph import Hydrograph
+    from src.hydromodel.preissmann import PreissmannSolver
+
+    if calibration:
+        inflow_path = "cases\\gerd_roseires\\data\\inflow_hydrograph_small.csv"
+        coords_path = None
+        sim_duration = None
+    else:
+        inflow_path = settings.inflow_hyd_path
+        coords_path = settings.coords_path
+        sim_duration = settings.sim_duration
+    sim_duration = over.get("sim_duration", sim_duration)
+    coords_path = over.get("coords_path", coords_path)
+    time_step = over.get("time_step", settings.time_step)
+    level0 = over.get("initial_roseires_level", settings.initial_roseires_level)
+
+    inflow = Hydrograph(table=import_hydrograph(inflow_path))
+    duration = int(inflow.table[-1, 0]) if sim_duration is None else int(sim_duration)
+    gerd = GerdHydrograph()
+    gerd.build(inflow_hydrograph=inflow, time_step=time_step, duration=duration,
+               initial_stage=settings.initial_gerd_level)
+    q0 = gerd.get_at(time=0)
+    chain, sections = load_trapzoid_xs(file_path=settings.cross_sections_path, n_fp=n_fp, n_main=n_main)
+    bed = sections[-1].z_min
+    up = Boundary(condition="flow_hydrograph", hydrograph=gerd, chainage=chain[0])
+    down = Boundary(initial_depth=level0 - bed, bed_level=bed, condition="rating_curve",
+                    rating_curve=RoseiresRatingCurve(initial_stage=level0, initial_flow=q0,
+                                                     jammed_sluice_gates=settings.JAMMED_SLUICEGATES,
+                                                     jammed_spillways=settings.JAMMED_SPILLWAYS),
+                    chainage=chain[-1])
+    ch = Channel(initial_flow=q0, upstream_boundary=up, downstream_boundary=down)
+    if coords_path is not None:
+        coords = import_table(coords_path, sort_by="chainage")
+        ch.set_coords(coords=coords[:, 1:], chainages=coords[:, 0])
+    ch.set_cross_sections(chainages=chain, sections=sections)
+    solver = PreissmannSolver(channel=ch, theta=settings.theta, time_step=time_step,
+                              spatial_step=settings.spatial_step, simulation_time=duration)
+    solver._pr_first_section_z = sections[0].z_min
+    return solver, dict(tolerance=settings.tolerance)
+
+
+# --------------------------------------------------------------------------------------
+
+def run_and_record(solver, run_kwargs, capture_iterations: int = 0):
+    """Run the reference solver; returns dict(depth, flow, iters, seconds, [captures])."""
+    from src.hydromodel import preissmann as ref_pr
+
+    counts: dict[int, int] = {}
+    captures = []
+    orig = ref_pr.spla.spsolve
+
+    def hooked(J, rhs, *a, **k):
+        lvl = int(solver.time_level)
+        counts[lvl] = counts.get(lvl, 0) + 1
+        delta = orig(J, rhs, *a, **k)
+        if len(captures) < capture_iterations:
+            captures.append(dict(level=lvl, J=np.array(J.data, dtype=np.float64),
+                                 R=-np.array(rhs, dtype=np.float64), delta=np.array(delta, dtype=np.float64),
+                                 x=np.array(solver.unknowns, dtype=np.float64)))
+        return delta
+
+    ref_pr.spla.spsolve = hooked
+    t0 = time.perf_counter()
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            solver.run(verbose=0, **run_kwargs)
+    finally:
+        ref_pr.spla.spsolve = orig
+    secs = time.perf_counter() - t0
+    levels = solver.depth.shape[0]
+    iters = np.array([counts.get(k, 0) for k in range(1, levels)], dtype=np.int32)
+    out = dict(depth=np.array(solver.depth), flow=np.array(solver.flow), iters=iters, seconds=secs)
+    st = getattr(solver, "storage_stage", None)
+    if st is not None:
+        out["storage_stage"] = np.array(st, dtype=np.float64)
+    if captures:
+        out["captures"] = captures
+    return out
+
+
+def gerd_calibration_levels(solver, result, Q):
+    """cases/gerd_roseires/model.py:105-113: stage at the upstream node interpolated at Q."""
+    return np.interp(Q, result["flow"][:, 0], result["depth"][:, 0] + solver._pr_first_section_z)
+
+
+CALIB_Q = np.array([1562.5, 3850, 6000, 10000, 14000, 21000], dtype=np.float64)        # n_calibrate.py:30
+CALIB_H_TARGET = np.array([497.5, 500, 502, 505, 507, 510], dtype=np.float64)           # n_calibrate.py:29
+
+
+def time_member(n_main: float):
+    """One config-4 member through the unmodified reference (used by bench.py --impl reference
+    only in this container; on the GPU box the reference is absent and the C port is timed)."""
+    solver, kw = build_gerd(n_main=n_main, calibration=True)
+    res = run_and_record(solver, kw)
+    return res["seconds"], int(res["iters"].sum())
+
+
+if __name__ == "__main__":
+    s, kw = build_example()
+    r = run_and_record(s, kw)
+    print("example iters", r["iters"].tolist(), r["depth"].sum(), r["flow"].sum(), r["seconds"])
