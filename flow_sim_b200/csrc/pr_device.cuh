@@ -1,0 +1,336 @@
+// pr_device.cuh - device-side data model and node / boundary math of the Preissmann scheme.
+//
+// Everything here is FP64 and written for sm_100a.  The formulas follow the reference
+// (cve-mohd/flow-sim, src/hydromodel) function by function - citations below - but are algebraically
+// condensed for the FP64 pipe: one cbrt and at most three sqrt per node instead of up to nine pow(),
+// reciprocals shared between terms, Manning factors n^-1.5 hoisted out of the Newton loop.  The
+// condensation changes results at the few-ulp level only (tests hold the device path to 1e-9 relative
+// and identical Newton iteration counts against the CPU oracle and the reference's golden outputs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/preissmann_b200.h"
+
+namespace pr {
+
+// ---- kernel parameter block (host builds it from the ABI structs) ---------------------------------
+
+struct DevRating {
+  int type, n_coef;
+  double a, b, c, shift;
+  double coef[PR_MAX_POLY], dcoef[PR_MAX_POLY];
+  double off, scl;
+  // Roseires, collapsed on the host (long double) to two quadratics centred on stage0:
+  //   Q_state(s) = q[0] + u*(q[1] + u*q[2]),  u = s - stage0
+  double lo[3], hi[3];
+  double stage0, buffer, inv_buffer, dY, inv_2dY;
+};
+
+struct DevBC {
+  int type;
+  double bed_level, slope_factor /* sign(S0)*sqrt|S0| */, fixed_depth;
+  const double* series;
+  long long series_stride;
+  DevRating rc;
+  double st_area, st_inv_area, st_min_stage;
+};
+
+struct DevGeom {
+  const int* kind;
+  const double *z, *b, *m, *hb, *Tb, *Wb, *bl, *br, *mfp, *nl, *nm, *nr, *curv;
+  const double *member_nm, *member_nfp;
+};
+
+struct DevParams {
+  int N, L, M, max_iter, out_mode;
+  double theta, dt, dx, tol, g;
+  DevGeom geo;
+  DevBC up, dn;
+  const double *ic_h, *ic_q;
+  long long ic_stride;
+  double *out_h, *out_q;
+  int *iters, *status, *fail_level;
+  double *storage_stage, *final_error;
+};
+
+// ---- per-node geometry staged in shared memory (SoA, NP = padded node count) -----------------------
+
+enum GeoField {
+  F_KIND = 0, F_Z, F_B, F_M, F_SQM, F_HB, F_TB, F_WB, F_BL, F_BR, F_MFP, F_SQFP, F_AMF, F_PM, F_INVPM,
+  F_NM, F_CNL, F_CNM, F_CNR, F_CURV, F_COUNT
+};
+
+__device__ __forceinline__ double inv_n15(double n) { return 1.0 / (n * sqrt(n)); }  // n^-1.5
+
+// Fills sg[F_COUNT][NP]; nodes >= N replicate node N-1 so padded lanes compute finite throw-away values.
+__device__ inline void stage_geometry(const DevGeom& g, int N, int NP, double* sg, int tid, int nthreads) {
+  for (int i = tid; i < NP; i += nthreads) {
+    const int s = i < N ? i : N - 1;
+    const double b = g.b[s], m = g.m[s], hb = g.hb[s], Tb = g.Tb[s], mfp = g.mfp[s];
+    const double sqm = sqrt(1.0 + m * m);
+    const double Pm = b + 2.0 * hb * sqm;               // cross_section.py:661,695
+    sg[F_KIND * NP + i] = (double)g.kind[s];
+    sg[F_Z * NP + i] = g.z[s];
+    sg[F_B * NP + i] = b;
+    sg[F_M * NP + i] = m;
+    sg[F_SQM * NP + i] = sqm;
+    sg[F_HB * NP + i] = hb;
+    sg[F_TB * NP + i] = Tb;
+    sg[F_WB * NP + i] = g.Wb[s];
+    sg[F_BL * NP + i] = g.bl[s];
+    sg[F_BR * NP + i] = g.br[s];
+    sg[F_MFP * NP + i] = mfp;
+    sg[F_SQFP * NP + i] = sqrt(1.0 + mfp * mfp);
+    sg[F_AMF * NP + i] = (b + Tb) / 2.0 * hb;           // cross_section.py:660
+    sg[F_PM * NP + i] = Pm;
+    sg[F_INVPM * NP + i] = Pm > 0.0 ? 1.0 / Pm : 0.0;
+    sg[F_NM * NP + i] = g.nm[s];
+    sg[F_CNL * NP + i] = inv_n15(g.nl[s]);
+    sg[F_CNM * NP + i] = inv_n15(g.nm[s]);
+    sg[F_CNR * NP + i] = inv_n15(g.nr[s]);
+    sg[F_CURV * NP + i] = g.curv[s];
+  }
+}
+
+// Per-member roughness override (model.run(n_main=, n_fp=)); has_* false -> the node's own values.
+struct Rough {
+  bool has_nm, has_nfp;
+  double nm, cnm, cnfp;
+};
+
+// Everything a cell needs from one node at the current iterate.
+struct NodeVals {
+  double Q;     // discharge
+  double A;     // wetted area                       (TrapezoidalSection.properties, cross_section.py:623-679)
+  double T;     // top width = dA/dh                 (:792-793)
+  double Y;     // water level z_min + h             (Solver.water_level_at, solver.py:287-288)
+  double Se;    // energy slope Sf + Sc              (Channel.Se, channel.py:53-69)
+  double F;     // Q^2 / A
+  double QA;    // Q / A
+  double dSeA;  // dSe/dA = dSf_dA + dSc_dA (the latter already x dA/dh, quirk 7) (channel.py:71-87)
+  double dSeQ;  // dSe/dQ                            (channel.py:89-105)
+  double K;     // conveyance                        (cross_section.py:741-754)
+  double dKA;   // dK/dA                             (cross_section.py:756-764)
+};
+
+// Node pass.  h = depth unknown, Q = discharge unknown, i = node slot in shared memory.
+template <bool CURV>
+__device__ __forceinline__ void node_eval(const double* __restrict__ sg, const int NP, const int i, const double h,
+                                          const double Q, const Rough& rg, const double g, NodeVals& o) {
+#define GEO(f) sg[(f)*NP + i]
+  const int kind = (int)GEO(F_KIND);
+  const double z = GEO(F_Z), b = GEO(F_B);
+  const double hw = z + h;        // Solver.water_level_at
+  const double d = hw - z;        // depth = max(0, hw - z_bed); a dry node (d <= 0) ends in status NaN
+  const double nm = rg.has_nm ? rg.nm : GEO(F_NM);
+  double A, P, T, dPdh, K, invK2;
+  bool compound_over = false;
+  if (kind == PR_XS_RECT) {
+    A = b * d;
+    P = b + 2.0 * d;
+    T = b;
+    dPdh = 2.0;
+  } else {
+    const double hb = GEO(F_HB);
+    if (kind == PR_XS_TRAPEZOID || d <= hb) {
+      const double m = GEO(F_M), sqm = GEO(F_SQM);
+      T = b + 2.0 * m * d;
+      A = (b + T) * 0.5 * d;
+      P = b + 2.0 * d * sqm;
+      dPdh = 2.0 * sqm;
+    } else {
+      compound_over = true;
+      const double dfp = d - hb, mfp = GEO(F_MFP), sqfp = GEO(F_SQFP);
+      const double bl = GEO(F_BL), br = GEO(F_BR);
+      const double Al = (bl + 0.5 * mfp * dfp) * dfp, Pl = bl + dfp * sqfp;
+      const double Ar = (br + 0.5 * mfp * dfp) * dfp, Pr = br + dfp * sqfp;
+      const double Amf = GEO(F_AMF);
+      A = Amf + Al + Ar;                                   // quirk 4: total area omits T_bank*dfp
+      P = GEO(F_PM) + Pl + Pr;
+      T = GEO(F_WB) + 2.0 * mfp * dfp;
+      dPdh = 2.0 * sqfp;
+      // K = (K_l^1.5 + K_m^1.5 + K_r^1.5)^(2/3), K_j = A_j R_j^(2/3)/n_j  (cross_section.py:681-754)
+      // K_j^1.5 = A_j^1.5 * R_j * n_j^-1.5 = A_j*sqrt(A_j) * (A_j/P_j) * n_j^-1.5
+      const double Am = Amf + GEO(F_TB) * dfp;             // conveyance area includes the column (:694)
+      const double cnm = rg.has_nm ? rg.cnm : GEO(F_CNM);
+      const double cnl = rg.has_nfp ? rg.cnfp : GEO(F_CNL);
+      const double cnr = rg.has_nfp ? rg.cnfp : GEO(F_CNR);
+      double S = Am * sqrt(Am) * (Am * GEO(F_INVPM)) * cnm;
+      if (Pl > 0.0) S += Al * sqrt(Al) * (Al / Pl) * cnl;
+      if (Pr > 0.0) S += Ar * sqrt(Ar) * (Ar / Pr) * cnr;
+      const double cS = cbrt(S);
+      K = cS * cS;
+      invK2 = 1.0 / (S * cS);
+    }
+  }
+  const double invP = 1.0 / P;
+  const double R = A * invP;
+  double cR = 0.0;
+  if (!compound_over) {
+    // K = A R^(2/3) / n_main (hydraulics.py:15-26); compound in-bank passes through
+    // (0 + K_m^1.5 + 0)^(2/3) in the reference, equal to K_m within an ulp (quirk 5)
+    cR = cbrt(R);
+    K = A * (cR * cR) / nm;
+    invK2 = 1.0 / (K * K);
+  }
+  const double invA = 1.0 / A;
+  const double invT = 1.0 / T;
+  // dK/dA = (R^(2/3) + A*(2/3)*R^(-1/3)*dR_dA)/n_eq with n_eq = A R^(2/3)/K (frozen, quirk 6)
+  //       = K*(1/A + (2/3)*dR_dA/R),  dR_dA = (P - A*dP_dh/T)/P^2            (cross_section.py:756-790)
+  const double dRA = (P - A * dPdh * invT) * (invP * invP);
+  const double dKA_over_K = invA + (2.0 / 3.0) * dRA / R;
+  const double absQ = fabs(Q);
+  const double Sf = Q * absQ * invK2;                       // hydraulics.py:42-57
+  double Se = Sf;
+  double dSeA = -2.0 * Sf * dKA_over_K;                     // hydraulics.py:59-75
+  double dSeQ = 2.0 * absQ * invK2;                         // hydraulics.py:77-92
+  if (CURV) {
+    const double curv = GEO(F_CURV);
+    if (curv != 0.0) {
+      // hydraulics.Sc / dSc_dA / dSc_dQ (hydraulics.py:94-229), CrossSection wrappers cross_section.py:143-175
+      if (compound_over) cR = cbrt(R);
+      const double n_eq = (kind == PR_XS_COMPOUND) ? A * (cR * cR) / K : nm;    // cross_section.py:710-739
+      const double rc = 1.0 / curv;
+      const double V = Q / fmax(A, 1e-6), D = A / fmax(T, 1e-6);
+      const double Fr = V / sqrt(g * fmax(D, 1e-6));
+      const double f = 8.0 * g * (n_eq * n_eq) / cR;        // C = R^(1/6)/n, f = 8g/C^2
+      const double sqf = sqrt(f);
+      const double lead = 2.86 * sqf + 2.07 * f;
+      const double num = lead * (h * h) * (Fr * Fr);
+      const double den = (0.565 + sqf) * (rc * rc);
+      Se += num / den;
+      if (fabs(curv) > 1e-12) {
+        const double gD = g * (A * invT);
+        const double rs = rsqrt(gD);                        // (gD)^-0.5, unclamped (quirk 7)
+        const double dFrA = -0.5 * (Q * invA) * (rs * rs * rs) * g * invT + (-Q * invA * invA) * rs;
+        const double dFrQ = invA * rs;
+        const double dfA = -(8.0 / 3.0) * g * (n_eq * n_eq) / (R * cR) * dRA;
+        const double dnumA = (2.86 / (2.0 * sqf) * dfA + 2.07 * dfA) * (h * h) * (Fr * Fr) +
+                             lead * (2.0 * h * invT * (Fr * Fr) + (h * h) * 2.0 * Fr * dFrA);
+        const double ddenA = (1.0 / (2.0 * sqf) * dfA) * (rc * rc);
+        const double dScA = (dnumA * den - num * ddenA) / (den * den);
+        dSeA += dScA * T;                                   // cross_section.py:164 (x dA_dh), multiplied again by the caller
+        const double dnumQ = lead * (h * h) * 2.0 * Fr * dFrQ;
+        dSeQ += (dnumQ * den) / (den * den);
+      }
+    }
+  }
+  o.Q = Q;
+  o.A = A;
+  o.T = T;
+  o.Y = hw;
+  o.Se = Se;
+  o.QA = Q * invA;
+  o.F = Q * o.QA;
+  o.dSeA = dSeA;
+  o.dSeQ = dSeQ;
+  o.K = K;
+  o.dKA = K * dKA_over_K;
+#undef GEO
+}
+
+// ---- rating curves ----------------------------------------------------------------------------------
+
+__device__ __forceinline__ double horner(const double* c, int n, double x) {
+  double acc = c[n - 1];
+  for (int i = n - 2; i >= 0; --i) acc = c[i] + acc * x;
+  return acc;
+}
+
+__device__ __forceinline__ double roseires_q(const DevRating& r, double stage) {
+  // RoseiresRatingCurve.alpha_smooth + effective_release (roseires_rating_curve.py:87-109)
+  const double u = stage - r.stage0;
+  double alpha;
+  if (stage >= r.stage0 + r.buffer) alpha = 1.0;
+  else if (stage <= r.stage0) alpha = 0.0;
+  else {
+    const double s = u * r.inv_buffer;
+    alpha = s * s * (3.0 - 2.0 * s);
+  }
+  const double lo = r.lo[0] + u * (r.lo[1] + u * r.lo[2]);
+  const double hi = r.hi[0] + u * (r.hi[1] + u * r.hi[2]);
+  return (1.0 - alpha) * lo + alpha * hi;
+}
+
+// RatingCurve.discharge (rating_curve.py:32-63)
+__device__ __forceinline__ double rating_q(const DevRating& r, double stage) {
+  switch (r.type) {
+    case PR_RC_POLY2: { const double x = stage + r.shift; return r.a * (x * x) + r.b * x + r.c; }
+    case PR_RC_POWER: return r.a * pow(stage + r.shift, r.b);
+    case PR_RC_POLYNOMIAL: return horner(r.coef, r.n_coef, r.off + r.scl * stage);   // NB: no shift (:48-49)
+    case PR_RC_ROSEIRES: return roseires_q(r, stage);
+    default: return nan("");
+  }
+}
+
+// RatingCurve.dQ_dz (rating_curve.py:132-147); Roseires: central difference, dY = 1e-3 (quirk 10)
+__device__ __forceinline__ double rating_dq(const DevRating& r, double stage) {
+  switch (r.type) {
+    case PR_RC_POLY2: return r.a * 2.0 * (stage + r.shift) + r.b;
+    case PR_RC_POWER: return r.a * r.b * pow(stage + r.shift, r.b - 1.0);
+    case PR_RC_POLYNOMIAL: return horner(r.dcoef, r.n_coef - 1, r.off + r.scl * (stage + r.shift));
+    case PR_RC_ROSEIRES: return (roseires_q(r, stage + r.dY) - roseires_q(r, stage - r.dY)) * r.inv_2dY;
+    default: return nan("");
+  }
+}
+
+// ---- boundary rows (Boundary.condition_residual / df_dh / df_dQ, boundary.py:56-242) --------------------
+
+struct BcRow {
+  double res, dh, dq;
+  double stage_rec;   // storage: reservoir stage recorded by this evaluation (boundary.py:126-131)
+};
+
+// level = time // dt; hyd = series sample at this level; q_prev = stored Q of the previous level at the node;
+// stage_prev = reservoir stage recorded for level-1.
+__device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int level, const double hyd, const double h,
+                                         const double Q, const double q_prev, const double stage_prev,
+                                         const double dt, const NodeVals& nv) {
+  BcRow o;
+  o.stage_rec = 0.0;
+  switch (bc.type) {
+    case PR_BC_FLOW_HYDROGRAPH:
+      o.res = Q - hyd; o.dh = 0.0; o.dq = 1.0;
+      break;
+    case PR_BC_STAGE_HYDROGRAPH:
+      o.res = h - (hyd - bc.bed_level); o.dh = 1.0; o.dq = 0.0;
+      break;
+    case PR_BC_FIXED_DEPTH:
+      o.res = h - bc.fixed_depth; o.dh = 1.0; o.dq = 0.0;
+      break;
+    case PR_BC_NORMAL_DEPTH:
+      // hydraulics.normal_flow / dQn_dA (hydraulics.py:4-13, 206-215); host checks bed_level == z_min
+      o.res = Q - nv.K * bc.slope_factor;
+      o.dh = 0.0 - nv.dKA * bc.slope_factor * nv.T;
+      o.dq = 1.0;
+      break;
+    case PR_BC_RATING_CURVE: {
+      const double stage = bc.bed_level + h;
+      o.res = Q - rating_q(bc.rc, stage);
+      o.dh = 0.0 - rating_dq(bc.rc, stage);
+      o.dq = 1.0;
+      break;
+    }
+    case PR_BC_FIXED_DEPTH_STORAGE: {
+      // LumpedStorage.mass_balance with constant area: the brentq root of
+      // (Y - Y_old)*A_s - vol_in is Y_old + vol_in/A_s, clamped at min_stage (lumped_storage.py:24-45)
+      const double vol_in = 0.5 * (q_prev + Q) * dt;                       // preissmann.py:314
+      const double y_old = (level == 1) ? h + bc.bed_level : stage_prev;    // quirk 9
+      double y_new = y_old + vol_in * bc.st_inv_area;
+      double dy_dvol = bc.st_inv_area;
+      if (y_new < bc.st_min_stage) y_new = bc.st_min_stage;
+      if (y_new <= bc.st_min_stage) dy_dvol = 0.0;
+      o.stage_rec = y_new;
+      o.res = h - (y_new - bc.bed_level);
+      o.dh = 1.0;
+      o.dq = 0.0 - dy_dvol * (0.5 * dt);
+      break;
+    }
+    default:
+      o.res = nan(""); o.dh = 1.0; o.dq = 0.0;
+  }
+  return o;
+}
+
+}  // namespace pr

@@ -1,0 +1,408 @@
+// pr_ensemble_kernel.cuh - the fused Preissmann ensemble kernel (short / medium reaches, N <= 249).
+//
+// One ensemble member is advanced through ALL time levels by a group of G lanes of one warp
+// (G = 32: one member per warp).  Lane l owns M consecutive nodes (slots) and the M cells to their
+// right, everything in registers / shared memory:
+//
+//   per Newton iteration (preissmann.py:122-156)
+//     node pass      each lane evaluates its M nodes (area, top width, conveyance, slopes, derivatives)
+//     cell pass      continuity + momentum residuals and their 8 Jacobian entries per cell
+//                    (preissmann.py:220-301, 407-733); ||R||^2 accumulated on the fly
+//     local solve    the lane condenses its M cells into ONE cell between its first node and the next
+//                    lane's first node by 2x2 Schur complements (block elimination of interior nodes)
+//     chain solve    the G condensed cells + both boundary rows form a 2x2-block tridiagonal system of
+//                    <= G block rows, one per lane: parallel cyclic reduction over warp shuffles
+//                    (log2 G steps; off-diagonal blocks are rank-1 and stay rank-1)
+//     back-subst.    interior nodes recovered locally; x += delta; convergence vote = warp-uniform flag
+//
+// This replaces scipy's SuperLU call (preissmann.py:146): pairing the rows as (U,C0),(M0,C1),...,(M_{N-2},D)
+// gives non-singular diagonal blocks (hard part 5).
+//
+// Level-k quantities enter the residuals only through four per-cell constants (cC, cM, cA, cS); they
+// are refreshed at convergence from partial sums the cell pass has anyway, and live in a shared-memory
+// ping-pong so that an iteration that turns out to be the converged one costs no re-evaluation.
+#pragma once
+#include "pr_device.cuh"
+
+namespace pr {
+
+constexpr int kWarpsPerCta = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+// A (possibly condensed) cell between nodes a (left) and b (right):
+//   C: c1 dh_a + c2 dQ_a + c3 dh_b + c4 dQ_b = rc        M: m1 dh_a + m2 dQ_a + m3 dh_b + m4 dQ_b = rm
+struct Cell {
+  double c1, c2, c3, c4, rc;
+  double m1, m2, m3, m4, rm;
+};
+
+// Back-substitution record of an eliminated node b between a and c:
+//   x_b = Dinv * ( [rm - m1 dh_a - m2 dQ_a ; rc - c3 dh_c - c4 dQ_c] )
+struct Elim {
+  double i11, i12, i21, i22;
+  double m1, m2, rm;
+  double c3, c4, rc;
+};
+
+// Schur-complement merge of S (a..b) and E (b..c) eliminating node b; pivot rows are S.M and E.C.
+__device__ __forceinline__ void merge_cells(Cell& S, const Cell& E, Elim& el) {
+  const double det = S.m3 * E.c2 - S.m4 * E.c1;
+  const double idet = 1.0 / det;
+  const double i11 = E.c2 * idet, i12 = -S.m4 * idet, i21 = -E.c1 * idet, i22 = S.m3 * idet;
+  el.i11 = i11; el.i12 = i12; el.i21 = i21; el.i22 = i22;
+  el.m1 = S.m1; el.m2 = S.m2; el.rm = S.rm;
+  el.c3 = E.c3; el.c4 = E.c4; el.rc = E.rc;
+  // w = [S.c3 S.c4] * Dinv ; v = [E.m1 E.m2] * Dinv
+  const double w1 = S.c3 * i11 + S.c4 * i21, w2 = S.c3 * i12 + S.c4 * i22;
+  const double v1 = E.m1 * i11 + E.m2 * i21, v2 = E.m1 * i12 + E.m2 * i22;
+  Cell n;
+  n.c1 = S.c1 - w1 * S.m1;  n.c2 = S.c2 - w1 * S.m2;
+  n.c3 = -w2 * E.c3;        n.c4 = -w2 * E.c4;
+  n.rc = S.rc - w1 * S.rm - w2 * E.rc;
+  n.m1 = -v1 * S.m1;        n.m2 = -v1 * S.m2;
+  n.m3 = E.m3 - v2 * E.c3;  n.m4 = E.m4 - v2 * E.c4;
+  n.rm = E.rm - v1 * S.rm - v2 * E.rc;
+  S = n;
+}
+
+// Residuals + Jacobian of one Preissmann cell (left node a, right node b) and the candidate level
+// constants.  pc = {cC, cM, cA, cS} of the stored level; returns R_C^2 + R_M^2.
+struct SchemeConst {
+  double i2dt, th_dx, hth, omt_dx, homt, g;
+};
+
+__device__ __forceinline__ double cell_assemble(const NodeVals& a, const NodeVals& b, const SchemeConst& k,
+                                                const double cC, const double cM, const double cA, const double cS,
+                                                Cell& e, double& nC, double& nM, double& nA, double& nS) {
+  const double sA = b.A + a.A, dQ = b.Q - a.Q, sQ = b.Q + a.Q, dF = b.F - a.F, dY = b.Y - a.Y, sSe = b.Se + a.Se;
+  // continuity_residual (preissmann.py:220-249): time_diff(A) + spatial_diff(Q)
+  const double RC = sA * k.i2dt + k.th_dx * dQ + cC;
+  // momentum_residual (preissmann.py:251-301)
+  const double avgA = k.hth * sA + cA;                       // cell_avg(A)
+  const double slope = k.th_dx * dY + k.hth * sSe + cS;      // spatial_diff(z+h) + cell_avg(Se)
+  const double RM = sQ * k.i2dt + k.th_dx * dF + cM + k.g * avgA * slope;
+  // level-(k) parts for the NEXT level, should this iterate be accepted
+  nC = -sA * k.i2dt + k.omt_dx * dQ;
+  nM = -sQ * k.i2dt + k.omt_dx * dF;
+  nA = k.homt * sA;
+  nS = k.omt_dx * dY + k.homt * sSe;
+  // dC_* (preissmann.py:407-494)
+  e.c1 = a.T * k.i2dt;  e.c2 = -k.th_dx;  e.c3 = b.T * k.i2dt;  e.c4 = k.th_dx;
+  e.rc = -RC;
+  // dM_dh_i / dM_dQ_i / dM_dh_ip1 / dM_dQ_ip1 (preissmann.py:496-733); s = -/+ theta/dx
+  const double ga = k.g * avgA, gs = k.g * k.hth * slope;
+  e.m1 = (k.th_dx * a.QA * a.QA) * a.T + ga * (-k.th_dx + k.hth * a.dSeA * a.T) + gs * a.T;
+  e.m2 = k.i2dt - k.th_dx * 2.0 * a.QA + ga * k.hth * a.dSeQ;
+  e.m3 = (-k.th_dx * b.QA * b.QA) * b.T + ga * (k.th_dx + k.hth * b.dSeA * b.T) + gs * b.T;
+  e.m4 = k.i2dt + k.th_dx * 2.0 * b.QA + ga * k.hth * b.dSeQ;
+  e.rm = -RM;
+  return RC * RC + RM * RM;
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int s = G / 2; s > 0; s >>= 1) v += __shfl_xor_sync(kFull, v, s, G);
+  return v;
+}
+
+// Shared memory: [geometry F_COUNT x NP doubles][per warp: 2 x 4 x M x 32 doubles]
+template <int G, int M>
+__host__ __device__ constexpr size_t ensemble_smem_bytes() {
+  return sizeof(double) * ((size_t)F_COUNT * G * M + (size_t)kWarpsPerCta * 2 * 4 * M * 32);
+}
+
+template <int G, int M, bool CURV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+pr_ensemble_kernel(const __grid_constant__ DevParams p) {
+  extern __shared__ double smem[];
+  constexpr int NP = G * M;           // padded node slots per member
+  constexpr int MPW = 32 / G;         // members per warp
+  double* sg = smem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* pcw = smem + (size_t)F_COUNT * NP + (size_t)warp * (2 * 4 * M * 32);   // level constants of this warp
+  stage_geometry(p.geo, p.N, NP, sg, threadIdx.x, blockDim.x);
+  __syncthreads();
+
+  const int gl = lane % G;            // lane within the member's group
+  const int N = p.N, L = p.L;
+  long long member = ((long long)blockIdx.x * kWarpsPerCta + warp) * MPW + lane / G;
+  const bool member_valid = member < p.M;
+  if (!member_valid) member = p.M - 1;
+
+  // chain topology (uniform): lanes 0..Lc hold one block row each
+  const int ncells_total = N - 1;
+  const int Lc = (ncells_total + M - 1) / M;           // lanes that own at least one cell
+  const int my_first = gl * M;                         // first node slot owned by this lane
+  int nc = ncells_total - my_first;                    // cells owned by this lane
+  nc = nc < 0 ? 0 : (nc > M ? M : nc);
+  const int owner_last = (N - 1) / M, slot_last = (N - 1) % M;   // where node N-1 lives
+  const bool is_first = (gl == 0);
+  const bool owns_last = (gl == owner_last);
+
+  SchemeConst k;
+  k.i2dt = 1.0 / (2.0 * p.dt);
+  k.th_dx = p.theta / p.dx;
+  k.hth = 0.5 * p.theta;
+  k.omt_dx = (1.0 - p.theta) / p.dx;
+  k.homt = 0.5 * (1.0 - p.theta);
+  k.g = p.g;
+
+  Rough rg;
+  rg.has_nm = p.geo.member_nm != nullptr;
+  rg.has_nfp = p.geo.member_nfp != nullptr;
+  rg.nm = rg.has_nm ? p.geo.member_nm[member] : 0.0;
+  rg.cnm = rg.has_nm ? inv_n15(rg.nm) : 0.0;
+  rg.cnfp = rg.has_nfp ? inv_n15(p.geo.member_nfp[member]) : 0.0;
+
+  // ---- state: initial conditions (Solver.initialize_t0, solver.py:61-63) ----
+  double h[M], q[M];
+  {
+    const double* ih = p.ic_h + member * p.ic_stride;
+    const double* iq = p.ic_q + member * p.ic_stride;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const int nd = my_first + j < N ? my_first + j : N - 1;
+      h[j] = ih[nd];
+      q[j] = iq[nd];
+    }
+  }
+  const size_t out_row = (p.out_mode == PR_OUT_FULL) ? (size_t)N : 1;
+  auto store_level = [&](int level, bool nanfill) {
+    if (!member_valid) return;
+    const size_t base = ((size_t)member * L + level) * out_row;
+    if (p.out_mode == PR_OUT_FULL) {
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        const int nd = my_first + j;
+        if (nd < N) {
+          if (p.out_h) p.out_h[base + nd] = nanfill ? nan("") : h[j];
+          if (p.out_q) p.out_q[base + nd] = nanfill ? nan("") : q[j];
+        }
+      }
+    } else if (is_first) {
+      if (p.out_h) p.out_h[base] = nanfill ? nan("") : h[0];
+      if (p.out_q) p.out_q[base] = nanfill ? nan("") : q[0];
+    }
+  };
+  store_level(0, false);
+
+  // boundary bookkeeping held by the lane that owns node N-1
+  double q_prev_last = q[slot_last];                                   // flow_at(k=-1, i=-1)
+  double stage_prev = sg[F_Z * NP + (N - 1)] + h[slot_last];           // solver.py:101-108
+  if (member_valid && owns_last && p.storage_stage) p.storage_stage[(size_t)member * L] = stage_prev;
+
+  int level = 1, it = 0;
+  bool active = member_valid && L > 1;
+  int status = PR_STATUS_OK, fail_level = 0;
+  int buf = 0;          // which half of the ping-pong holds the stored level's constants
+  bool init_pass = true;   // first trip: only builds the level-0 constants from the initial state
+  double hyd_up = 0.0, hyd_dn = 0.0;
+
+#define PC(b, c, j) pcw[(((b)*4 + (c)) * M + (j)) * 32 + lane]
+
+  while (__any_sync(kFull, active) || init_pass) {
+    if (!init_pass && it == 0) {
+      // hydrograph samples at t = level*dt (preissmann.py:215,313)
+      if (p.up.series) hyd_up = p.up.series[member * p.up.series_stride + (level < L ? level : L - 1)];
+      if (p.dn.series) hyd_dn = p.dn.series[member * p.dn.series_stride + (level < L ? level : L - 1)];
+    }
+    if (active && !init_pass) it += 1;
+
+    // ------------------------------ node + cell pass ------------------------------
+    NodeVals left, right, first;
+    node_eval<CURV>(sg, NP, my_first, h[0], q[0], rg, k.g, first);
+    // the next lane's first node closes this lane's last cell
+    NodeVals nxt;
+    nxt.Q = __shfl_down_sync(kFull, first.Q, 1, G);
+    nxt.A = __shfl_down_sync(kFull, first.A, 1, G);
+    nxt.T = __shfl_down_sync(kFull, first.T, 1, G);
+    nxt.Y = __shfl_down_sync(kFull, first.Y, 1, G);
+    nxt.Se = __shfl_down_sync(kFull, first.Se, 1, G);
+    nxt.F = __shfl_down_sync(kFull, first.F, 1, G);
+    nxt.QA = __shfl_down_sync(kFull, first.QA, 1, G);
+    nxt.dSeA = __shfl_down_sync(kFull, first.dSeA, 1, G);
+    nxt.dSeQ = __shfl_down_sync(kFull, first.dSeQ, 1, G);
+    nxt.K = 0.0; nxt.dKA = 0.0;
+
+    double ss = 0.0;
+    Cell S;                     // condensed cell of this lane
+    Elim el[M > 1 ? M - 1 : 1];
+    NodeVals lastnode = first;  // values at node N-1 when this lane owns it
+    left = first;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      if (j + 1 < M) {
+        node_eval<CURV>(sg, NP, my_first + j + 1, h[j + 1], q[j + 1], rg, k.g, right);
+        if (j + 1 == slot_last) lastnode = right;
+      } else {
+        right = nxt;
+      }
+      if (j < nc) {
+        Cell e;
+        double nC, nM, nA, nS;
+        const double r2 = cell_assemble(left, right, k, PC(buf, 0, j), PC(buf, 1, j), PC(buf, 2, j), PC(buf, 3, j), e,
+                                        nC, nM, nA, nS);
+        PC(buf ^ 1, 0, j) = nC; PC(buf ^ 1, 1, j) = nM; PC(buf ^ 1, 2, j) = nA; PC(buf ^ 1, 3, j) = nS;
+        ss += r2;
+        if (j == 0) S = e;
+        else merge_cells(S, e, el[j - 1]);
+      }
+      left = right;
+    }
+    __syncwarp();
+
+    if (init_pass) {   // level-0 constants are now in buf^1
+      buf ^= 1;
+      init_pass = false;
+      continue;
+    }
+
+    // ------------------------------ boundary rows ------------------------------
+    BcRow U, D;
+    U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0;
+    D = U;
+    if (is_first) U = bc_eval(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, first);
+    if (owns_last) {
+      double hl = h[0], ql = q[0];
+#pragma unroll
+      for (int j = 1; j < M; ++j)
+        if (j == slot_last) { hl = h[j]; ql = q[j]; }
+      D = bc_eval(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, lastnode);
+    }
+    if (is_first) ss += U.res * U.res;
+    if (owns_last) ss += D.res * D.res;
+    const double err = sqrt(group_sum<G>(ss));                  // utility.euclidean_norm (utility.py:20-22)
+
+    // ------------------------------ chain rows ------------------------------
+    // row a (top): lane 0 -> U ; lane 1..Lc -> M~ of the previous lane's condensed cell
+    // row b (bottom): lane < Lc -> own C~ ; lane Lc -> D ; beyond -> identity
+    double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
+    {
+      const double pm1 = __shfl_up_sync(kFull, S.m1, 1, G), pm2 = __shfl_up_sync(kFull, S.m2, 1, G);
+      const double pm3 = __shfl_up_sync(kFull, S.m3, 1, G), pm4 = __shfl_up_sync(kFull, S.m4, 1, G);
+      const double prm = __shfl_up_sync(kFull, S.rm, 1, G);
+      // D row travels one lane up when node N-1 is interior to lane Lc-1
+      const double Dh = (owner_last == Lc) ? D.dh : __shfl_up_sync(kFull, D.dh, 1, G);
+      const double Dq = (owner_last == Lc) ? D.dq : __shfl_up_sync(kFull, D.dq, 1, G);
+      const double Dr = (owner_last == Lc) ? D.res : __shfl_up_sync(kFull, D.res, 1, G);
+      if (gl == 0) { l1 = 0.0; l2 = 0.0; d11 = U.dh; d12 = U.dq; ra = -U.res; }
+      else if (gl <= Lc) { l1 = pm1; l2 = pm2; d11 = pm3; d12 = pm4; ra = prm; }
+      else { l1 = 0.0; l2 = 0.0; d11 = 1.0; d12 = 0.0; ra = 0.0; }
+      if (gl < Lc) { d21 = S.c1; d22 = S.c2; u1 = S.c3; u2 = S.c4; rb = S.rc; }
+      else if (gl == Lc) { d21 = Dh; d22 = Dq; u1 = 0.0; u2 = 0.0; rb = -Dr; }
+      else { d21 = 0.0; d22 = 1.0; u1 = 0.0; u2 = 0.0; rb = 0.0; }
+    }
+    // ------------------------------ parallel cyclic reduction ------------------------------
+#pragma unroll
+    for (int s = 1; s < G; s <<= 1) {
+      if (s > Lc) break;      // uniform: the chain has Lc+1 rows
+      const double idet = 1.0 / (d11 * d22 - d12 * d21);
+      const double i11 = d22 * idet, i12 = -d12 * idet, i21 = -d21 * idet, i22 = d11 * idet;
+      const int up_src = gl - s, dn_src = gl + s;
+      // rows of lane gl-s
+      const double P_i11 = __shfl_sync(kFull, i11, up_src, G), P_i12 = __shfl_sync(kFull, i12, up_src, G);
+      const double P_i21 = __shfl_sync(kFull, i21, up_src, G), P_i22 = __shfl_sync(kFull, i22, up_src, G);
+      const double P_l1 = __shfl_sync(kFull, l1, up_src, G), P_l2 = __shfl_sync(kFull, l2, up_src, G);
+      const double P_u1 = __shfl_sync(kFull, u1, up_src, G), P_u2 = __shfl_sync(kFull, u2, up_src, G);
+      const double P_ra = __shfl_sync(kFull, ra, up_src, G), P_rb = __shfl_sync(kFull, rb, up_src, G);
+      // rows of lane gl+s
+      const double N_i11 = __shfl_sync(kFull, i11, dn_src, G), N_i12 = __shfl_sync(kFull, i12, dn_src, G);
+      const double N_i21 = __shfl_sync(kFull, i21, dn_src, G), N_i22 = __shfl_sync(kFull, i22, dn_src, G);
+      const double N_l1 = __shfl_sync(kFull, l1, dn_src, G), N_l2 = __shfl_sync(kFull, l2, dn_src, G);
+      const double N_u1 = __shfl_sync(kFull, u1, dn_src, G), N_u2 = __shfl_sync(kFull, u2, dn_src, G);
+      const double N_ra = __shfl_sync(kFull, ra, dn_src, G), N_rb = __shfl_sync(kFull, rb, dn_src, G);
+      double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+      if (up_src >= 0) { a1 = l1 * P_i11 + l2 * P_i21; a2 = l1 * P_i12 + l2 * P_i22; }   // [l1 l2] * Dinv(P)
+      if (dn_src < G) { b1 = u1 * N_i11 + u2 * N_i21; b2 = u1 * N_i12 + u2 * N_i22; }    // [u1 u2] * Dinv(N)
+      // row a -= a1*rowa(P) + a2*rowb(P) ; row b -= b1*rowa(N) + b2*rowb(N)
+      l1 = -a1 * P_l1;  l2 = -a1 * P_l2;
+      d11 -= a2 * P_u1; d12 -= a2 * P_u2;
+      ra -= a1 * P_ra + a2 * P_rb;
+      u1 = -b2 * N_u1;  u2 = -b2 * N_u2;
+      d21 -= b1 * N_l1; d22 -= b1 * N_l2;
+      rb -= b1 * N_ra + b2 * N_rb;
+    }
+    double dh0, dq0;    // update of this lane's chain node
+    {
+      const double idet = 1.0 / (d11 * d22 - d12 * d21);
+      dh0 = (d22 * ra - d12 * rb) * idet;
+      dq0 = (d11 * rb - d21 * ra) * idet;
+    }
+    // ------------------------------ back-substitution ------------------------------
+    const double dhR = __shfl_down_sync(kFull, dh0, 1, G), dqR = __shfl_down_sync(kFull, dq0, 1, G);
+    double dh[M], dq[M];
+    dh[0] = dh0; dq[0] = dq0;
+    {
+      double rh = dhR, rq = dqR;       // right end of the span being unwound
+#pragma unroll
+      for (int j = M - 1; j >= 1; --j) {
+        if (j < nc) {                  // node slot j was eliminated by merge j-1
+          const Elim& e = el[j - 1];
+          const double t1 = e.rm - e.m1 * dh0 - e.m2 * dq0;
+          const double t2 = e.rc - e.c3 * rh - e.c4 * rq;
+          dh[j] = e.i11 * t1 + e.i12 * t2;
+          dq[j] = e.i21 * t1 + e.i22 * t2;
+          rh = dh[j]; rq = dq[j];
+        } else if (j == nc && nc > 0) {  // right end node of a short last lane: it is the chain's last node
+          dh[j] = dhR; dq[j] = dqR;
+        } else {
+          dh[j] = 0.0; dq[j] = 0.0;
+        }
+      }
+    }
+
+    // ------------------------------ accept / update (preissmann.py:146-156) ------------------------------
+    const bool converged = err < p.tol;
+    if (active) {
+      if (converged) {
+        store_level(level, false);                     // stored level = iterate BEFORE the update
+        if (is_first) {
+          if (p.iters) p.iters[(size_t)member * (L - 1) + (level - 1)] = it;
+          if (p.final_error) p.final_error[(size_t)member * (L - 1) + (level - 1)] = err;
+        }
+        if (owns_last) {
+          double ql = q[0];
+#pragma unroll
+          for (int j = 1; j < M; ++j)
+            if (j == slot_last) ql = q[j];
+          q_prev_last = ql;
+          if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE) {
+            stage_prev = D.stage_rec;
+            if (p.storage_stage) p.storage_stage[(size_t)member * L + level] = D.stage_rec;
+          }
+        }
+        buf ^= 1;
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) { h[j] += dh[j]; q[j] += dq[j]; }     // unknowns += delta
+      if (converged) {
+        level += 1; it = 0;
+        if (level >= L) active = false;
+      } else if (it >= p.max_iter) {
+        status = (err == err) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
+        fail_level = level;
+        if (is_first) {
+          if (p.iters) p.iters[(size_t)member * (L - 1) + (level - 1)] = it;
+          if (p.final_error) p.final_error[(size_t)member * (L - 1) + (level - 1)] = err;
+        }
+        for (int kk = level; kk < L; ++kk) {
+          store_level(kk, true);
+          if (kk > level && is_first) {
+            if (p.iters) p.iters[(size_t)member * (L - 1) + (kk - 1)] = 0;
+            if (p.final_error) p.final_error[(size_t)member * (L - 1) + (kk - 1)] = nan("");
+          }
+          if (owns_last && p.storage_stage) p.storage_stage[(size_t)member * L + kk] = nan("");
+        }
+        active = false;
+      }
+    }
+  }
+#undef PC
+  if (member_valid && is_first) {
+    if (p.status) p.status[member] = status;
+    if (p.fail_level) p.fail_level[member] = fail_level;
+  }
+}
+
+}  // namespace pr

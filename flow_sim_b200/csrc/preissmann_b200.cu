@@ -1,0 +1,399 @@
+// preissmann_b200.cu - C ABI (include/preissmann_b200.h) over the sm_100a kernels.
+//
+// Host side only: argument validation, staging of PR_MEM_HOST arrays through the device, collapsing the
+// Roseires gate tables to two quadratics, choosing the lanes-per-member / nodes-per-lane instantiation,
+// and launching.  No CPU implementation of the scheme lives here: if CUDA is unavailable every entry
+// point fails with PR_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pr_aux_kernels.cuh"
+#include "pr_ensemble_kernel.cuh"
+#include "pr_long_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) return fail(PR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+// Owns the device copies of one PR_MEM_HOST call.
+struct Stage {
+  bool host;
+  cudaStream_t stream;
+  std::vector<void*> allocs;
+  struct Back { void* host; void* dev; size_t bytes; };
+  std::vector<Back> backs;
+  cudaError_t err = cudaSuccess;
+
+  Stage(bool host_mem, cudaStream_t s) : host(host_mem), stream(s) {}
+  ~Stage() {
+    for (void* p : allocs) cudaFree(p);
+  }
+  template <class T>
+  const T* in(const T* p, size_t n) {
+    if (!p || !host) return p;
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, n * sizeof(T));
+    if (err != cudaSuccess) return nullptr;
+    allocs.push_back(d);
+    err = cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, stream);
+    return static_cast<const T*>(d);
+  }
+  template <class T>
+  T* out(T* p, size_t n) {
+    if (!p || !host) return p;
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, n * sizeof(T));
+    if (err != cudaSuccess) return nullptr;
+    allocs.push_back(d);
+    backs.push_back({p, d, n * sizeof(T)});
+    return static_cast<T*>(d);
+  }
+  cudaError_t finish() {
+    if (err != cudaSuccess) return err;
+    for (auto& b : backs) {
+      err = cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, stream);
+      if (err != cudaSuccess) return err;
+    }
+    if (host) err = cudaStreamSynchronize(stream);
+    return err;
+  }
+};
+
+// copy n doubles that live in `mem` space to the host
+int fetch(const double* p, size_t n, int mem, std::vector<double>& out) {
+  out.resize(n);
+  if (mem == PR_MEM_HOST) {
+    std::memcpy(out.data(), p, n * sizeof(double));
+    return PR_OK;
+  }
+  CUDA_TRY(cudaMemcpy(out.data(), p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return PR_OK;
+}
+
+// Roseires: Q_state(s) = sum_{o_j>0} spill(s,o_j) + n_sl*sluice(s,twl) + q_hydro, as a quadratic in u = s - stage0
+void collapse_roseires(const pr_rating& r, const double* openings, int sluices, double out[3]) {
+  long double k0 = r.q_hydro, k1 = 0, k2 = 0;
+  const long double s0 = r.stage0;
+  auto add = [&](const double c[6], long double o, long double w) {
+    // c0 + c1 s + c2 o + c3 s^2 + c4 s o + c5 o^2 with s = s0 + u
+    const long double a0 = c[0] + c[2] * o + c[5] * o * o, a1 = c[1] + c[4] * o, a2 = c[3];
+    k0 += w * (a0 + a1 * s0 + a2 * s0 * s0);
+    k1 += w * (a1 + 2 * a2 * s0);
+    k2 += w * a2;
+  };
+  for (int j = 0; j < r.n_gates; ++j)
+    if (openings[j] > 0) add(r.spill, openings[j], 1.0L);
+  add(r.sluice, r.twl, (long double)sluices);
+  out[0] = (double)k0; out[1] = (double)k1; out[2] = (double)k2;
+}
+
+int make_rating(const pr_rating& r, pr::DevRating& d) {
+  std::memset(&d, 0, sizeof d);
+  d.type = r.type;
+  d.n_coef = r.n_coef;
+  d.a = r.a; d.b = r.b; d.c = r.c; d.shift = r.stage_shift;
+  d.off = r.off; d.scl = r.scl;
+  if (r.type == PR_RC_POLYNOMIAL) {
+    if (r.n_coef < 1 || r.n_coef > PR_MAX_POLY) return fail(PR_ERR_ARG, "rating: n_coef=%d out of range", r.n_coef);
+    for (int i = 0; i < r.n_coef; ++i) { d.coef[i] = r.coef[i]; d.dcoef[i] = r.dcoef[i]; }
+  }
+  if (r.type == PR_RC_ROSEIRES) {
+    if (r.n_gates < 0 || r.n_gates > PR_MAX_GATES) return fail(PR_ERR_ARG, "rating: n_gates=%d out of range", r.n_gates);
+    if (!(r.buffer > 0) || !(r.dY > 0)) return fail(PR_ERR_ARG, "rating: Roseires buffer and dY must be positive");
+    collapse_roseires(r, r.closed_state, r.sluices_closed, d.lo);
+    collapse_roseires(r, r.open_state, r.sluices_open, d.hi);
+    d.stage0 = r.stage0; d.buffer = r.buffer; d.inv_buffer = 1.0 / r.buffer;
+    d.dY = r.dY; d.inv_2dY = 1.0 / (2 * r.dY);
+  }
+  if (r.type < PR_RC_NONE || r.type > PR_RC_ROSEIRES) return fail(PR_ERR_ARG, "rating: unknown type %d", r.type);
+  return PR_OK;
+}
+
+int make_bc(const pr_bc& b, const char* which, bool downstream, const pr_config& cfg, double z_node, Stage& st,
+            pr::DevBC& d) {
+  std::memset(&d, 0, sizeof d);
+  d.type = b.type;
+  d.bed_level = b.bed_level;
+  d.fixed_depth = b.fixed_depth;
+  switch (b.type) {
+    case PR_BC_FLOW_HYDROGRAPH:
+    case PR_BC_STAGE_HYDROGRAPH: {
+      if (!b.series) return fail(PR_ERR_ARG, "%s boundary: hydrograph series is NULL", which);
+      if (b.series_member_stride != 0 && b.series_member_stride < cfg.n_levels)
+        return fail(PR_ERR_ARG, "%s boundary: series_member_stride < n_levels", which);
+      const size_t n = b.series_member_stride ? (size_t)b.series_member_stride * cfg.n_members : (size_t)cfg.n_levels;
+      d.series = st.in(b.series, n);
+      d.series_stride = b.series_member_stride;
+      break;
+    }
+    case PR_BC_FIXED_DEPTH:
+      break;
+    case PR_BC_NORMAL_DEPTH:
+      if (!(b.bed_slope == b.bed_slope)) return fail(PR_ERR_ARG, "%s boundary: normal_depth needs bed_slope", which);
+      if (b.bed_level != z_node)
+        return fail(PR_ERR_UNSUPPORTED, "%s boundary: normal_depth with bed_level (%g) != cross-section z_min (%g)",
+                    which, b.bed_level, z_node);
+      d.slope_factor = (b.bed_slope < 0 ? -1.0 : 1.0) * std::sqrt(std::fabs(b.bed_slope));
+      break;
+    case PR_BC_RATING_CURVE:
+      if (b.rating.type == PR_RC_NONE) return fail(PR_ERR_ARG, "%s boundary: rating_curve without a curve", which);
+      if (int rc = make_rating(b.rating, d.rc)) return rc;
+      break;
+    case PR_BC_FIXED_DEPTH_STORAGE:
+      if (!downstream) return fail(PR_ERR_UNSUPPORTED, "lumped storage at the upstream boundary");
+      if (!(b.storage_area > 0)) return fail(PR_ERR_ARG, "storage: surface area must be positive");
+      d.st_area = b.storage_area;
+      d.st_inv_area = 1.0 / b.storage_area;
+      d.st_min_stage = b.storage_min_stage;
+      break;
+    default:
+      return fail(PR_ERR_ARG, "%s boundary: unknown type %d", which, b.type);
+  }
+  return PR_OK;
+}
+
+int check_config(const pr_config* cfg) {
+  if (!cfg) return fail(PR_ERR_ARG, "cfg is NULL");
+  if (cfg->abi_version != PR_ABI_VERSION)
+    return fail(PR_ERR_ARG, "abi_version %d != library %d", cfg->abi_version, PR_ABI_VERSION);
+  if (cfg->n_nodes < 2) return fail(PR_ERR_ARG, "n_nodes must be >= 2");
+  if (cfg->n_levels < 1) return fail(PR_ERR_ARG, "n_levels must be >= 1");
+  if (cfg->n_members < 1) return fail(PR_ERR_ARG, "n_members must be >= 1");
+  if (cfg->mem != PR_MEM_HOST && cfg->mem != PR_MEM_DEVICE) return fail(PR_ERR_ARG, "mem must be HOST or DEVICE");
+  if (!(cfg->dt > 0) || !(cfg->dx > 0)) return fail(PR_ERR_ARG, "dt and dx must be positive");
+  if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
+  return PR_OK;
+}
+
+int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d) {
+  if (!g) return fail(PR_ERR_ARG, "geom is NULL");
+  const void* req[] = {g->kind, g->z_bed, g->b_main, g->m_main, g->h_bank, g->T_bank, g->W_bank,
+                       g->b_fp_l, g->b_fp_r, g->m_fp, g->n_l, g->n_m, g->n_r, g->curvature};
+  for (const void* p : req)
+    if (!p) return fail(PR_ERR_ARG, "geom: a per-node array is NULL");
+  const size_t N = cfg.n_nodes, M = cfg.n_members;
+  d.kind = st.in(g->kind, N);
+  d.z = st.in(g->z_bed, N); d.b = st.in(g->b_main, N); d.m = st.in(g->m_main, N);
+  d.hb = st.in(g->h_bank, N); d.Tb = st.in(g->T_bank, N); d.Wb = st.in(g->W_bank, N);
+  d.bl = st.in(g->b_fp_l, N); d.br = st.in(g->b_fp_r, N); d.mfp = st.in(g->m_fp, N);
+  d.nl = st.in(g->n_l, N); d.nm = st.in(g->n_m, N); d.nr = st.in(g->n_r, N);
+  d.curv = st.in(g->curvature, N);
+  d.member_nm = st.in(g->member_n_main, M);
+  d.member_nfp = st.in(g->member_n_fp, M);
+  return PR_OK;
+}
+
+template <int G, int M, bool CURV>
+int launch_ensemble(const pr::DevParams& p, cudaStream_t s) {
+  constexpr size_t smem = pr::ensemble_smem_bytes<G, M>();
+  auto kern = pr::pr_ensemble_kernel<G, M, CURV>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_cta = pr::kWarpsPerCta * (32 / G);
+  const unsigned grid = (unsigned)((p.M + per_cta - 1) / per_cta);
+  kern<<<grid, pr::kWarpsPerCta * 32, smem, s>>>(p);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PR_OK;
+}
+
+template <int G, int M>
+int launch_ensemble_c(const pr::DevParams& p, bool curv, cudaStream_t s) {
+  return curv ? launch_ensemble<G, M, true>(p, s) : launch_ensemble<G, M, false>(p, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pr_abi_version(void) { return PR_ABI_VERSION; }
+
+const char* pr_last_error(void) { return g_err.c_str(); }
+
+int64_t pr_launch_count(void) { return g_launches.load(); }
+
+int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upstream, const pr_bc* downstream,
+                    const pr_state* initial, const pr_outputs* out, void* cuda_stream) {
+  if (int rc = check_config(cfg)) return rc;
+  if (!upstream || !downstream || !initial || !out) return fail(PR_ERR_ARG, "a struct pointer is NULL");
+  if (!initial->depth || !initial->flow) return fail(PR_ERR_ARG, "initial conditions are NULL");
+  if (initial->member_stride != 0 && initial->member_stride < cfg->n_nodes)
+    return fail(PR_ERR_ARG, "initial.member_stride < n_nodes");
+  if (cfg->out_mode != PR_OUT_FULL && cfg->out_mode != PR_OUT_UPSTREAM) return fail(PR_ERR_ARG, "bad out_mode");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t N = cfg->n_nodes, L = cfg->n_levels, M = cfg->n_members;
+  Stage st(cfg->mem == PR_MEM_HOST, s);
+
+  pr::DevParams p;
+  std::memset(&p, 0, sizeof p);
+  p.N = (int)N; p.L = (int)L; p.M = (int)M; p.max_iter = cfg->max_iter; p.out_mode = cfg->out_mode;
+  p.theta = cfg->theta; p.dt = cfg->dt; p.dx = cfg->dx; p.tol = cfg->tol; p.g = cfg->g;
+
+  // host-side look at the few geometry values the dispatch needs
+  std::vector<double> curv, zb;
+  if (int rc = (geom && geom->curvature && geom->z_bed) ? PR_OK : fail(PR_ERR_ARG, "geom is incomplete")) return rc;
+  if (int rc = fetch(geom->curvature, N, cfg->mem, curv)) return rc;
+  if (int rc = fetch(geom->z_bed, N, cfg->mem, zb)) return rc;
+  bool has_curv = false;
+  for (double c : curv) has_curv |= (c != 0.0);
+
+  if (int rc = stage_geom(*cfg, geom, st, p.geo)) return rc;
+  if (int rc = make_bc(*upstream, "upstream", false, *cfg, zb[0], st, p.up)) return rc;
+  if (int rc = make_bc(*downstream, "downstream", true, *cfg, zb[N - 1], st, p.dn)) return rc;
+
+  const size_t icn = initial->member_stride ? (size_t)initial->member_stride * M : N;
+  p.ic_h = st.in(initial->depth, icn);
+  p.ic_q = st.in(initial->flow, icn);
+  p.ic_stride = initial->member_stride;
+  const size_t on = (cfg->out_mode == PR_OUT_FULL) ? M * L * N : M * L;
+  p.out_h = st.out(out->depth, on);
+  p.out_q = st.out(out->flow, on);
+  p.iters = st.out(out->iters, M * (L > 1 ? L - 1 : 1));
+  p.status = st.out(out->status, M);
+  p.fail_level = st.out(out->fail_level, M);
+  p.storage_stage = st.out(out->storage_stage, M * L);
+  p.final_error = st.out(out->final_error, M * (L > 1 ? L - 1 : 1));
+  if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
+
+  // nodes per lane: smallest M with ceil((N-1)/M) + 1 <= 32 chain rows
+  const int need = (int)((N - 1 + 30) / 31);      // ceil((N-1)/31)
+  int rc;
+  if (cfg->lanes_per_member != 0 && cfg->lanes_per_member != 32)
+    return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: this build has the 32-lane instantiations", cfg->lanes_per_member);
+  if (need <= 1) rc = launch_ensemble_c<32, 1>(p, has_curv, s);
+  else if (need <= 2) rc = launch_ensemble_c<32, 2>(p, has_curv, s);
+  else if (need <= 4) rc = launch_ensemble_c<32, 4>(p, has_curv, s);
+  else if (need <= 8) rc = launch_ensemble_c<32, 8>(p, has_curv, s);
+  else rc = pr::long_reach_run(p, has_curv, s, g_launches, g_err);
+  if (rc) return rc;
+  cudaError_t e = st.finish();
+  if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_ensemble_run: %s", cudaGetErrorString(e));
+  return PR_OK;
+}
+
+int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const double* q0, int64_t q0_member_stride,
+                              double downstream_depth, double* ic_depth, double* ic_flow, int32_t* status,
+                              void* cuda_stream) {
+  if (int rc = check_config(cfg)) return rc;
+  if (!q0 || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "q0 / ic buffers are NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t N = cfg->n_nodes, M = cfg->n_members;
+  Stage st(cfg->mem == PR_MEM_HOST, s);
+  pr::GvfParams p;
+  std::memset(&p, 0, sizeof p);
+  p.N = (int)N; p.M = (int)M; p.dx = cfg->dx; p.g = cfg->g; p.h_down = downstream_depth;
+  std::vector<double> curv;
+  if (!geom || !geom->curvature) return fail(PR_ERR_ARG, "geom is incomplete");
+  if (int rc = fetch(geom->curvature, N, cfg->mem, curv)) return rc;
+  bool has_curv = false;
+  for (double c : curv) has_curv |= (c != 0.0);
+  if (int rc = stage_geom(*cfg, geom, st, p.geo)) return rc;
+  p.q0 = st.in(q0, q0_member_stride ? M * (size_t)q0_member_stride : 1);
+  p.q0_stride = q0_member_stride;
+  p.ic_h = st.out(ic_depth, M * N);
+  p.ic_q = st.out(ic_flow, M * N);
+  p.status = st.out(status, M);
+  if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
+  const size_t smem = sizeof(double) * pr::F_COUNT * N;
+  if (smem > 200 * 1024) return fail(PR_ERR_UNSUPPORTED, "GVF initial conditions: n_nodes=%zu exceeds the shared-memory geometry stage", N);
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  if (has_curv) {
+    CUDA_TRY(cudaFuncSetAttribute(pr::pr_gvf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pr::pr_gvf_kernel<true><<<grid, 128, smem, s>>>(p);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(pr::pr_gvf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pr::pr_gvf_kernel<false><<<grid, 128, smem, s>>>(p);
+  }
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  cudaError_t e = st.finish();
+  if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_gvf_initial_conditions: %s", cudaGetErrorString(e));
+  return PR_OK;
+}
+
+int pr_rating_objective(const pr_config* cfg, const double* up_flow, const double* up_depth, double z0,
+                        const double* q_query, const double* h_target, int32_t n_query, double* levels_out,
+                        double* rmse_out, void* cuda_stream) {
+  if (int rc = check_config(cfg)) return rc;
+  if (!up_flow || !up_depth || !q_query || !h_target || n_query < 1) return fail(PR_ERR_ARG, "objective: NULL input");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t L = cfg->n_levels, M = cfg->n_members;
+  Stage st(cfg->mem == PR_MEM_HOST, s);
+  pr::ObjParams p;
+  p.L = (int)L; p.M = (int)M; p.nq = n_query; p.z0 = z0;
+  p.up_q = st.in(up_flow, M * L);
+  p.up_h = st.in(up_depth, M * L);
+  p.q_query = st.in(q_query, (size_t)n_query);
+  p.h_target = st.in(h_target, (size_t)n_query);
+  p.levels = st.out(levels_out, M * (size_t)n_query);
+  p.rmse = st.out(rmse_out, M);
+  if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
+  pr::pr_objective_kernel<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(p);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  cudaError_t e = st.finish();
+  if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_rating_objective: %s", cudaGetErrorString(e));
+  return PR_OK;
+}
+
+int pr_fp64_peak(double millis, double* tflops_out) {
+  if (!tflops_out) return fail(PR_ERR_ARG, "tflops_out is NULL");
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* sink = nullptr;
+  CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int grid = sms * 8, block = 256;
+  int iters = 1 << 14;
+  double best = 0.0, spent = 0.0;
+  pr::pr_dfma_kernel<<<grid, block>>>(sink, 1024, 1.0000001, 1e-9);   // warm-up
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaDeviceSynchronize());
+  while (spent < millis) {
+    CUDA_TRY(cudaEventRecord(e0));
+    pr::pr_dfma_kernel<<<grid, block>>>(sink, iters, 1.0000001, 1e-9);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    spent += ms;
+    const double flops = 2.0 * 8.0 * (double)iters * grid * block;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+    if (ms < 5.0) iters *= 2;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops_out = best;
+  return PR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""Ensemble entry point (additive to the reference API): many members of one reach -
+Manning-roughness calibration sweeps, inflow scenarios - advanced together on one GPU.
+
+The reference runs members one after another (cases/gerd_roseires/n_calibrate.py:55-63 calls model.run
+per roughness value).  Here the member axis is the parallel axis: per-member inputs go to the device once,
+initial conditions, the whole time loop and the calibration objective run there, and only reduced outputs
+come back.  torch is used for device buffers and streams only.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from . import abi
+from .flatten import FlatCase
+from .runner import PreparedCall, gvf_initial_conditions, rating_objective
+
+
+class EnsembleRunner:
+    """Holds one reach (geometry + boundary description) resident on a device and runs member batches."""
+
+    def __init__(self, flat: FlatCase, device="cuda:0"):
+        import torch
+
+        self.torch = torch
+        self.device = torch.device(device)
+        self.lib = abi.load_library()
+        self.flat = copy.copy(flat)
+        # geometry is member-independent: upload once, reuse for every call
+        self.flat.geom = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in flat.geom.items()}
+        self.flat.up = copy.copy(flat.up)
+        self.flat.down = copy.copy(flat.down)
+        for b in (self.flat.up, self.flat.down):
+            if b.series is not None and not hasattr(b.series, "data_ptr"):
+                b.series = torch.from_numpy(np.ascontiguousarray(b.series, dtype=np.float64)).to(self.device)
+        self.flat.ic_depth = torch.from_numpy(np.ascontiguousarray(flat.ic_depth)).to(self.device)
+        self.flat.ic_flow = torch.from_numpy(np.ascontiguousarray(flat.ic_flow)).to(self.device)
+
+    def _to_device(self, a):
+        t = self.torch
+        if a is None:
+            return None
+        if isinstance(a, t.Tensor):
+            return a.to(self.device, non_blocking=True)
+        return t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device, non_blocking=True)
+
+    def solve(self, n_members: int, member_n_main=None, member_n_fp=None, up_series=None, ic_depth=None, ic_flow=None,
+              out_mode: int = abi.PR_OUT_UPSTREAM, stream=None, want_error: bool = False) -> dict:
+        """One pr_ensemble_run on device buffers; returns torch tensors (no synchronisation)."""
+        f = copy.copy(self.flat)
+        f.member_n_main = self._to_device(member_n_main)
+        f.member_n_fp = self._to_device(member_n_fp)
+        if up_series is not None:
+            f.up = copy.copy(f.up)
+            f.up.series = self._to_device(up_series)
+        if ic_depth is not None:
+            f.ic_depth, f.ic_flow = self._to_device(ic_depth), self._to_device(ic_flow)
+        call = PreparedCall(f, n_members, out_mode, abi.PR_MEM_DEVICE, self.device, want_error=want_error)
+        import ctypes as C
+
+        rc = self.lib.pr_ensemble_run(*call.args(), C.c_void_p(stream or 0))
+        abi.check(self.lib, rc, "pr_ensemble_run")
+        return call.results()
+
+    def roughness_sweep(self, n_main, n_fp=None, q_query=None, h_target=None, downstream_depth=None, q0=None,
+                        out_mode: int = abi.PR_OUT_UPSTREAM, stream=None) -> dict:
+        """The calibration ensemble (config 4): for every n_main[m] recompute the GVF initial profile
+        (it depends on the roughness), run the whole simulation and, when q_query / h_target are given,
+        evaluate the rating objective.  Inputs may be pinned host tensors; outputs stay on the device."""
+        n_dev = self._to_device(n_main)
+        nfp_dev = self._to_device(n_fp)
+        M = int(n_dev.shape[0])
+        f = copy.copy(self.flat)
+        f.member_n_main, f.member_n_fp = n_dev, nfp_dev
+        h_dn = float(self.flat.meta["downstream_depth"] if downstream_depth is None else downstream_depth)
+        q_init = self.flat.meta["initial_flow"] if q0 is None else q0
+        ich, icq, ic_status = gvf_initial_conditions(f, M, q_init, h_dn, abi.PR_MEM_DEVICE, self.device, stream)
+        res = self.solve(M, member_n_main=n_dev, member_n_fp=nfp_dev, ic_depth=ich, ic_flow=icq, out_mode=out_mode,
+                         stream=stream)
+        res["ic_status"] = ic_status
+        if q_query is not None:
+            if out_mode == abi.PR_OUT_UPSTREAM:
+                upq, uph = res["flow"], res["depth"]
+            else:
+                upq, uph = res["flow"][:, :, 0].contiguous(), res["depth"][:, :, 0].contiguous()
+            lv, rm = rating_objective(self.flat.n_levels, upq, uph, float(self.flat.meta["z0"]),
+                                      self._to_device(q_query), self._to_device(h_target), abi.PR_MEM_DEVICE,
+                                      self.device, stream)
+            res["levels"], res["rmse"] = lv, rm
+        return res
+
+
+def to_host(res: dict) -> dict:
+    """Device results -> numpy (one synchronising copy per array)."""
+    return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}

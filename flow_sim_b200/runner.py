@@ -118,3 +118,72 @@ def run_flat(flat: FlatCase, n_members: int | None = None, out_mode: int = abi.P
 
         torch.cuda.synchronize()
     return call.results()
+
+
+def _geom_struct(flat: FlatCase, arena: abi.Arena, M: int) -> abi.pr_geom:
+    g = abi.pr_geom()
+    for name in abi.GEOM_FIELDS:
+        setattr(g, name, arena.put(flat.geom[name], np.int32 if name == "kind" else np.float64)[0])
+    for name in ("member_n_main", "member_n_fp"):
+        v = getattr(flat, name)
+        if v is not None and len(v) != M:
+            raise ValueError(f"{name} has {len(v)} entries for {M} members")
+        setattr(g, name, arena.put(v)[0])
+    return g
+
+
+def _config(flat: FlatCase, M: int, mem: int, device, out_mode: int = abi.PR_OUT_UPSTREAM) -> abi.pr_config:
+    dev_index = -1
+    if mem == abi.PR_MEM_DEVICE:
+        import torch
+
+        dev_index = torch.device(device).index if device is not None else None
+        if dev_index is None:
+            dev_index = torch.cuda.current_device()
+    return abi.pr_config(abi_version=abi.PR_ABI_VERSION, n_nodes=flat.n_nodes, n_levels=flat.n_levels, n_members=M,
+                         max_iter=flat.max_iter, out_mode=out_mode, mem=mem, device=dev_index, lanes_per_member=0,
+                         theta=flat.theta, dt=flat.dt, dx=flat.dx, tol=flat.tol, g=flat.g)
+
+
+def gvf_initial_conditions(flat: FlatCase, n_members: int, q0, downstream_depth: float,
+                           mem: int = abi.PR_MEM_HOST, device=None, stream=None):
+    """Channel._gvh_conditions (channel.py:307-378) for every member on the device.
+    Returns (depth[M,N], flow[M,N], status[M])."""
+    lib = abi.load_library()
+    ar = abi.Arena(mem, device)
+    cfg = _config(flat, n_members, mem, device)
+    g = _geom_struct(flat, ar, n_members)
+    if mem == abi.PR_MEM_HOST or not hasattr(q0, "data_ptr"):
+        q0 = np.atleast_1d(np.asarray(q0, dtype=np.float64))
+    n_q0 = q0.shape[0]
+    if n_q0 not in (1, n_members):
+        raise ValueError("q0 must have 1 or M entries")
+    q0p, _ = ar.put(q0)
+    hp, h = ar.empty((n_members, flat.n_nodes))
+    qp, q = ar.empty((n_members, flat.n_nodes))
+    sp, st = ar.empty((n_members,), np.int32)
+    rc = lib.pr_gvf_initial_conditions(C.byref(cfg), C.byref(g), q0p, 0 if n_q0 == 1 else 1,
+                                       float(downstream_depth), hp, qp, sp, C.c_void_p(stream or 0))
+    abi.check(lib, rc, "pr_gvf_initial_conditions")
+    return h, q, st
+
+
+def rating_objective(n_levels: int, up_flow, up_depth, z0: float, q_query, h_target,
+                     mem: int = abi.PR_MEM_HOST, device=None, stream=None):
+    """np.interp(Q, flow[:,0], depth[:,0]+z0) and its RMSE against h_target per member
+    (model.py:105-113, n_calibrate.py:55-63).  Returns (levels[M,nq], rmse[M])."""
+    lib = abi.load_library()
+    ar = abi.Arena(mem, device)
+    M = int(up_flow.shape[0])
+    cfg = abi.pr_config(abi_version=abi.PR_ABI_VERSION, n_nodes=2, n_levels=n_levels, n_members=M, max_iter=1,
+                        out_mode=abi.PR_OUT_UPSTREAM, mem=mem, device=-1, theta=0.5, dt=1.0, dx=1.0, tol=1.0, g=9.80665)
+    fq, _ = ar.put(up_flow)
+    fh, _ = ar.put(up_depth)
+    qq, qa = ar.put(np.asarray(q_query, dtype=np.float64) if not hasattr(q_query, "data_ptr") else q_query)
+    ht, _ = ar.put(np.asarray(h_target, dtype=np.float64) if not hasattr(h_target, "data_ptr") else h_target)
+    nq = int(qa.shape[0])
+    lp, lv = ar.empty((M, nq))
+    rp, rm = ar.empty((M,))
+    rc = lib.pr_rating_objective(C.byref(cfg), fq, fh, float(z0), qq, ht, nq, lp, rp, C.c_void_p(stream or 0))
+    abi.check(lib, rc, "pr_rating_objective")
+    return lv, rm

@@ -1,0 +1,49 @@
+"""Shared helpers of the parity tests."""
+import os
+
+import numpy as np
+
+from flow_sim_b200.flatten import load_flat
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+#: the north star's tolerance: 1e-9 relative on stage and discharge at every node and step
+RTOL = 1e-9
+
+CALIB_MEMBERS = [0, 8191, 21845, 30000, 36408, 43690, 54321, 65535]
+SMALL_CASES = ["example", "akbari"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
+
+
+def calib_n(m):
+    return 0.020 + 0.040 * m / 65535
+
+
+def golden_inputs(case):
+    return load_flat(os.path.join(GOLD, f"{case}.in.npz"))
+
+
+def golden_outputs(case):
+    return np.load(os.path.join(GOLD, f"{case}.ref.npz"))
+
+
+def has_golden_outputs(case):
+    return os.path.exists(os.path.join(GOLD, f"{case}.ref.npz"))
+
+
+def max_rel(a, b, floor=0.0):
+    """max |a-b| / max(|b|, floor) over all entries."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), floor if floor > 0 else np.finfo(float).tiny)
+    return float(np.max(np.abs(a - b) / den))
+
+
+def assert_parity(got_depth, got_flow, ref_depth, ref_flow, what, rtol=RTOL):
+    """Stage = depth (+ constant bed), discharge = flow.  Discharge can pass through zero (example case,
+    level 1 at the storage boundary), so its error is taken relative to max(|Q|, 1e-3 * max|Q|)."""
+    ed = max_rel(got_depth, ref_depth)
+    qfloor = 1e-3 * float(np.max(np.abs(ref_flow)))
+    eq = max_rel(got_flow, ref_flow, floor=qfloor)
+    assert ed <= rtol, f"{what}: depth rel err {ed:.3e} > {rtol}"
+    assert eq <= rtol, f"{what}: flow rel err {eq:.3e} > {rtol}"
+    return ed, eq
