@@ -36,16 +36,11 @@ template <bool CURV>
 __global__ void __launch_bounds__(128) pr_gvf_kernel(const __grid_constant__ GvfParams p) {
   extern __shared__ double smem[];
   const int NP = p.N;
-  stage_geometry(p.geo, p.N, NP, smem, threadIdx.x, blockDim.x);
+  stage_geometry(p.geo, p.N, NP, smem, threadIdx.x, blockDim.x, [](int idx) { return idx; });
   __syncthreads();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= p.M) return;
-  Rough rg;
-  rg.has_nm = p.geo.member_nm != nullptr;
-  rg.has_nfp = p.geo.member_nfp != nullptr;
-  rg.nm = rg.has_nm ? p.geo.member_nm[m] : 0.0;
-  rg.cnm = rg.has_nm ? inv_n15(rg.nm) : 0.0;
-  rg.cnfp = rg.has_nfp ? inv_n15(p.geo.member_nfp[m]) : 0.0;
+  const Rough rg = load_rough(p.geo, m);
   const double Q = p.q0[m * p.q0_stride];
   const int N = p.N;
   double* oh = p.ic_h + (size_t)m * N;

@@ -2,8 +2,8 @@
 //
 // Everything here is FP64 and written for sm_100a.  The formulas follow the reference
 // (cve-mohd/flow-sim, src/hydromodel) function by function - citations below - but are algebraically
-// condensed for the FP64 pipe: one cbrt and at most three sqrt per node instead of up to nine pow(),
-// reciprocals shared between terms, Manning factors n^-1.5 hoisted out of the Newton loop.  The
+// condensed for the FP64 pipe: one reciprocal cube root and at most three square roots per node instead
+// of up to nine pow(), reciprocals shared between terms, Manning factors n^-1.5 hoisted out of the loop.  The
 // condensation changes results at the few-ulp level only (tests hold the device path to 1e-9 relative
 // and identical Newton iteration counts against the CPU oracle and the reference's golden outputs).
 #pragma once
@@ -45,6 +45,7 @@ struct DevGeom {
 struct DevParams {
   int N, L, M, max_iter, out_mode;
   double theta, dt, dx, tol, g;
+  double i2dt, th_dx, hth, omt_dx, homt;   // 1/(2dt), theta/dx, theta/2, (1-theta)/dx, (1-theta)/2
   DevGeom geo;
   DevBC up, dn;
   const double *ic_h, *ic_q;
@@ -54,50 +55,115 @@ struct DevParams {
   double *storage_stage, *final_error;
 };
 
-// ---- per-node geometry staged in shared memory (SoA, NP = padded node count) -----------------------
+// ---- FP64 primitives without slow-path branches ----------------------------------------------------
+// CUDA's IEEE division / sqrt / cbrt carry special-case branches (BSSY/BSYNC/CALL) that cost issue slots
+// and diverge.  The scheme only needs ~1e-15 relative accuracy on positive, normal arguments, so these use
+// the SFU seed (MUFU.RCP64H / RSQ64H, fp32 LG2/EX2) plus two Newton / Goldschmidt steps, all on the FMA pipe.
+
+__device__ __forceinline__ double fast_rcp(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+__device__ __forceinline__ double fast_sqrt(double a) {   // a >= 0 (0 -> 0)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  return a > 0.0 ? g : 0.0;
+}
+
+__device__ __forceinline__ double fast_rsqrt(double a) {  // a > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a * y, y, 1.0);          // y <- y*(1 + e/2 + 3e^2/8)
+  y = fma(y * fma(0.375, e, 0.5), e, y);
+  e = fma(-a * y, y, 1.0);
+  y = fma(y * 0.5, e, y);
+  return y;
+}
+
+__device__ __forceinline__ double fast_rcbrt(double x) {  // x^(-1/3), x > 0 within float range
+  const float xf = __double2float_rn(x);
+  double r = (double)exp2f(-0.33333334f * __log2f(xf));   // ~2^-21 relative
+  double r2 = r * r;
+  double t = fma(-x * r, r2, 1.0);                        // Newton on r^-3 = x: r <- r + r(1 - x r^3)/3
+  r = fma(r * (1.0 / 3.0), t, r);
+  r2 = r * r;
+  t = fma(-x * r, r2, 1.0);
+  r = fma(r * (1.0 / 3.0), t, r);
+  return r;
+}
+
+// ---- per-node geometry staged in shared memory (SoA: field f of slot idx at sg[f*NP + idx]) -----------
 
 enum GeoField {
   F_KIND = 0, F_Z, F_B, F_M, F_SQM, F_HB, F_TB, F_WB, F_BL, F_BR, F_MFP, F_SQFP, F_AMF, F_PM, F_INVPM,
-  F_NM, F_CNL, F_CNM, F_CNR, F_CURV, F_COUNT
+  F_NM, F_INVNM, F_CNL, F_CNM, F_CNR, F_CURV, F_COUNT
 };
 
 __device__ __forceinline__ double inv_n15(double n) { return 1.0 / (n * sqrt(n)); }  // n^-1.5
 
-// Fills sg[F_COUNT][NP]; nodes >= N replicate node N-1 so padded lanes compute finite throw-away values.
-__device__ inline void stage_geometry(const DevGeom& g, int N, int NP, double* sg, int tid, int nthreads) {
-  for (int i = tid; i < NP; i += nthreads) {
-    const int s = i < N ? i : N - 1;
+// Fills sg[F_COUNT][NP].  Slot `idx` holds node map(idx) (identity for the per-thread kernels; lane-major
+// for the cooperative kernel so that a warp reads consecutive doubles).  Nodes >= N replicate node N-1 so
+// padded lanes compute finite throw-away values.
+template <class Map>
+__device__ inline void stage_geometry(const DevGeom& g, int N, int NP, double* sg, int tid, int nthreads, Map map) {
+  for (int idx = tid; idx < NP; idx += nthreads) {
+    const int node = map(idx);
+    const int s = node < N ? node : N - 1;
     const double b = g.b[s], m = g.m[s], hb = g.hb[s], Tb = g.Tb[s], mfp = g.mfp[s];
     const double sqm = sqrt(1.0 + m * m);
     const double Pm = b + 2.0 * hb * sqm;               // cross_section.py:661,695
-    sg[F_KIND * NP + i] = (double)g.kind[s];
-    sg[F_Z * NP + i] = g.z[s];
-    sg[F_B * NP + i] = b;
-    sg[F_M * NP + i] = m;
-    sg[F_SQM * NP + i] = sqm;
-    sg[F_HB * NP + i] = hb;
-    sg[F_TB * NP + i] = Tb;
-    sg[F_WB * NP + i] = g.Wb[s];
-    sg[F_BL * NP + i] = g.bl[s];
-    sg[F_BR * NP + i] = g.br[s];
-    sg[F_MFP * NP + i] = mfp;
-    sg[F_SQFP * NP + i] = sqrt(1.0 + mfp * mfp);
-    sg[F_AMF * NP + i] = (b + Tb) / 2.0 * hb;           // cross_section.py:660
-    sg[F_PM * NP + i] = Pm;
-    sg[F_INVPM * NP + i] = Pm > 0.0 ? 1.0 / Pm : 0.0;
-    sg[F_NM * NP + i] = g.nm[s];
-    sg[F_CNL * NP + i] = inv_n15(g.nl[s]);
-    sg[F_CNM * NP + i] = inv_n15(g.nm[s]);
-    sg[F_CNR * NP + i] = inv_n15(g.nr[s]);
-    sg[F_CURV * NP + i] = g.curv[s];
+    sg[F_KIND * NP + idx] = (double)g.kind[s];
+    sg[F_Z * NP + idx] = g.z[s];
+    sg[F_B * NP + idx] = b;
+    sg[F_M * NP + idx] = m;
+    sg[F_SQM * NP + idx] = sqm;
+    sg[F_HB * NP + idx] = hb;
+    sg[F_TB * NP + idx] = Tb;
+    sg[F_WB * NP + idx] = g.Wb[s];
+    sg[F_BL * NP + idx] = g.bl[s];
+    sg[F_BR * NP + idx] = g.br[s];
+    sg[F_MFP * NP + idx] = mfp;
+    sg[F_SQFP * NP + idx] = sqrt(1.0 + mfp * mfp);
+    sg[F_AMF * NP + idx] = (b + Tb) / 2.0 * hb;         // cross_section.py:660
+    sg[F_PM * NP + idx] = Pm;
+    sg[F_INVPM * NP + idx] = Pm > 0.0 ? 1.0 / Pm : 0.0;
+    sg[F_NM * NP + idx] = g.nm[s];
+    sg[F_INVNM * NP + idx] = 1.0 / g.nm[s];
+    sg[F_CNL * NP + idx] = inv_n15(g.nl[s]);
+    sg[F_CNM * NP + idx] = inv_n15(g.nm[s]);
+    sg[F_CNR * NP + idx] = inv_n15(g.nr[s]);
+    sg[F_CURV * NP + idx] = g.curv[s];
   }
 }
 
 // Per-member roughness override (model.run(n_main=, n_fp=)); has_* false -> the node's own values.
 struct Rough {
   bool has_nm, has_nfp;
-  double nm, cnm, cnfp;
+  double nm, inm, cnm, cnfp;    // n_main, 1/n_main, n_main^-1.5, n_fp^-1.5
 };
+
+__device__ __forceinline__ Rough load_rough(const DevGeom& g, long long member) {
+  Rough rg;
+  rg.has_nm = g.member_nm != nullptr;
+  rg.has_nfp = g.member_nfp != nullptr;
+  rg.nm = rg.has_nm ? g.member_nm[member] : 1.0;
+  rg.inm = 1.0 / rg.nm;
+  rg.cnm = inv_n15(rg.nm);
+  rg.cnfp = rg.has_nfp ? inv_n15(g.member_nfp[member]) : 1.0;
+  return rg;
+}
 
 // Everything a cell needs from one node at the current iterate.
 struct NodeVals {
@@ -114,18 +180,25 @@ struct NodeVals {
   double dKA;   // dK/dA                             (cross_section.py:756-764)
 };
 
-// Node pass.  h = depth unknown, Q = discharge unknown, i = node slot in shared memory.
+// Node pass.  h = depth unknown, Q = discharge unknown, idx = node slot in shared memory.
+//
+// Conveyance without pow():  with r = X^(-1/3),
+//   simple / in-bank : X = R = A/P,  K = A R^(2/3)/n = A (R r)/n,      1/K^2 = (n/A)^2 r^4
+//   over-bank        : X = S = sum_j A_j^1.5 R_j n_j^-1.5 (= sum K_j^1.5),  K = S^(2/3) = S r,  1/K^2 = r^4
+// and dK/dA = K (5/(3A) - (2/3) dP_dh/(T P)) in every case (n_eq frozen at A R^(2/3)/K, quirk 6).
+// One reciprocal of A*P*T yields 1/A and 1/(T P); the over-bank branch needs one more for the
+// floodplain hydraulic radii.  The expensive tail (reciprocal, cube root) is common to all branches, so
+// lanes of a warp that sit on different branches re-converge before it.
 template <bool CURV>
-__device__ __forceinline__ void node_eval(const double* __restrict__ sg, const int NP, const int i, const double h,
+__device__ __forceinline__ void node_eval(const double* __restrict__ sg, const int NP, const int idx, const double h,
                                           const double Q, const Rough& rg, const double g, NodeVals& o) {
-#define GEO(f) sg[(f)*NP + i]
+#define GEO(f) sg[(f)*NP + idx]
   const int kind = (int)GEO(F_KIND);
   const double z = GEO(F_Z), b = GEO(F_B);
   const double hw = z + h;        // Solver.water_level_at
   const double d = hw - z;        // depth = max(0, hw - z_bed); a dry node (d <= 0) ends in status NaN
-  const double nm = rg.has_nm ? rg.nm : GEO(F_NM);
-  double A, P, T, dPdh, K, invK2;
-  bool compound_over = false;
+  double A, P, T, dPdh, X = 0.0;
+  bool over = false;
   if (kind == PR_XS_RECT) {
     A = b * d;
     P = b + 2.0 * d;
@@ -140,46 +213,46 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       P = b + 2.0 * d * sqm;
       dPdh = 2.0 * sqm;
     } else {
-      compound_over = true;
+      over = true;
       const double dfp = d - hb, mfp = GEO(F_MFP), sqfp = GEO(F_SQFP);
       const double bl = GEO(F_BL), br = GEO(F_BR);
-      const double Al = (bl + 0.5 * mfp * dfp) * dfp, Pl = bl + dfp * sqfp;
-      const double Ar = (br + 0.5 * mfp * dfp) * dfp, Pr = br + dfp * sqfp;
+      const double hm = 0.5 * mfp * dfp;
+      const double Al = (bl + hm) * dfp, Pl = bl + dfp * sqfp;
+      const double Ar = (br + hm) * dfp, Pr = br + dfp * sqfp;
       const double Amf = GEO(F_AMF);
       A = Amf + Al + Ar;                                   // quirk 4: total area omits T_bank*dfp
       P = GEO(F_PM) + Pl + Pr;
       T = GEO(F_WB) + 2.0 * mfp * dfp;
       dPdh = 2.0 * sqfp;
-      // K = (K_l^1.5 + K_m^1.5 + K_r^1.5)^(2/3), K_j = A_j R_j^(2/3)/n_j  (cross_section.py:681-754)
-      // K_j^1.5 = A_j^1.5 * R_j * n_j^-1.5 = A_j*sqrt(A_j) * (A_j/P_j) * n_j^-1.5
+      // K_j^1.5 = A_j*sqrt(A_j) * (A_j/P_j) * n_j^-1.5   (cross_section.py:681-754, hydraulics.py:15-26)
       const double Am = Amf + GEO(F_TB) * dfp;             // conveyance area includes the column (:694)
       const double cnm = rg.has_nm ? rg.cnm : GEO(F_CNM);
       const double cnl = rg.has_nfp ? rg.cnfp : GEO(F_CNL);
       const double cnr = rg.has_nfp ? rg.cnfp : GEO(F_CNR);
-      double S = Am * sqrt(Am) * (Am * GEO(F_INVPM)) * cnm;
-      if (Pl > 0.0) S += Al * sqrt(Al) * (Al / Pl) * cnl;
-      if (Pr > 0.0) S += Ar * sqrt(Ar) * (Ar / Pr) * cnr;
-      const double cS = cbrt(S);
-      K = cS * cS;
-      invK2 = 1.0 / (S * cS);
+      const double w = fast_rcp(Pl * Pr);                  // Pl, Pr > 0 because dfp > 0
+      X = (Am * Am) * fast_sqrt(Am) * (GEO(F_INVPM) * cnm);
+      X = fma((Al * Al) * fast_sqrt(Al), (Pr * w) * cnl, X);
+      X = fma((Ar * Ar) * fast_sqrt(Ar), (Pl * w) * cnr, X);
     }
   }
-  const double invP = 1.0 / P;
-  const double R = A * invP;
-  double cR = 0.0;
-  if (!compound_over) {
-    // K = A R^(2/3) / n_main (hydraulics.py:15-26); compound in-bank passes through
-    // (0 + K_m^1.5 + 0)^(2/3) in the reference, equal to K_m within an ulp (quirk 5)
-    cR = cbrt(R);
-    K = A * (cR * cR) / nm;
-    invK2 = 1.0 / (K * K);
+  const double PT = P * T;
+  const double u = fast_rcp(A * PT);
+  const double invA = u * PT, invTP = u * A;
+  const double nm = rg.has_nm ? rg.nm : GEO(F_NM);
+  if (!over) X = A * (invTP * T);                          // R = A/P
+  const double r = fast_rcbrt(X);
+  const double r2 = r * r, r4 = r2 * r2;
+  double K, invK2;
+  if (over) {
+    K = X * r;
+    invK2 = r4;
+  } else {
+    const double inm = rg.has_nm ? rg.inm : GEO(F_INVNM);
+    K = A * (X * r) * inm;
+    const double na = nm * invA;
+    invK2 = (na * na) * r4;
   }
-  const double invA = 1.0 / A;
-  const double invT = 1.0 / T;
-  // dK/dA = (R^(2/3) + A*(2/3)*R^(-1/3)*dR_dA)/n_eq with n_eq = A R^(2/3)/K (frozen, quirk 6)
-  //       = K*(1/A + (2/3)*dR_dA/R),  dR_dA = (P - A*dP_dh/T)/P^2            (cross_section.py:756-790)
-  const double dRA = (P - A * dPdh * invT) * (invP * invP);
-  const double dKA_over_K = invA + (2.0 / 3.0) * dRA / R;
+  const double dKA_over_K = (5.0 / 3.0) * invA - (2.0 / 3.0) * dPdh * invTP;
   const double absQ = fabs(Q);
   const double Sf = Q * absQ * invK2;                       // hydraulics.py:42-57
   double Se = Sf;
@@ -189,7 +262,10 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
     const double curv = GEO(F_CURV);
     if (curv != 0.0) {
       // hydraulics.Sc / dSc_dA / dSc_dQ (hydraulics.py:94-229), CrossSection wrappers cross_section.py:143-175
-      if (compound_over) cR = cbrt(R);
+      const double invT = invTP * P, invP = invTP * T;
+      const double R = A * invP;
+      const double rR = over ? fast_rcbrt(R) : r;           // R^(-1/3)
+      const double cR = R * rR * rR;                        // R^(1/3)
       const double n_eq = (kind == PR_XS_COMPOUND) ? A * (cR * cR) / K : nm;    // cross_section.py:710-739
       const double rc = 1.0 / curv;
       const double V = Q / fmax(A, 1e-6), D = A / fmax(T, 1e-6);
@@ -201,6 +277,7 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       const double den = (0.565 + sqf) * (rc * rc);
       Se += num / den;
       if (fabs(curv) > 1e-12) {
+        const double dRA = (P - A * dPdh * invT) * (invP * invP);
         const double gD = g * (A * invT);
         const double rs = rsqrt(gD);                        // (gD)^-0.5, unclamped (quirk 7)
         const double dFrA = -0.5 * (Q * invA) * (rs * rs * rs) * g * invT + (-Q * invA * invA) * rs;
@@ -286,7 +363,7 @@ struct BcRow {
 // stage_prev = reservoir stage recorded for level-1.
 __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int level, const double hyd, const double h,
                                          const double Q, const double q_prev, const double stage_prev,
-                                         const double dt, const NodeVals& nv) {
+                                         const double dt, const double K, const double dKA, const double T) {
   BcRow o;
   o.stage_rec = 0.0;
   switch (bc.type) {
@@ -301,8 +378,8 @@ __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int level, const
       break;
     case PR_BC_NORMAL_DEPTH:
       // hydraulics.normal_flow / dQn_dA (hydraulics.py:4-13, 206-215); host checks bed_level == z_min
-      o.res = Q - nv.K * bc.slope_factor;
-      o.dh = 0.0 - nv.dKA * bc.slope_factor * nv.T;
+      o.res = Q - K * bc.slope_factor;
+      o.dh = 0.0 - dKA * bc.slope_factor * T;
       o.dq = 1.0;
       break;
     case PR_BC_RATING_CURVE: {

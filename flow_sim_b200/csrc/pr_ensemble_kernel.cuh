@@ -26,7 +26,6 @@
 
 namespace pr {
 
-constexpr int kWarpsPerCta = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
 // A (possibly condensed) cell between nodes a (left) and b (right):
@@ -41,17 +40,17 @@ struct Cell {
 struct Elim {
   double i11, i12, i21, i22;
   double m1, m2, rm;
-  double c3, c4, rc;
+  double c3, rc;          // c4 of a raw cell is the constant theta/dx
 };
 
 // Schur-complement merge of S (a..b) and E (b..c) eliminating node b; pivot rows are S.M and E.C.
 __device__ __forceinline__ void merge_cells(Cell& S, const Cell& E, Elim& el) {
   const double det = S.m3 * E.c2 - S.m4 * E.c1;
-  const double idet = 1.0 / det;
+  const double idet = fast_rcp(det);
   const double i11 = E.c2 * idet, i12 = -S.m4 * idet, i21 = -E.c1 * idet, i22 = S.m3 * idet;
   el.i11 = i11; el.i12 = i12; el.i21 = i21; el.i22 = i22;
   el.m1 = S.m1; el.m2 = S.m2; el.rm = S.rm;
-  el.c3 = E.c3; el.c4 = E.c4; el.rc = E.rc;
+  el.c3 = E.c3; el.rc = E.rc;
   // w = [S.c3 S.c4] * Dinv ; v = [E.m1 E.m2] * Dinv
   const double w1 = S.c3 * i11 + S.c4 * i21, w2 = S.c3 * i12 + S.c4 * i22;
   const double v1 = E.m1 * i11 + E.m2 * i21, v2 = E.m1 * i12 + E.m2 * i22;
@@ -67,11 +66,7 @@ __device__ __forceinline__ void merge_cells(Cell& S, const Cell& E, Elim& el) {
 
 // Residuals + Jacobian of one Preissmann cell (left node a, right node b) and the candidate level
 // constants.  pc = {cC, cM, cA, cS} of the stored level; returns R_C^2 + R_M^2.
-struct SchemeConst {
-  double i2dt, th_dx, hth, omt_dx, homt, g;
-};
-
-__device__ __forceinline__ double cell_assemble(const NodeVals& a, const NodeVals& b, const SchemeConst& k,
+__device__ __forceinline__ double cell_assemble(const NodeVals& a, const NodeVals& b, const DevParams& k,
                                                 const double cC, const double cM, const double cA, const double cS,
                                                 Cell& e, double& nC, double& nM, double& nA, double& nS) {
   const double sA = b.A + a.A, dQ = b.Q - a.Q, sQ = b.Q + a.Q, dF = b.F - a.F, dY = b.Y - a.Y, sSe = b.Se + a.Se;
@@ -106,27 +101,37 @@ __device__ __forceinline__ double group_sum(double v) {
   return v;
 }
 
-// Shared memory: [geometry F_COUNT x NP doubles][per warp: 2 x 4 x M x 32 doubles]
-template <int G, int M>
+// Shared memory (doubles): [geometry F_COUNT x NP] then per warp
+//   level constants  2 x 4 x M x 32   (ping-pong: stored level / candidate)
+//   elimination recs (M-1) x 9 x 32
+//   neighbour exchange 9 x 32         (first-node values handed to the lane on the left)
+// every per-warp array is indexed [..][lane]: consecutive lanes, consecutive doubles, no bank conflicts.
+template <int M>
+__host__ __device__ constexpr int warp_smem_doubles() { return 32 * (8 * M + 9 * (M - 1) + 9); }
+
+template <int G, int M, int W>
 __host__ __device__ constexpr size_t ensemble_smem_bytes() {
-  return sizeof(double) * ((size_t)F_COUNT * G * M + (size_t)kWarpsPerCta * 2 * 4 * M * 32);
+  return sizeof(double) * ((size_t)F_COUNT * G * M + (size_t)W * warp_smem_doubles<M>());
 }
 
-template <int G, int M, bool CURV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <int G, int M, int W, bool CURV>
+__global__ void __launch_bounds__(W * 32, 1)
 pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ double smem[];
   constexpr int NP = G * M;           // padded node slots per member
   constexpr int MPW = 32 / G;         // members per warp
   double* sg = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* pcw = smem + (size_t)F_COUNT * NP + (size_t)warp * (2 * 4 * M * 32);   // level constants of this warp
-  stage_geometry(p.geo, p.N, NP, sg, threadIdx.x, blockDim.x);
+  double* pcw = smem + (size_t)F_COUNT * NP + (size_t)warp * warp_smem_doubles<M>();   // level constants
+  double* elw = pcw + 2 * 4 * M * 32;                                                    // elimination records
+  double* xw = elw + (M - 1) * 9 * 32;                                                   // neighbour exchange
+  // slot (j, gl) at index j*G + gl holds node gl*M + j
+  stage_geometry(p.geo, p.N, NP, sg, threadIdx.x, blockDim.x, [](int idx) { return (idx % G) * M + idx / G; });
   __syncthreads();
 
   const int gl = lane % G;            // lane within the member's group
   const int N = p.N, L = p.L;
-  long long member = ((long long)blockIdx.x * kWarpsPerCta + warp) * MPW + lane / G;
+  long long member = ((long long)blockIdx.x * W + warp) * MPW + lane / G;
   const bool member_valid = member < p.M;
   if (!member_valid) member = p.M - 1;
 
@@ -140,20 +145,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   const bool is_first = (gl == 0);
   const bool owns_last = (gl == owner_last);
 
-  SchemeConst k;
-  k.i2dt = 1.0 / (2.0 * p.dt);
-  k.th_dx = p.theta / p.dx;
-  k.hth = 0.5 * p.theta;
-  k.omt_dx = (1.0 - p.theta) / p.dx;
-  k.homt = 0.5 * (1.0 - p.theta);
-  k.g = p.g;
-
-  Rough rg;
-  rg.has_nm = p.geo.member_nm != nullptr;
-  rg.has_nfp = p.geo.member_nfp != nullptr;
-  rg.nm = rg.has_nm ? p.geo.member_nm[member] : 0.0;
-  rg.cnm = rg.has_nm ? inv_n15(rg.nm) : 0.0;
-  rg.cnfp = rg.has_nfp ? inv_n15(p.geo.member_nfp[member]) : 0.0;
+  const DevParams& k = p;
+  const Rough rg = load_rough(p.geo, member);
 
   // ---- state: initial conditions (Solver.initialize_t0, solver.py:61-63) ----
   double h[M], q[M];
@@ -189,7 +182,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
   // boundary bookkeeping held by the lane that owns node N-1
   double q_prev_last = q[slot_last];                                   // flow_at(k=-1, i=-1)
-  double stage_prev = sg[F_Z * NP + (N - 1)] + h[slot_last];           // solver.py:101-108
+  double stage_prev = sg[F_Z * NP + slot_last * G + owner_last] + h[slot_last];   // solver.py:101-108
   if (member_valid && owns_last && p.storage_stage) p.storage_stage[(size_t)member * L] = stage_prev;
 
   int level = 1, it = 0;
@@ -210,33 +203,30 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     if (active && !init_pass) it += 1;
 
     // ------------------------------ node + cell pass ------------------------------
+#define EL(j, c) elw[((j)*9 + (c)) * 32 + lane]
     NodeVals left, right, first;
-    node_eval<CURV>(sg, NP, my_first, h[0], q[0], rg, k.g, first);
-    // the next lane's first node closes this lane's last cell
-    NodeVals nxt;
-    nxt.Q = __shfl_down_sync(kFull, first.Q, 1, G);
-    nxt.A = __shfl_down_sync(kFull, first.A, 1, G);
-    nxt.T = __shfl_down_sync(kFull, first.T, 1, G);
-    nxt.Y = __shfl_down_sync(kFull, first.Y, 1, G);
-    nxt.Se = __shfl_down_sync(kFull, first.Se, 1, G);
-    nxt.F = __shfl_down_sync(kFull, first.F, 1, G);
-    nxt.QA = __shfl_down_sync(kFull, first.QA, 1, G);
-    nxt.dSeA = __shfl_down_sync(kFull, first.dSeA, 1, G);
-    nxt.dSeQ = __shfl_down_sync(kFull, first.dSeQ, 1, G);
-    nxt.K = 0.0; nxt.dKA = 0.0;
+    node_eval<CURV>(sg, NP, gl, h[0], q[0], rg, p.g, first);
+    // hand the first node to the lane on the left: it closes that lane's last cell
+    __syncwarp();
+    xw[0 * 32 + lane] = first.Q;  xw[1 * 32 + lane] = first.A;  xw[2 * 32 + lane] = first.T;
+    xw[3 * 32 + lane] = first.Y;  xw[4 * 32 + lane] = first.Se; xw[5 * 32 + lane] = first.F;
+    xw[6 * 32 + lane] = first.QA; xw[7 * 32 + lane] = first.dSeA; xw[8 * 32 + lane] = first.dSeQ;
+    __syncwarp();
 
     double ss = 0.0;
     Cell S;                     // condensed cell of this lane
-    Elim el[M > 1 ? M - 1 : 1];
-    NodeVals lastnode = first;  // values at node N-1 when this lane owns it
+    double lastK = first.K, lastdKA = first.dKA, lastT = first.T;   // node N-1 (normal-depth boundary)
     left = first;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       if (j + 1 < M) {
-        node_eval<CURV>(sg, NP, my_first + j + 1, h[j + 1], q[j + 1], rg, k.g, right);
-        if (j + 1 == slot_last) lastnode = right;
+        node_eval<CURV>(sg, NP, (j + 1) * G + gl, h[j + 1], q[j + 1], rg, p.g, right);
+        if (j + 1 == slot_last) { lastK = right.K; lastdKA = right.dKA; lastT = right.T; }
       } else {
-        right = nxt;
+        const int nl = (lane + 1) & 31;
+        right.Q = xw[0 * 32 + nl];  right.A = xw[1 * 32 + nl];  right.T = xw[2 * 32 + nl];
+        right.Y = xw[3 * 32 + nl];  right.Se = xw[4 * 32 + nl]; right.F = xw[5 * 32 + nl];
+        right.QA = xw[6 * 32 + nl]; right.dSeA = xw[7 * 32 + nl]; right.dSeQ = xw[8 * 32 + nl];
       }
       if (j < nc) {
         Cell e;
@@ -246,11 +236,16 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
         PC(buf ^ 1, 0, j) = nC; PC(buf ^ 1, 1, j) = nM; PC(buf ^ 1, 2, j) = nA; PC(buf ^ 1, 3, j) = nS;
         ss += r2;
         if (j == 0) S = e;
-        else merge_cells(S, e, el[j - 1]);
+        else {
+          Elim el;
+          merge_cells(S, e, el);
+          EL(j - 1, 0) = el.i11; EL(j - 1, 1) = el.i12; EL(j - 1, 2) = el.i21; EL(j - 1, 3) = el.i22;
+          EL(j - 1, 4) = el.m1;  EL(j - 1, 5) = el.m2;  EL(j - 1, 6) = el.rm;
+          EL(j - 1, 7) = el.c3;  EL(j - 1, 8) = el.rc;
+        }
       }
       left = right;
     }
-    __syncwarp();
 
     if (init_pass) {   // level-0 constants are now in buf^1
       buf ^= 1;
@@ -262,13 +257,13 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     BcRow U, D;
     U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0;
     D = U;
-    if (is_first) U = bc_eval(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, first);
+    if (is_first) U = bc_eval(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, first.K, first.dKA, first.T);
     if (owns_last) {
       double hl = h[0], ql = q[0];
 #pragma unroll
       for (int j = 1; j < M; ++j)
         if (j == slot_last) { hl = h[j]; ql = q[j]; }
-      D = bc_eval(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, lastnode);
+      D = bc_eval(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, lastK, lastdKA, lastT);
     }
     if (is_first) ss += U.res * U.res;
     if (owns_last) ss += D.res * D.res;
@@ -297,7 +292,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 #pragma unroll
     for (int s = 1; s < G; s <<= 1) {
       if (s > Lc) break;      // uniform: the chain has Lc+1 rows
-      const double idet = 1.0 / (d11 * d22 - d12 * d21);
+      const double idet = fast_rcp(d11 * d22 - d12 * d21);
       const double i11 = d22 * idet, i12 = -d12 * idet, i21 = -d21 * idet, i22 = d11 * idet;
       const int up_src = gl - s, dn_src = gl + s;
       // rows of lane gl-s
@@ -325,7 +320,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
     double dh0, dq0;    // update of this lane's chain node
     {
-      const double idet = 1.0 / (d11 * d22 - d12 * d21);
+      const double idet = fast_rcp(d11 * d22 - d12 * d21);
       dh0 = (d22 * ra - d12 * rb) * idet;
       dq0 = (d11 * rb - d21 * ra) * idet;
     }
@@ -338,11 +333,10 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 #pragma unroll
       for (int j = M - 1; j >= 1; --j) {
         if (j < nc) {                  // node slot j was eliminated by merge j-1
-          const Elim& e = el[j - 1];
-          const double t1 = e.rm - e.m1 * dh0 - e.m2 * dq0;
-          const double t2 = e.rc - e.c3 * rh - e.c4 * rq;
-          dh[j] = e.i11 * t1 + e.i12 * t2;
-          dq[j] = e.i21 * t1 + e.i22 * t2;
+          const double t1 = EL(j - 1, 6) - EL(j - 1, 4) * dh0 - EL(j - 1, 5) * dq0;
+          const double t2 = EL(j - 1, 8) - EL(j - 1, 7) * rh - p.th_dx * rq;
+          dh[j] = EL(j - 1, 0) * t1 + EL(j - 1, 1) * t2;
+          dq[j] = EL(j - 1, 2) * t1 + EL(j - 1, 3) * t2;
           rh = dh[j]; rq = dq[j];
         } else if (j == nc && nc > 0) {  // right end node of a short last lane: it is the chain's last node
           dh[j] = dhR; dq[j] = dqR;
@@ -399,6 +393,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
   }
 #undef PC
+#undef EL
   if (member_valid && is_first) {
     if (p.status) p.status[member] = status;
     if (p.fail_level) p.fail_level[member] = fail_level;

@@ -207,22 +207,23 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
   return PR_OK;
 }
 
-template <int G, int M, bool CURV>
+template <int G, int M, int W, bool CURV>
 int launch_ensemble(const pr::DevParams& p, cudaStream_t s) {
-  constexpr size_t smem = pr::ensemble_smem_bytes<G, M>();
-  auto kern = pr::pr_ensemble_kernel<G, M, CURV>;
+  constexpr size_t smem = pr::ensemble_smem_bytes<G, M, W>();
+  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+  auto kern = pr::pr_ensemble_kernel<G, M, W, CURV>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int per_cta = pr::kWarpsPerCta * (32 / G);
+  const int per_cta = W * (32 / G);
   const unsigned grid = (unsigned)((p.M + per_cta - 1) / per_cta);
-  kern<<<grid, pr::kWarpsPerCta * 32, smem, s>>>(p);
+  kern<<<grid, W * 32, smem, s>>>(p);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return PR_OK;
 }
 
-template <int G, int M>
+template <int G, int M, int W>
 int launch_ensemble_c(const pr::DevParams& p, bool curv, cudaStream_t s) {
-  return curv ? launch_ensemble<G, M, true>(p, s) : launch_ensemble<G, M, false>(p, s);
+  return curv ? launch_ensemble<G, M, W, true>(p, s) : launch_ensemble<G, M, W, false>(p, s);
 }
 
 }  // namespace
@@ -251,6 +252,11 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   std::memset(&p, 0, sizeof p);
   p.N = (int)N; p.L = (int)L; p.M = (int)M; p.max_iter = cfg->max_iter; p.out_mode = cfg->out_mode;
   p.theta = cfg->theta; p.dt = cfg->dt; p.dx = cfg->dx; p.tol = cfg->tol; p.g = cfg->g;
+  p.i2dt = 1.0 / (2.0 * cfg->dt);
+  p.th_dx = cfg->theta / cfg->dx;
+  p.hth = 0.5 * cfg->theta;
+  p.omt_dx = (1.0 - cfg->theta) / cfg->dx;
+  p.homt = 0.5 * (1.0 - cfg->theta);
 
   // host-side look at the few geometry values the dispatch needs
   std::vector<double> curv, zb;
@@ -283,10 +289,11 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   int rc;
   if (cfg->lanes_per_member != 0 && cfg->lanes_per_member != 32)
     return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: this build has the 32-lane instantiations", cfg->lanes_per_member);
-  if (need <= 1) rc = launch_ensemble_c<32, 1>(p, has_curv, s);
-  else if (need <= 2) rc = launch_ensemble_c<32, 2>(p, has_curv, s);
-  else if (need <= 4) rc = launch_ensemble_c<32, 4>(p, has_curv, s);
-  else if (need <= 8) rc = launch_ensemble_c<32, 8>(p, has_curv, s);
+  // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
+  if (need <= 1) rc = launch_ensemble_c<32, 1, 12>(p, has_curv, s);
+  else if (need <= 2) rc = launch_ensemble_c<32, 2, 12>(p, has_curv, s);
+  else if (need <= 4) rc = launch_ensemble_c<32, 4, 12>(p, has_curv, s);
+  else if (need <= 8) rc = launch_ensemble_c<32, 8, 5>(p, has_curv, s);
   else rc = pr::long_reach_run(p, has_curv, s, g_launches, g_err);
   if (rc) return rc;
   cudaError_t e = st.finish();
