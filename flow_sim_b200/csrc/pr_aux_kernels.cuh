@@ -10,6 +10,7 @@ namespace pr {
 struct GvfParams {
   int N, M;
   double dx, g, h_down;
+  double th_dx, hth, th_dx2;   // unused scheme constants node_eval reads (zero)
   DevGeom geo;
   const double* q0;
   long long q0_stride;
@@ -18,11 +19,12 @@ struct GvfParams {
 };
 
 // dh/dx of the gradually-varied-flow equation at one node (get_dh_dx, channel.py:316-347)
-template <bool CURV>
+template <bool CURV, int RM>
 __device__ __forceinline__ double gvf_slope(const double* sg, int NP, int node, double h_in, double Q, double S0,
-                                            const Rough& rg, double g, int& status) {
+                                            const Rough& rg, const GvfParams& p, int& status) {
+  const double g = p.g;
   NodeVals nv;
-  node_eval<CURV>(sg, NP, node, h_in, Q, rg, g, nv);
+  node_eval<CURV, RM, false, GvfParams>(sg, NP, node, h_in, Q, rg, p, nv);
   if (nv.T < 1e-6 || nv.A < 1e-6 || !(h_in > 0.0)) return 0.0;
   const double V = Q / fmax(nv.A, 1e-6), D = nv.A / fmax(nv.T, 1e-6);    // hydraulics.froude_num (:155-168)
   const double Fr = V / sqrt(g * fmax(D, 1e-6));
@@ -32,7 +34,7 @@ __device__ __forceinline__ double gvf_slope(const double* sg, int NP, int node, 
   return (S0 - nv.Se) / den;
 }
 
-template <bool CURV>
+template <bool CURV, int RM>
 __global__ void __launch_bounds__(128) pr_gvf_kernel(const __grid_constant__ GvfParams p) {
   extern __shared__ double smem[];
   const int NP = p.N;
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(128) pr_gvf_kernel(const __grid_constant__ Gvf
   __syncthreads();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= p.M) return;
-  const Rough rg = load_rough(p.geo, m);
+  const Rough rg = load_rough<RM>(p.geo, m);
   const double Q = p.q0[m * p.q0_stride];
   const int N = p.N;
   double* oh = p.ic_h + (size_t)m * N;
@@ -52,10 +54,10 @@ __global__ void __launch_bounds__(128) pr_gvf_kernel(const __grid_constant__ Gvf
   for (int i = N - 2; i >= 0; --i) {
     const double S0 = (smem[F_Z * NP + i] - smem[F_Z * NP + i + 1]) / p.dx;   // channel.py:344
     const double h_down = h;
-    const double s_down = gvf_slope<CURV>(smem, NP, i + 1, h_down, Q, S0, rg, p.g, status);   // predictor
+    const double s_down = gvf_slope<CURV, RM>(smem, NP, i + 1, h_down, Q, S0, rg, p, status);   // predictor
     double h_pred = h_down - s_down * p.dx;
     if (h_pred <= 0.0) h_pred = 0.01;
-    const double s_pred = gvf_slope<CURV>(smem, NP, i, h_pred, Q, S0, rg, p.g, status);       // corrector
+    const double s_pred = gvf_slope<CURV, RM>(smem, NP, i, h_pred, Q, S0, rg, p, status);       // corrector
     double h_up = h_down - 0.5 * (s_down + s_pred) * p.dx;
     if (h_up <= 0.0) h_up = 0.01;
     h = h_up;

@@ -23,7 +23,7 @@ struct DevRating {
   double off, scl;
   // Roseires, collapsed on the host (long double) to two quadratics centred on stage0:
   //   Q_state(s) = q[0] + u*(q[1] + u*q[2]),  u = s - stage0
-  double lo[3], hi[3];
+  double lo[3], hi[3], dlt[3];   // dlt = hi - lo
   double stage0, buffer, inv_buffer, dY, inv_2dY;
 };
 
@@ -46,6 +46,7 @@ struct DevParams {
   int N, L, M, max_iter, out_mode;
   double theta, dt, dx, tol, g;
   double i2dt, th_dx, hth, omt_dx, homt;   // 1/(2dt), theta/dx, theta/2, (1-theta)/dx, (1-theta)/2
+  double ghth, th_dx2;                     // g*theta/2, 2*theta/dx
   DevGeom geo;
   DevBC up, dn;
   const double *ic_h, *ic_q;
@@ -70,16 +71,16 @@ __device__ __forceinline__ double fast_rcp(double a) {
   return r;
 }
 
-__device__ __forceinline__ double fast_sqrt(double a) {   // a >= 0 (0 -> 0)
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+__device__ __forceinline__ double fast_sqrt(double a) {   // a >= 0; sqrt(0) = 0 without a select:
+  double y;                                               // the seed of a + tiny is finite, and 0 * finite = 0
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a + 1e-300));
   double g = a * y, h = 0.5 * y;
   double r = fma(-h, g, 0.5);
   g = fma(g, r, g);
   h = fma(h, r, h);
   r = fma(-h, g, 0.5);
   g = fma(g, r, g);
-  return a > 0.0 ? g : 0.0;
+  return g;
 }
 
 __device__ __forceinline__ double fast_rsqrt(double a) {  // a > 0
@@ -148,24 +149,26 @@ __device__ inline void stage_geometry(const DevGeom& g, int N, int NP, double* s
   }
 }
 
-// Per-member roughness override (model.run(n_main=, n_fp=)); has_* false -> the node's own values.
+// Roughness mode (template parameter RM of the kernels): bit 0 = per-member n_main override,
+// bit 1 = per-member n_fp override (model.run(n_main=, n_fp=)); 0 = the node's own values.
 struct Rough {
-  bool has_nm, has_nfp;
   double nm, inm, cnm, cnfp;    // n_main, 1/n_main, n_main^-1.5, n_fp^-1.5
 };
 
+template <int RM>
 __device__ __forceinline__ Rough load_rough(const DevGeom& g, long long member) {
   Rough rg;
-  rg.has_nm = g.member_nm != nullptr;
-  rg.has_nfp = g.member_nfp != nullptr;
-  rg.nm = rg.has_nm ? g.member_nm[member] : 1.0;
+  rg.nm = (RM & 1) ? g.member_nm[member] : 1.0;
   rg.inm = 1.0 / rg.nm;
   rg.cnm = inv_n15(rg.nm);
-  rg.cnfp = rg.has_nfp ? inv_n15(g.member_nfp[member]) : 1.0;
+  rg.cnfp = (RM & 2) ? inv_n15(g.member_nfp[member]) : 1.0;
   return rg;
 }
 
-// Everything a cell needs from one node at the current iterate.
+__host__ __device__ inline int rough_mode(const DevGeom& g) { return (g.member_nm ? 1 : 0) | (g.member_nfp ? 2 : 0); }
+
+// Everything the two adjacent cells need from one node at the current iterate.  The Jacobian pieces that
+// depend on this node alone are formed here once instead of once per adjacent cell.
 struct NodeVals {
   double Q;     // discharge
   double A;     // wetted area                       (TrapezoidalSection.properties, cross_section.py:623-679)
@@ -174,8 +177,14 @@ struct NodeVals {
   double Se;    // energy slope Sf + Sc              (Channel.Se, channel.py:53-69)
   double F;     // Q^2 / A
   double QA;    // Q / A
-  double dSeA;  // dSe/dA = dSf_dA + dSc_dA (the latter already x dA/dh, quirk 7) (channel.py:71-87)
-  double dSeQ;  // dSe/dQ                            (channel.py:89-105)
+  double w1;    // (theta/dx) (Q/A)^2 T              |d_dQ2Adx_dA * dA_dh|       (preissmann.py:540,546)
+  double w2;    // (theta/2) dSe_dA T                d_avgSe_dA * dA_dh          (:543,547); dSe_dA = dSf_dA + dSc_dA,
+                //                                   the latter already x dA/dh (quirk 7, channel.py:71-87)
+  double w3;    // (theta/2) dSe_dQ                  d_avgSe_dQ                  (:665; channel.py:89-105)
+  double w4;    // 2 (theta/dx) Q/A                  |d_dQ2Adx_dQ|               (:662)
+};
+
+struct NodeConv {
   double K;     // conveyance                        (cross_section.py:741-754)
   double dKA;   // dK/dA                             (cross_section.py:756-764)
 };
@@ -189,9 +198,10 @@ struct NodeVals {
 // One reciprocal of A*P*T yields 1/A and 1/(T P); the over-bank branch needs one more for the
 // floodplain hydraulic radii.  The expensive tail (reciprocal, cube root) is common to all branches, so
 // lanes of a warp that sit on different branches re-converge before it.
-template <bool CURV>
+template <bool CURV, int RM, bool WANT_K = false, class KP = DevParams>
 __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const int NP, const int idx, const double h,
-                                          const double Q, const Rough& rg, const double g, NodeVals& o) {
+                                          const double Q, const Rough& rg, const KP& k, NodeVals& o,
+                                          NodeConv* kc = nullptr) {
 #define GEO(f) sg[(f)*NP + idx]
   const int kind = (int)GEO(F_KIND);
   const double z = GEO(F_Z), b = GEO(F_B);
@@ -226,9 +236,9 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       dPdh = 2.0 * sqfp;
       // K_j^1.5 = A_j*sqrt(A_j) * (A_j/P_j) * n_j^-1.5   (cross_section.py:681-754, hydraulics.py:15-26)
       const double Am = Amf + GEO(F_TB) * dfp;             // conveyance area includes the column (:694)
-      const double cnm = rg.has_nm ? rg.cnm : GEO(F_CNM);
-      const double cnl = rg.has_nfp ? rg.cnfp : GEO(F_CNL);
-      const double cnr = rg.has_nfp ? rg.cnfp : GEO(F_CNR);
+      const double cnm = (RM & 1) ? rg.cnm : GEO(F_CNM);
+      const double cnl = (RM & 2) ? rg.cnfp : GEO(F_CNL);
+      const double cnr = (RM & 2) ? rg.cnfp : GEO(F_CNR);
       const double w = fast_rcp(Pl * Pr);                  // Pl, Pr > 0 because dfp > 0
       X = (Am * Am) * fast_sqrt(Am) * (GEO(F_INVPM) * cnm);
       X = fma((Al * Al) * fast_sqrt(Al), (Pr * w) * cnl, X);
@@ -238,17 +248,14 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
   const double PT = P * T;
   const double u = fast_rcp(A * PT);
   const double invA = u * PT, invTP = u * A;
-  const double nm = rg.has_nm ? rg.nm : GEO(F_NM);
+  const double nm = (RM & 1) ? rg.nm : GEO(F_NM);
   if (!over) X = A * (invTP * T);                          // R = A/P
   const double r = fast_rcbrt(X);
   const double r2 = r * r, r4 = r2 * r2;
-  double K, invK2;
+  double invK2;
   if (over) {
-    K = X * r;
     invK2 = r4;
   } else {
-    const double inm = rg.has_nm ? rg.inm : GEO(F_INVNM);
-    K = A * (X * r) * inm;
     const double na = nm * invA;
     invK2 = (na * na) * r4;
   }
@@ -258,6 +265,11 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
   double Se = Sf;
   double dSeA = -2.0 * Sf * dKA_over_K;                     // hydraulics.py:59-75
   double dSeQ = 2.0 * absQ * invK2;                         // hydraulics.py:77-92
+  double K = 0.0;
+  if (WANT_K || CURV) {
+    const double inm = (RM & 1) ? rg.inm : GEO(F_INVNM);
+    K = over ? X * r : A * (X * r) * inm;
+  }
   if (CURV) {
     const double curv = GEO(F_CURV);
     if (curv != 0.0) {
@@ -269,8 +281,8 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       const double n_eq = (kind == PR_XS_COMPOUND) ? A * (cR * cR) / K : nm;    // cross_section.py:710-739
       const double rc = 1.0 / curv;
       const double V = Q / fmax(A, 1e-6), D = A / fmax(T, 1e-6);
-      const double Fr = V / sqrt(g * fmax(D, 1e-6));
-      const double f = 8.0 * g * (n_eq * n_eq) / cR;        // C = R^(1/6)/n, f = 8g/C^2
+      const double Fr = V / sqrt(k.g * fmax(D, 1e-6));
+      const double f = 8.0 * k.g * (n_eq * n_eq) / cR;      // C = R^(1/6)/n, f = 8g/C^2
       const double sqf = sqrt(f);
       const double lead = 2.86 * sqf + 2.07 * f;
       const double num = lead * (h * h) * (Fr * Fr);
@@ -278,11 +290,11 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       Se += num / den;
       if (fabs(curv) > 1e-12) {
         const double dRA = (P - A * dPdh * invT) * (invP * invP);
-        const double gD = g * (A * invT);
+        const double gD = k.g * (A * invT);
         const double rs = rsqrt(gD);                        // (gD)^-0.5, unclamped (quirk 7)
-        const double dFrA = -0.5 * (Q * invA) * (rs * rs * rs) * g * invT + (-Q * invA * invA) * rs;
+        const double dFrA = -0.5 * (Q * invA) * (rs * rs * rs) * k.g * invT + (-Q * invA * invA) * rs;
         const double dFrQ = invA * rs;
-        const double dfA = -(8.0 / 3.0) * g * (n_eq * n_eq) / (R * cR) * dRA;
+        const double dfA = -(8.0 / 3.0) * k.g * (n_eq * n_eq) / (R * cR) * dRA;
         const double dnumA = (2.86 / (2.0 * sqf) * dfA + 2.07 * dfA) * (h * h) * (Fr * Fr) +
                              lead * (2.0 * h * invT * (Fr * Fr) + (h * h) * 2.0 * Fr * dFrA);
         const double ddenA = (1.0 / (2.0 * sqf) * dfA) * (rc * rc);
@@ -293,17 +305,22 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       }
     }
   }
+  const double QA = Q * invA;
   o.Q = Q;
   o.A = A;
   o.T = T;
   o.Y = hw;
   o.Se = Se;
-  o.QA = Q * invA;
-  o.F = Q * o.QA;
-  o.dSeA = dSeA;
-  o.dSeQ = dSeQ;
-  o.K = K;
-  o.dKA = K * dKA_over_K;
+  o.F = Q * QA;
+  o.QA = QA;
+  o.w1 = (k.th_dx * QA) * (QA * T);
+  o.w2 = (k.hth * dSeA) * T;
+  o.w3 = k.hth * dSeQ;
+  o.w4 = k.th_dx2 * QA;
+  if (WANT_K) {
+    kc->K = K;
+    kc->dKA = K * dKA_over_K;
+  }
 #undef GEO
 }
 
@@ -317,17 +334,13 @@ __device__ __forceinline__ double horner(const double* c, int n, double x) {
 
 __device__ __forceinline__ double roseires_q(const DevRating& r, double stage) {
   // RoseiresRatingCurve.alpha_smooth + effective_release (roseires_rating_curve.py:87-109)
+  // alpha = 0 below stage0, 1 above stage0 + buffer, smoothstep between: clamping s does all three
   const double u = stage - r.stage0;
-  double alpha;
-  if (stage >= r.stage0 + r.buffer) alpha = 1.0;
-  else if (stage <= r.stage0) alpha = 0.0;
-  else {
-    const double s = u * r.inv_buffer;
-    alpha = s * s * (3.0 - 2.0 * s);
-  }
+  const double s = fmin(fmax(u * r.inv_buffer, 0.0), 1.0);
+  const double alpha = s * s * (3.0 - 2.0 * s);
   const double lo = r.lo[0] + u * (r.lo[1] + u * r.lo[2]);
-  const double hi = r.hi[0] + u * (r.hi[1] + u * r.hi[2]);
-  return (1.0 - alpha) * lo + alpha * hi;
+  const double dl = r.dlt[0] + u * (r.dlt[1] + u * r.dlt[2]);
+  return fma(alpha, dl, lo);                                // (1 - alpha) lo + alpha hi
 }
 
 // RatingCurve.discharge (rating_curve.py:32-63)

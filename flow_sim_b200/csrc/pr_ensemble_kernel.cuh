@@ -2,7 +2,7 @@
 //
 // One ensemble member is advanced through ALL time levels by a group of G lanes of one warp
 // (G = 32: one member per warp).  Lane l owns M consecutive nodes (slots) and the M cells to their
-// right, everything in registers / shared memory:
+// right; the state lives in registers, per-warp scratch in shared memory:
 //
 //   per Newton iteration (preissmann.py:122-156)
 //     node pass      each lane evaluates its M nodes (area, top width, conveyance, slopes, derivatives)
@@ -10,7 +10,7 @@
 //                    (preissmann.py:220-301, 407-733); ||R||^2 accumulated on the fly
 //     local solve    the lane condenses its M cells into ONE cell between its first node and the next
 //                    lane's first node by 2x2 Schur complements (block elimination of interior nodes)
-//     chain solve    the G condensed cells + both boundary rows form a 2x2-block tridiagonal system of
+//     chain solve    the condensed cells + both boundary rows form a 2x2-block tridiagonal system of
 //                    <= G block rows, one per lane: parallel cyclic reduction over warp shuffles
 //                    (log2 G steps; off-diagonal blocks are rank-1 and stay rank-1)
 //     back-subst.    interior nodes recovered locally; x += delta; convergence vote = warp-uniform flag
@@ -28,7 +28,7 @@ namespace pr {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// A (possibly condensed) cell between nodes a (left) and b (right):
+// A (possibly condensed) cell between nodes a (left) and b (right), right-hand sides already negated:
 //   C: c1 dh_a + c2 dQ_a + c3 dh_b + c4 dQ_b = rc        M: m1 dh_a + m2 dQ_a + m3 dh_b + m4 dQ_b = rm
 struct Cell {
   double c1, c2, c3, c4, rc;
@@ -65,33 +65,32 @@ __device__ __forceinline__ void merge_cells(Cell& S, const Cell& E, Elim& el) {
 }
 
 // Residuals + Jacobian of one Preissmann cell (left node a, right node b) and the candidate level
-// constants.  pc = {cC, cM, cA, cS} of the stored level; returns R_C^2 + R_M^2.
+// constants.  (cC, cM, cA, cS) are the stored level's contributions; returns R_C^2 + R_M^2.
 __device__ __forceinline__ double cell_assemble(const NodeVals& a, const NodeVals& b, const DevParams& k,
                                                 const double cC, const double cM, const double cA, const double cS,
                                                 Cell& e, double& nC, double& nM, double& nA, double& nS) {
   const double sA = b.A + a.A, dQ = b.Q - a.Q, sQ = b.Q + a.Q, dF = b.F - a.F, dY = b.Y - a.Y, sSe = b.Se + a.Se;
-  // continuity_residual (preissmann.py:220-249): time_diff(A) + spatial_diff(Q)
-  const double RC = sA * k.i2dt + k.th_dx * dQ + cC;
-  // momentum_residual (preissmann.py:251-301)
-  const double avgA = k.hth * sA + cA;                       // cell_avg(A)
-  const double slope = k.th_dx * dY + k.hth * sSe + cS;      // spatial_diff(z+h) + cell_avg(Se)
-  const double RM = sQ * k.i2dt + k.th_dx * dF + cM + k.g * avgA * slope;
+  // continuity_residual (preissmann.py:220-249): R_C = time_diff(A) + spatial_diff(Q);  e.rc = -R_C
+  e.rc = fma(-sA, k.i2dt, fma(-k.th_dx, dQ, -cC));
+  // momentum_residual (preissmann.py:251-301): R_M = time_diff(Q) + spatial_diff(Q^2/A) + g avgA (dYdx + avgSe)
+  const double avgA = fma(k.hth, sA, cA);                              // cell_avg(A)
+  const double slope = fma(k.th_dx, dY, fma(k.hth, sSe, cS));          // spatial_diff(z+h) + cell_avg(Se)
+  const double ga = k.g * avgA;
+  e.rm = fma(-ga, slope, fma(-sQ, k.i2dt, fma(-k.th_dx, dF, -cM)));
   // level-(k) parts for the NEXT level, should this iterate be accepted
-  nC = -sA * k.i2dt + k.omt_dx * dQ;
-  nM = -sQ * k.i2dt + k.omt_dx * dF;
+  nC = fma(-sA, k.i2dt, k.omt_dx * dQ);
+  nM = fma(-sQ, k.i2dt, k.omt_dx * dF);
   nA = k.homt * sA;
-  nS = k.omt_dx * dY + k.homt * sSe;
+  nS = fma(k.omt_dx, dY, k.homt * sSe);
   // dC_* (preissmann.py:407-494)
   e.c1 = a.T * k.i2dt;  e.c2 = -k.th_dx;  e.c3 = b.T * k.i2dt;  e.c4 = k.th_dx;
-  e.rc = -RC;
-  // dM_dh_i / dM_dQ_i / dM_dh_ip1 / dM_dQ_ip1 (preissmann.py:496-733); s = -/+ theta/dx
-  const double ga = k.g * avgA, gs = k.g * k.hth * slope;
-  e.m1 = (k.th_dx * a.QA * a.QA) * a.T + ga * (-k.th_dx + k.hth * a.dSeA * a.T) + gs * a.T;
-  e.m2 = k.i2dt - k.th_dx * 2.0 * a.QA + ga * k.hth * a.dSeQ;
-  e.m3 = (-k.th_dx * b.QA * b.QA) * b.T + ga * (k.th_dx + k.hth * b.dSeA * b.T) + gs * b.T;
-  e.m4 = k.i2dt + k.th_dx * 2.0 * b.QA + ga * k.hth * b.dSeQ;
-  e.rm = -RM;
-  return RC * RC + RM * RM;
+  // dM_dh_i / dM_dQ_i / dM_dh_ip1 / dM_dQ_ip1 (preissmann.py:496-733); spatial_diff(unit) = -/+ theta/dx
+  const double gs = k.ghth * slope;
+  e.m1 = fma(gs, a.T, fma(ga, a.w2 - k.th_dx, a.w1));
+  e.m2 = fma(ga, a.w3, k.i2dt - a.w4);
+  e.m3 = fma(gs, b.T, fma(ga, b.w2 + k.th_dx, -b.w1));
+  e.m4 = fma(ga, b.w3, k.i2dt + b.w4);
+  return fma(e.rc, e.rc, e.rm * e.rm);
 }
 
 template <int G>
@@ -106,15 +105,16 @@ __device__ __forceinline__ double group_sum(double v) {
 //   elimination recs (M-1) x 9 x 32
 //   neighbour exchange 9 x 32         (first-node values handed to the lane on the left)
 // every per-warp array is indexed [..][lane]: consecutive lanes, consecutive doubles, no bank conflicts.
+constexpr int kXch = 9;
 template <int M>
-__host__ __device__ constexpr int warp_smem_doubles() { return 32 * (8 * M + 9 * (M - 1) + 9); }
+__host__ __device__ constexpr int warp_smem_doubles() { return 32 * (8 * M + 9 * (M - 1) + kXch); }
 
 template <int G, int M, int W>
 __host__ __device__ constexpr size_t ensemble_smem_bytes() {
   return sizeof(double) * ((size_t)F_COUNT * G * M + (size_t)W * warp_smem_doubles<M>());
 }
 
-template <int G, int M, int W, bool CURV>
+template <int G, int M, int W, bool CURV, int RM>
 __global__ void __launch_bounds__(W * 32, 1)
 pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ double smem[];
@@ -138,7 +138,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   // chain topology (uniform): lanes 0..Lc hold one block row each
   const int ncells_total = N - 1;
   const int Lc = (ncells_total + M - 1) / M;           // lanes that own at least one cell
-  const int my_first = gl * M;                         // first node slot owned by this lane
+  const int my_first = gl * M;                         // first node owned by this lane
   int nc = ncells_total - my_first;                    // cells owned by this lane
   nc = nc < 0 ? 0 : (nc > M ? M : nc);
   const int owner_last = (N - 1) / M, slot_last = (N - 1) % M;   // where node N-1 lives
@@ -146,7 +146,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   const bool owns_last = (gl == owner_last);
 
   const DevParams& k = p;
-  const Rough rg = load_rough(p.geo, member);
+  const Rough rg = load_rough<RM>(p.geo, member);
 
   // ---- state: initial conditions (Solver.initialize_t0, solver.py:61-63) ----
   double h[M], q[M];
@@ -160,6 +160,13 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       q[j] = iq[nd];
     }
   }
+  // the downstream boundary node's unknowns
+  auto last_node = [&](double& hl, double& ql) {
+    hl = h[0]; ql = q[0];
+#pragma unroll
+    for (int j = 1; j < M; ++j)
+      if (slot_last == j) { hl = h[j]; ql = q[j]; }
+  };
   const size_t out_row = (p.out_mode == PR_OUT_FULL) ? (size_t)N : 1;
   auto store_level = [&](int level, bool nanfill) {
     if (!member_valid) return;
@@ -181,18 +188,26 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   store_level(0, false);
 
   // boundary bookkeeping held by the lane that owns node N-1
-  double q_prev_last = q[slot_last];                                   // flow_at(k=-1, i=-1)
-  double stage_prev = sg[F_Z * NP + slot_last * G + owner_last] + h[slot_last];   // solver.py:101-108
+  double q_prev_last, stage_prev;
+  {
+    double hl, ql;
+    last_node(hl, ql);
+    q_prev_last = ql;                                                   // flow_at(k=-1, i=-1)
+    stage_prev = sg[F_Z * NP + slot_last * G + owner_last] + hl;        // solver.py:101-108
+  }
   if (member_valid && owns_last && p.storage_stage) p.storage_stage[(size_t)member * L] = stage_prev;
+  const bool up_normal = p.up.type == PR_BC_NORMAL_DEPTH, dn_normal = p.dn.type == PR_BC_NORMAL_DEPTH;
 
   int level = 1, it = 0;
   bool active = member_valid && L > 1;
   int status = PR_STATUS_OK, fail_level = 0;
-  int buf = 0;          // which half of the ping-pong holds the stored level's constants
+  int buf = 0;             // which half of the ping-pong holds the stored level's constants
   bool init_pass = true;   // first trip: only builds the level-0 constants from the initial state
   double hyd_up = 0.0, hyd_dn = 0.0;
 
 #define PC(b, c, j) pcw[(((b)*4 + (c)) * M + (j)) * 32 + lane]
+#define EL(j, c) elw[((j)*9 + (c)) * 32 + lane]
+#define XW(c, l) xw[(c)*32 + (l)]
 
   while (__any_sync(kFull, active) || init_pass) {
     if (!init_pass && it == 0) {
@@ -203,38 +218,32 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     if (active && !init_pass) it += 1;
 
     // ------------------------------ node + cell pass ------------------------------
-#define EL(j, c) elw[((j)*9 + (c)) * 32 + lane]
-    NodeVals left, right, first;
-    node_eval<CURV>(sg, NP, gl, h[0], q[0], rg, p.g, first);
+    NodeVals left, right;
+    node_eval<CURV, RM>(sg, NP, gl, h[0], q[0], rg, k, left);
     // hand the first node to the lane on the left: it closes that lane's last cell
     __syncwarp();
-    xw[0 * 32 + lane] = first.Q;  xw[1 * 32 + lane] = first.A;  xw[2 * 32 + lane] = first.T;
-    xw[3 * 32 + lane] = first.Y;  xw[4 * 32 + lane] = first.Se; xw[5 * 32 + lane] = first.F;
-    xw[6 * 32 + lane] = first.QA; xw[7 * 32 + lane] = first.dSeA; xw[8 * 32 + lane] = first.dSeQ;
+    XW(0, lane) = left.Q;  XW(1, lane) = left.A;  XW(2, lane) = left.T;  XW(3, lane) = left.Y;  XW(4, lane) = left.Se;
+    XW(5, lane) = left.F;  XW(6, lane) = left.QA; XW(7, lane) = left.w2; XW(8, lane) = left.w3;
     __syncwarp();
 
     double ss = 0.0;
     Cell S;                     // condensed cell of this lane
-    double lastK = first.K, lastdKA = first.dKA, lastT = first.T;   // node N-1 (normal-depth boundary)
-    left = first;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       if (j + 1 < M) {
-        node_eval<CURV>(sg, NP, (j + 1) * G + gl, h[j + 1], q[j + 1], rg, p.g, right);
-        if (j + 1 == slot_last) { lastK = right.K; lastdKA = right.dKA; lastT = right.T; }
+        node_eval<CURV, RM>(sg, NP, (j + 1) * G + gl, h[j + 1], q[j + 1], rg, k, right);
       } else {
         const int nl = (lane + 1) & 31;
-        right.Q = xw[0 * 32 + nl];  right.A = xw[1 * 32 + nl];  right.T = xw[2 * 32 + nl];
-        right.Y = xw[3 * 32 + nl];  right.Se = xw[4 * 32 + nl]; right.F = xw[5 * 32 + nl];
-        right.QA = xw[6 * 32 + nl]; right.dSeA = xw[7 * 32 + nl]; right.dSeQ = xw[8 * 32 + nl];
+        right.Q = XW(0, nl);  right.A = XW(1, nl);  right.T = XW(2, nl);  right.Y = XW(3, nl);  right.Se = XW(4, nl);
+        right.F = XW(5, nl);  right.QA = XW(6, nl); right.w2 = XW(7, nl); right.w3 = XW(8, nl);
+        right.w1 = (k.th_dx * right.QA) * (right.QA * right.T);
+        right.w4 = k.th_dx2 * right.QA;
       }
       if (j < nc) {
         Cell e;
         double nC, nM, nA, nS;
-        const double r2 = cell_assemble(left, right, k, PC(buf, 0, j), PC(buf, 1, j), PC(buf, 2, j), PC(buf, 3, j), e,
-                                        nC, nM, nA, nS);
+        ss += cell_assemble(left, right, k, PC(buf, 0, j), PC(buf, 1, j), PC(buf, 2, j), PC(buf, 3, j), e, nC, nM, nA, nS);
         PC(buf ^ 1, 0, j) = nC; PC(buf ^ 1, 1, j) = nM; PC(buf ^ 1, 2, j) = nA; PC(buf ^ 1, 3, j) = nS;
-        ss += r2;
         if (j == 0) S = e;
         else {
           Elim el;
@@ -257,16 +266,30 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     BcRow U, D;
     U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0;
     D = U;
-    if (is_first) U = bc_eval(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, first.K, first.dKA, first.T);
-    if (owns_last) {
-      double hl = h[0], ql = q[0];
-#pragma unroll
-      for (int j = 1; j < M; ++j)
-        if (j == slot_last) { hl = h[j]; ql = q[j]; }
-      D = bc_eval(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, lastK, lastdKA, lastT);
+    if (is_first) {
+      NodeConv kc = {0.0, 0.0};
+      double T0 = 0.0;
+      if (up_normal) {     // conveyance of the boundary node is only needed by the normal-depth condition
+        NodeVals t;
+        node_eval<CURV, RM, true>(sg, NP, gl, h[0], q[0], rg, k, t, &kc);
+        T0 = t.T;
+      }
+      U = bc_eval(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, kc.K, kc.dKA, T0);
     }
-    if (is_first) ss += U.res * U.res;
-    if (owns_last) ss += D.res * D.res;
+    if (owns_last) {
+      double hl, ql;
+      last_node(hl, ql);
+      NodeConv kc = {0.0, 0.0};
+      double T0 = 0.0;
+      if (dn_normal) {
+        NodeVals t;
+        node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
+        T0 = t.T;
+      }
+      D = bc_eval(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, kc.K, kc.dKA, T0);
+    }
+    if (is_first) ss = fma(U.res, U.res, ss);
+    if (owns_last) ss = fma(D.res, D.res, ss);
     const double err = sqrt(group_sum<G>(ss));                  // utility.euclidean_norm (utility.py:20-22)
 
     // ------------------------------ chain rows ------------------------------
@@ -289,12 +312,14 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       else { d21 = 0.0; d22 = 1.0; u1 = 0.0; u2 = 0.0; rb = 0.0; }
     }
     // ------------------------------ parallel cyclic reduction ------------------------------
+    // Rows whose partner lies outside the chain have a zero coupling (l = 0 / u = 0) by construction, and
+    // every lane (rows beyond the chain are identity rows) holds finite data, so no guards are needed.
 #pragma unroll
     for (int s = 1; s < G; s <<= 1) {
       if (s > Lc) break;      // uniform: the chain has Lc+1 rows
       const double idet = fast_rcp(d11 * d22 - d12 * d21);
       const double i11 = d22 * idet, i12 = -d12 * idet, i21 = -d21 * idet, i22 = d11 * idet;
-      const int up_src = gl - s, dn_src = gl + s;
+      const int up_src = (gl - s) & (G - 1), dn_src = (gl + s) & (G - 1);
       // rows of lane gl-s
       const double P_i11 = __shfl_sync(kFull, i11, up_src, G), P_i12 = __shfl_sync(kFull, i12, up_src, G);
       const double P_i21 = __shfl_sync(kFull, i21, up_src, G), P_i22 = __shfl_sync(kFull, i22, up_src, G);
@@ -307,9 +332,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       const double N_l1 = __shfl_sync(kFull, l1, dn_src, G), N_l2 = __shfl_sync(kFull, l2, dn_src, G);
       const double N_u1 = __shfl_sync(kFull, u1, dn_src, G), N_u2 = __shfl_sync(kFull, u2, dn_src, G);
       const double N_ra = __shfl_sync(kFull, ra, dn_src, G), N_rb = __shfl_sync(kFull, rb, dn_src, G);
-      double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
-      if (up_src >= 0) { a1 = l1 * P_i11 + l2 * P_i21; a2 = l1 * P_i12 + l2 * P_i22; }   // [l1 l2] * Dinv(P)
-      if (dn_src < G) { b1 = u1 * N_i11 + u2 * N_i21; b2 = u1 * N_i12 + u2 * N_i22; }    // [u1 u2] * Dinv(N)
+      const double a1 = l1 * P_i11 + l2 * P_i21, a2 = l1 * P_i12 + l2 * P_i22;   // [l1 l2] * Dinv(P)
+      const double b1 = u1 * N_i11 + u2 * N_i21, b2 = u1 * N_i12 + u2 * N_i22;   // [u1 u2] * Dinv(N)
       // row a -= a1*rowa(P) + a2*rowb(P) ; row b -= b1*rowa(N) + b2*rowb(N)
       l1 = -a1 * P_l1;  l2 = -a1 * P_l2;
       d11 -= a2 * P_u1; d12 -= a2 * P_u2;
@@ -356,10 +380,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
           if (p.final_error) p.final_error[(size_t)member * (L - 1) + (level - 1)] = err;
         }
         if (owns_last) {
-          double ql = q[0];
-#pragma unroll
-          for (int j = 1; j < M; ++j)
-            if (j == slot_last) ql = q[j];
+          double hl, ql;
+          last_node(hl, ql);
           q_prev_last = ql;
           if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE) {
             stage_prev = D.stage_rec;
@@ -394,10 +416,44 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   }
 #undef PC
 #undef EL
+#undef XW
   if (member_valid && is_first) {
     if (p.status) p.status[member] = status;
     if (p.fail_level) p.fail_level[member] = fail_level;
   }
 }
+
+// Launch of one nodes-per-lane family (all CURV x RM variants); defined in pr_ensemble_m<M>.cu so that the
+// instantiations compile in parallel.  Returns a cudaError_t as int.
+template <int M, int W>
+int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
+
+#define PR_DEFINE_ENSEMBLE_FAMILY(M_, W_)                                                                    \
+  namespace pr {                                                                                             \
+  template <bool CURV, int RM>                                                                               \
+  static int launch_one_##M_(const DevParams& p, cudaStream_t s) {                                           \
+    constexpr size_t smem = ensemble_smem_bytes<32, M_, W_>();                                               \
+    static_assert(smem <= 227 * 1024, "shared memory budget exceeded");                                      \
+    auto kern = pr_ensemble_kernel<32, M_, W_, CURV, RM>;                                                    \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return (int)e;                                                                     \
+    const unsigned grid = (unsigned)((p.M + W_ - 1) / W_);                                                   \
+    kern<<<grid, W_ * 32, smem, s>>>(p);                                                                     \
+    return (int)cudaGetLastError();                                                                          \
+  }                                                                                                          \
+  template <bool CURV>                                                                                       \
+  static int launch_rm_##M_(const DevParams& p, cudaStream_t s) {                                            \
+    switch (rough_mode(p.geo)) {                                                                             \
+      case 0: return launch_one_##M_<CURV, 0>(p, s);                                                         \
+      case 1: return launch_one_##M_<CURV, 1>(p, s);                                                         \
+      case 2: return launch_one_##M_<CURV, 2>(p, s);                                                         \
+      default: return launch_one_##M_<CURV, 3>(p, s);                                                        \
+    }                                                                                                        \
+  }                                                                                                          \
+  template <>                                                                                                \
+  int launch_ensemble_family<M_, W_>(const DevParams& p, bool curv, cudaStream_t s) {                        \
+    return curv ? launch_rm_##M_<true>(p, s) : launch_rm_##M_<false>(p, s);                                  \
+  }                                                                                                          \
+  }
 
 }  // namespace pr

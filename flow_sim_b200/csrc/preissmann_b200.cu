@@ -95,7 +95,7 @@ int fetch(const double* p, size_t n, int mem, std::vector<double>& out) {
 }
 
 // Roseires: Q_state(s) = sum_{o_j>0} spill(s,o_j) + n_sl*sluice(s,twl) + q_hydro, as a quadratic in u = s - stage0
-void collapse_roseires(const pr_rating& r, const double* openings, int sluices, double out[3]) {
+void collapse_roseires(const pr_rating& r, const double* openings, int sluices, long double out[3]) {
   long double k0 = r.q_hydro, k1 = 0, k2 = 0;
   const long double s0 = r.stage0;
   auto add = [&](const double c[6], long double o, long double w) {
@@ -108,7 +108,7 @@ void collapse_roseires(const pr_rating& r, const double* openings, int sluices, 
   for (int j = 0; j < r.n_gates; ++j)
     if (openings[j] > 0) add(r.spill, openings[j], 1.0L);
   add(r.sluice, r.twl, (long double)sluices);
-  out[0] = (double)k0; out[1] = (double)k1; out[2] = (double)k2;
+  out[0] = k0; out[1] = k1; out[2] = k2;
 }
 
 int make_rating(const pr_rating& r, pr::DevRating& d) {
@@ -124,8 +124,10 @@ int make_rating(const pr_rating& r, pr::DevRating& d) {
   if (r.type == PR_RC_ROSEIRES) {
     if (r.n_gates < 0 || r.n_gates > PR_MAX_GATES) return fail(PR_ERR_ARG, "rating: n_gates=%d out of range", r.n_gates);
     if (!(r.buffer > 0) || !(r.dY > 0)) return fail(PR_ERR_ARG, "rating: Roseires buffer and dY must be positive");
-    collapse_roseires(r, r.closed_state, r.sluices_closed, d.lo);
-    collapse_roseires(r, r.open_state, r.sluices_open, d.hi);
+    long double lo[3], hi[3];
+    collapse_roseires(r, r.closed_state, r.sluices_closed, lo);
+    collapse_roseires(r, r.open_state, r.sluices_open, hi);
+    for (int i = 0; i < 3; ++i) { d.lo[i] = (double)lo[i]; d.hi[i] = (double)hi[i]; d.dlt[i] = (double)(hi[i] - lo[i]); }
     d.stage0 = r.stage0; d.buffer = r.buffer; d.inv_buffer = 1.0 / r.buffer;
     d.dY = r.dY; d.inv_2dY = 1.0 / (2 * r.dY);
   }
@@ -207,23 +209,29 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
   return PR_OK;
 }
 
-template <int G, int M, int W, bool CURV>
-int launch_ensemble(const pr::DevParams& p, cudaStream_t s) {
-  constexpr size_t smem = pr::ensemble_smem_bytes<G, M, W>();
-  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
-  auto kern = pr::pr_ensemble_kernel<G, M, W, CURV>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int per_cta = W * (32 / G);
-  const unsigned grid = (unsigned)((p.M + per_cta - 1) / per_cta);
-  kern<<<grid, W * 32, smem, s>>>(p);
+int launch_family(int rc_cuda) {
+  if (rc_cuda != 0) return fail(PR_ERR_CUDA, "ensemble kernel launch: %s", cudaGetErrorString((cudaError_t)rc_cuda));
+  g_launches.fetch_add(1);
+  return PR_OK;
+}
+
+template <bool CURV, int RM>
+int launch_gvf(const pr::GvfParams& p, unsigned grid, size_t smem, cudaStream_t s) {
+  CUDA_TRY(cudaFuncSetAttribute(pr::pr_gvf_kernel<CURV, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pr::pr_gvf_kernel<CURV, RM><<<grid, 128, smem, s>>>(p);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return PR_OK;
 }
 
-template <int G, int M, int W>
-int launch_ensemble_c(const pr::DevParams& p, bool curv, cudaStream_t s) {
-  return curv ? launch_ensemble<G, M, W, true>(p, s) : launch_ensemble<G, M, W, false>(p, s);
+template <bool CURV>
+int launch_gvf_rm(const pr::GvfParams& p, unsigned grid, size_t smem, cudaStream_t s) {
+  switch (pr::rough_mode(p.geo)) {
+    case 0: return launch_gvf<CURV, 0>(p, grid, smem, s);
+    case 1: return launch_gvf<CURV, 1>(p, grid, smem, s);
+    case 2: return launch_gvf<CURV, 2>(p, grid, smem, s);
+    default: return launch_gvf<CURV, 3>(p, grid, smem, s);
+  }
 }
 
 }  // namespace
@@ -257,6 +265,8 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   p.hth = 0.5 * cfg->theta;
   p.omt_dx = (1.0 - cfg->theta) / cfg->dx;
   p.homt = 0.5 * (1.0 - cfg->theta);
+  p.ghth = cfg->g * 0.5 * cfg->theta;
+  p.th_dx2 = 2.0 * cfg->theta / cfg->dx;
 
   // host-side look at the few geometry values the dispatch needs
   std::vector<double> curv, zb;
@@ -290,10 +300,10 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   if (cfg->lanes_per_member != 0 && cfg->lanes_per_member != 32)
     return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: this build has the 32-lane instantiations", cfg->lanes_per_member);
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
-  if (need <= 1) rc = launch_ensemble_c<32, 1, 12>(p, has_curv, s);
-  else if (need <= 2) rc = launch_ensemble_c<32, 2, 12>(p, has_curv, s);
-  else if (need <= 4) rc = launch_ensemble_c<32, 4, 12>(p, has_curv, s);
-  else if (need <= 8) rc = launch_ensemble_c<32, 8, 5>(p, has_curv, s);
+  if (need <= 1) rc = launch_family(pr::launch_ensemble_family<1, 12>(p, has_curv, s));
+  else if (need <= 2) rc = launch_family(pr::launch_ensemble_family<2, 12>(p, has_curv, s));
+  else if (need <= 4) rc = launch_family(pr::launch_ensemble_family<4, 12>(p, has_curv, s));
+  else if (need <= 8) rc = launch_family(pr::launch_ensemble_family<8, 5>(p, has_curv, s));
   else rc = pr::long_reach_run(p, has_curv, s, g_launches, g_err);
   if (rc) return rc;
   cudaError_t e = st.finish();
@@ -327,15 +337,7 @@ int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const d
   const size_t smem = sizeof(double) * pr::F_COUNT * N;
   if (smem > 200 * 1024) return fail(PR_ERR_UNSUPPORTED, "GVF initial conditions: n_nodes=%zu exceeds the shared-memory geometry stage", N);
   const unsigned grid = (unsigned)((M + 127) / 128);
-  if (has_curv) {
-    CUDA_TRY(cudaFuncSetAttribute(pr::pr_gvf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pr::pr_gvf_kernel<true><<<grid, 128, smem, s>>>(p);
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(pr::pr_gvf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pr::pr_gvf_kernel<false><<<grid, 128, smem, s>>>(p);
-  }
-  g_launches.fetch_add(1);
-  CUDA_TRY(cudaGetLastError());
+  if (int rc = has_curv ? launch_gvf_rm<true>(p, grid, smem, s) : launch_gvf_rm<false>(p, grid, smem, s)) return rc;
   cudaError_t e = st.finish();
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_gvf_initial_conditions: %s", cudaGetErrorString(e));
   return PR_OK;
