@@ -94,3 +94,41 @@ class EnsembleRunner:
 def to_host(res: dict) -> dict:
     """Device results -> numpy (one synchronising copy per array)."""
     return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
+
+
+# -------------------------------------------------------------------------------------------------
+# Multi-GPU: members are independent, so the ensemble is cut into contiguous blocks, one per rank
+# (one process per GPU), with no traffic inside the time loop and ONE collective at the end
+# (SURVEY.md 8e).  The helpers below hold the host-side logic; they are backend-agnostic
+# (NCCL on GPUs, gloo in the CPU tests).
+# -------------------------------------------------------------------------------------------------
+
+def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
+    """[first, last) of the contiguous member block owned by `rank`; the first total % world ranks get one more."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, extra = divmod(total, world)
+    first = rank * base + min(rank, extra)
+    return first, first + base + (1 if rank < extra else 0)
+
+
+def gather_members(local, total: int, rank: int, world: int):
+    """All ranks receive the per-member array of the whole ensemble, in member order.
+    `local` is this rank's block ([m_local, ...] torch tensor on the backend's device)."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    sizes = [shard_bounds(total, r, world) for r in range(world)]
+    counts = [b - a for a, b in sizes]
+    if len(set(counts)) == 1:
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+    pad = max(counts)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)

@@ -1,0 +1,52 @@
+"""``LumpedStorage`` (lumped_storage.py:7-179): 0-D reservoir behind the downstream node.
+
+The device path implements the constant-surface-area form without outflow rating curve or head losses
+(the only form a shipped case uses, cases/example/main.py:42-43); the area-curve / outflow / loss variants
+are recorded here so that ``flatten`` can reject them explicitly.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class LumpedStorage:
+    def __init__(self, solution_boundaries, surface_area=None, min_stage=None, rating_curve=None):
+        self.rating_curve = rating_curve
+        self.surface_area = surface_area
+        self.min_stage = min_stage
+        self.stage_hydrograph = []
+        self.area_curve = None
+        self.reservoir_length = None
+        self.capture_losses = False
+        self.Cc = 0.5
+        self.K_q = 0
+        if solution_boundaries is not None:
+            self.Y_min, self.Y_max = solution_boundaries[0], solution_boundaries[1]
+
+    def set_area_curve(self, table, alpha=1, beta=0, update_solution_boundaries=True):
+        self.alpha, self.beta = alpha, beta
+        self.area_curve = np.asarray(table, dtype=np.float64)
+        self.area_gradient = np.gradient(self.area_curve[:, 1], self.area_curve[:, 0])
+        if update_solution_boundaries:
+            self.Y_min = np.min(self.area_curve[:, 0])
+            self.Y_max = np.max(self.area_curve[:, 0])
+
+    def area_at(self, stage):
+        if self.area_curve is None:
+            return self.surface_area
+        return self.alpha * np.interp(stage + self.beta, self.area_curve[:, 0], self.area_curve[:, 1])
+
+    def net_vol_change(self, Y1, Y2):
+        if self.area_curve is None:
+            return (Y2 - Y1) * self.surface_area
+        step = np.min(np.abs(np.diff(self.area_curve[:, 0])))
+        n = int(abs(Y2 - Y1) / step)
+        if n > 2:
+            ys = np.linspace(Y1, Y2, n)
+            return np.trapezoid([self.area_at(y) for y in ys], ys)
+        return 0.5 * (self.area_at(Y2) + self.area_at(Y1)) * (Y2 - Y1)
+
+    def energy_loss(self, entry_area, flow, roughness, hydraulic_radius, A_str=None):
+        if not self.capture_losses:
+            return 0
+        raise NotImplementedError("capture_losses=True (head losses) is not on the device path (SURVEY.md 8f-3)")

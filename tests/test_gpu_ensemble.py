@@ -1,0 +1,183 @@
+"""GPU tests of the ensemble path through the C ABI: per-member roughness / inflow / initial conditions,
+device-side GVF profile and objective, independence of members, boundary-condition and section coverage,
+edge cases (smallest grids, single level, non-convergence) - each against the CPU oracle on identical inputs."""
+import copy
+
+import numpy as np
+import pytest
+
+import util
+from flow_sim_b200 import abi
+from flow_sim_b200.runner import gvf_initial_conditions, rating_objective, run_flat
+
+pytestmark = pytest.mark.gpu
+
+Q_QUERY = [1562.5, 3850, 6000, 10000, 14000, 21000]
+H_TARGET = [497.5, 500, 502, 505, 507, 510]
+
+
+def _check(flat, M, what, out_mode=abi.PR_OUT_FULL, rtol=util.RTOL):
+    import oracle_py
+
+    ora = oracle_py.run(flat, n_members=M, out_mode=out_mode)
+    out = run_flat(flat, n_members=M, out_mode=out_mode)
+    assert np.array_equal(out["status"], ora["status"]), what
+    assert np.array_equal(np.isnan(out["depth"]), np.isnan(ora["depth"])), f"{what}: NaN fill differs"
+    fin = ~np.isnan(ora["depth"])
+    util.assert_parity(out["depth"][fin], out["flow"][fin], ora["depth"][fin], ora["flow"][fin], what, rtol)
+    assert np.array_equal(out["iters"], ora["iters"]), f"{what}: Newton iteration counts differ"
+    assert np.array_equal(out["fail_level"], ora["fail_level"])
+    return out, ora
+
+
+def test_roughness_ensemble_with_device_gvf_and_objective():
+    """256 members of the config-4 grid: GVF kernel, Newton kernel and objective kernel against the oracle."""
+    import oracle_py
+
+    flat = util.golden_inputs("gerd_calib_m0")
+    M = 256
+    flat.member_n_main = 0.020 + 0.040 * np.arange(M) / (M - 1)
+    h, q, st = gvf_initial_conditions(flat, M, flat.meta["initial_flow"], flat.meta["downstream_depth"])
+    ho, qo, sto = oracle_py.gvf(flat, flat.meta["initial_flow"], flat.meta["downstream_depth"], n_members=M)
+    assert np.array_equal(st, sto) and not st.any()
+    assert util.max_rel(h, ho) <= 1e-12 and np.array_equal(q, qo)
+    flat.ic_depth, flat.ic_flow = ho, qo            # identical initial state for both solvers
+    out, ora = _check(flat, M, "roughness ensemble", out_mode=abi.PR_OUT_UPSTREAM)
+    lv, rm = rating_objective(flat.n_levels, out["flow"], out["depth"], flat.meta["z0"], Q_QUERY, H_TARGET)
+    lvo, rmo = oracle_py.objective(flat.n_levels, ora["flow"], ora["depth"], flat.meta["z0"], Q_QUERY, H_TARGET)
+    assert util.max_rel(lv, lvo) <= util.RTOL and util.max_rel(rm, rmo) <= util.RTOL
+    # the reference's own numbers for the two ends of the grid
+    assert abs(rm[0] - 5.847778566618879) <= 1e-9 * 5.85 and abs(rm[-1] - 1.7408210264943833) <= 1e-9 * 1.75
+
+
+def test_members_are_independent_of_batch_composition():
+    """A member's result must not depend on which other members share its launch, CTA or batch position:
+    this is what makes 1/2/4/8-GPU sharding bit-identical."""
+    flat = util.golden_inputs("gerd_calib_m0")
+    n = 0.020 + 0.040 * np.arange(64) / 63
+    f = copy.copy(flat); f.member_n_main = n
+    h, q, _ = gvf_initial_conditions(f, 64, flat.meta["initial_flow"], flat.meta["downstream_depth"])
+    f.ic_depth, f.ic_flow = h, q
+    full = run_flat(f, n_members=64, out_mode=abi.PR_OUT_UPSTREAM)
+    perm = np.random.default_rng(0).permutation(64)[:13]
+    g = copy.copy(flat); g.member_n_main = n[perm]; g.ic_depth, g.ic_flow = h[perm], q[perm]
+    part = run_flat(g, n_members=13, out_mode=abi.PR_OUT_UPSTREAM)
+    for key in ("depth", "flow", "iters", "status"):
+        assert np.array_equal(part[key], full[key][perm]), key
+
+
+def test_host_and_device_memory_paths_agree():
+    import torch
+
+    flat = util.golden_inputs("gerd_calib_m21845")
+    host = run_flat(flat, mem=abi.PR_MEM_HOST)
+    dev = run_flat(flat, mem=abi.PR_MEM_DEVICE, device="cuda:0")
+    for key in ("depth", "flow", "iters", "status"):
+        assert np.array_equal(host[key], dev[key].cpu().numpy()), key
+    assert isinstance(dev["depth"], torch.Tensor) and dev["depth"].is_cuda
+
+
+def test_inflow_scenarios_and_floodplain_roughness_per_member():
+    """Per-member upstream hydrographs [M, levels] and an n_fp override."""
+    flat = util.golden_inputs("gerd_calib_m30000")
+    M = 6
+    scale = np.linspace(0.8, 1.1, M)[:, None]
+    base = flat.up.series[None, :]
+    flat.up.series = base[:, :1] + (base - base[:, :1]) * scale        # same initial flow, scaled wave
+    flat.member_n_fp = np.linspace(0.04, 0.07, M)
+    _check(flat, M, "inflow scenarios + n_fp")
+
+
+def _prismatic(kind="rect", down="normal_depth", up="flow_hydrograph", n_nodes=12, levels=8, rating=None):
+    """Small synthetic reach built on the mirror API."""
+    from math import pi, sin
+
+    from flow_sim_b200.flatten import flatten_solver
+    from flow_sim_b200.hydromodel import Boundary, Channel, Hydrograph, PreissmannSolver, TrapezoidalSection
+
+    L, S0, dt = 1000.0 * (n_nodes - 1), 0.0005, 1800
+    wave = lambda t: 60 + 40 * sin(pi * min(t, 6 * dt) / (6 * dt)) ** 2
+    if up == "flow_hydrograph":
+        us = Boundary("flow_hydrograph", chainage=0, bed_level=S0 * L, initial_depth=2.0, hydrograph=Hydrograph(wave))
+    else:
+        us = Boundary("stage_hydrograph", chainage=0, bed_level=S0 * L, initial_depth=2.0,
+                      hydrograph=Hydrograph(lambda t: S0 * L + 2.0 + 0.3 * sin(pi * min(t, 6 * dt) / (6 * dt)) ** 2))
+    kw = dict(rating_curve=rating) if down == "rating_curve" else {}
+    ds = Boundary(down, chainage=L, bed_level=0.0, initial_depth=2.0, **kw)
+    ch = Channel(us, ds, initial_flow=60.0, roughness=0.03, width=30.0, interpolation_method="linear")
+    if kind != "rect":
+        mk = lambda z: TrapezoidalSection(z_bed=z, b_main=20.0, m_main=1.5, n_main=0.03, bed_slope=S0,
+                                          **(dict(z_bank=z + 1.6, b_fp_left=15.0, b_fp_right=5.0, m_fp=3.0, n_left=0.05,
+                                                  n_right=0.06) if kind == "compound" else {}))
+        ch.set_cross_sections([0.0, L], [mk(S0 * L), mk(0.0)])
+    s = PreissmannSolver(channel=ch, theta=0.6, time_step=dt, spatial_step=1000.0, simulation_time=(levels - 1) * dt)
+    return flatten_solver(s, tolerance=1e-6, max_iter=60)
+
+
+@pytest.mark.parametrize("kind", ["rect", "trapezoid", "compound"])
+@pytest.mark.parametrize("down", ["normal_depth", "fixed_depth"])
+def test_section_kinds_and_simple_boundaries(kind, down):
+    _check(_prismatic(kind=kind, down=down), 1, f"{kind}/{down}")
+
+
+def test_stage_hydrograph_upstream():
+    _check(_prismatic(kind="trapezoid", up="stage_hydrograph"), 1, "stage hydrograph")
+
+
+@pytest.mark.parametrize("form", ["polynomial", "power", "fitted"])
+def test_rating_curve_forms(form):
+    from flow_sim_b200.hydromodel import RatingCurve
+
+    rc = RatingCurve()
+    if form == "polynomial":
+        rc.set("polynomial", a=6.0, b=9.0, c=18.0, stage_shift=0.0)
+    elif form == "power":
+        rc.set("power", a=21.0, b=1.55, stage_shift=0.0)
+    else:
+        st = np.linspace(0.5, 4.0, 9)
+        rc.fit(discharges=21.0 * st ** 1.55, stages=st, stage_shift=0.0, type="polynomial", scale=True, degree=3)
+    _check(_prismatic(kind="rect", down="rating_curve", rating=rc), 1, f"rating {form}")
+
+
+@pytest.mark.parametrize("n_nodes", [2, 3, 33, 34, 63, 125, 126, 249])
+def test_grid_sizes_across_nodes_per_lane_families(n_nodes):
+    """N = 2 (one cell) up to 249 (the largest reach the fused kernel takes: 8 nodes per lane), including sizes
+    where the last node is interior to a lane."""
+    _check(_prismatic(kind="compound", n_nodes=n_nodes, levels=4), 1, f"N={n_nodes}")
+
+
+def test_single_level_run_returns_initial_state():
+    flat = _prismatic(levels=1)
+    out = run_flat(flat)
+    assert np.array_equal(out["depth"][0, 0], flat.ic_depth) and out["status"][0] == 0
+
+
+def test_non_convergence_is_reported_per_member_not_raised():
+    """max_iter exhausted -> status 1 with the failing level, NaN-filled remainder; the healthy member next to it
+    is unaffected (preissmann.py:124-126 raises for a single run)."""
+    flat = util.golden_inputs("gerd_calib_m0")
+    flat.max_iter = 11                      # level 3 needs 11, level 6 needs 12 iterations for n = 0.020
+    flat.member_n_main = np.array([0.020, 0.020])
+    out, ora = _check(flat, 2, "max_iter")
+    assert out["status"].tolist() == [abi.PR_STATUS_MAX_ITER] * 2 and out["fail_level"][0] == 6
+    assert np.isnan(out["depth"][0, 6:]).all() and not np.isnan(out["depth"][0, :6]).any()
+    assert out["iters"][0, 5] == 11 and not out["iters"][0, 6:].any()
+
+
+def test_mirror_solver_run_matches_reference_golden():
+    """The drop-in surface: PreissmannSolver.run() on the mirror objects, result attributes as in the reference."""
+    from flow_sim_b200.cases import build_example
+
+    ref = util.golden_outputs("example")
+    solver, kw = build_example()
+    solver.run(verbose=0, **kw)
+    util.assert_parity(solver.depth, solver.flow, ref["depth"], ref["flow"], "mirror example")
+    assert np.array_equal(solver.iterations, ref["iters"])
+    assert util.max_rel(solver.storage_stage, ref["storage_stage"]) <= util.RTOL
+    assert solver.level.shape == solver.depth.shape == (25, 21)
+    for name in ("area", "top_width", "froude_number", "velocity", "wave_celerity", "amplitude", "peak_amplitude",
+                 "storage_outflow"):
+        assert np.all(np.isfinite(getattr(solver, name)))
+    solver2, kw = build_example()
+    with pytest.raises(ValueError, match="Convergence within 5 iterations couldn't be achieved."):
+        solver2.run(verbose=0, tolerance=1e-4, max_iter=5)

@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference API (flow_sim_b200.hydromodel) and the case builders: the flattened
+inputs they produce must be bit-identical to those flattened from the reference's own objects
+(tests/golden/*.in.npz, made in the build container by oracle/make_golden.py)."""
+import sys
+
+import numpy as np
+import pytest
+
+import util
+from flow_sim_b200 import abi, hydromodel
+from flow_sim_b200.cases import build_akbari, build_example, build_gerd
+from flow_sim_b200.cases import akbari_firoozi, gerd_roseires
+from flow_sim_b200.flatten import flatten_solver, load_flat, save_flat
+
+
+def _same_flat(a, b):
+    assert (a.n_nodes, a.n_levels, a.theta, a.dt, a.dx, a.tol, a.max_iter, a.g) == \
+           (b.n_nodes, b.n_levels, b.theta, b.dt, b.dx, b.tol, b.max_iter, b.g)
+    for k in a.geom:
+        assert np.array_equal(a.geom[k], b.geom[k]), f"geometry field {k}"
+    assert np.array_equal(a.ic_depth, b.ic_depth) and np.array_equal(a.ic_flow, b.ic_flow)
+    for x, y in ((a.up, b.up), (a.down, b.down)):
+        assert x.type == y.type
+        for f in ("bed_level", "bed_slope", "fixed_depth", "storage_area", "storage_min_stage", "storage_ymin", "storage_ymax"):
+            u, v = getattr(x, f), getattr(y, f)
+            assert u == v or (u != u and v != v), f
+        assert (x.series is None) == (y.series is None)
+        if x.series is not None:
+            assert np.array_equal(x.series, y.series)
+        assert (x.rating is None) == (y.rating is None)
+        if x.rating:
+            for k, v in x.rating.items():
+                assert np.array_equal(np.asarray(v, float), np.asarray(y.rating[k], float)), f"rating {k}"
+
+
+@pytest.mark.parametrize("case,builder", [
+    ("example", lambda: build_example()),
+    ("akbari", lambda: build_akbari()),
+    ("akbari_long", lambda: build_akbari(length=200000, spatial_step=100, time_step=600, duration=16 * 600, theta=0.6)),
+    ("gerd_calib_m0", lambda: build_gerd(n_main=util.calib_n(0), calibration=True)),
+    ("gerd_calib_m36408", lambda: build_gerd(n_main=util.calib_n(36408), calibration=True)),
+    ("gerd_full", lambda: build_gerd()),
+])
+def test_case_builders_reproduce_reference_inputs(case, builder):
+    solver, kw = builder()
+    flat = flatten_solver(solver, tolerance=kw.get("tolerance", 1e-4), max_iter=kw.get("max_iter", 100))
+    _same_flat(util.golden_inputs(case), flat)
+
+
+def test_flat_roundtrip(tmp_path):
+    solver, kw = build_gerd(n_main=0.03, calibration=True)
+    flat = flatten_solver(solver, tolerance=kw["tolerance"])
+    p = str(tmp_path / "c.npz")
+    save_flat(p, flat)
+    _same_flat(flat, load_flat(p))
+    assert load_flat(p).meta["downstream_depth"] == flat.meta["downstream_depth"]
+
+
+def test_grid_sizing_matches_reference_rules():
+    """N = round(L/dx)+1, dx = L/(N-1), levels = T//dt + 1 (solver.py:34-35,53-55)."""
+    s, _ = build_gerd(calibration=True)
+    assert s.number_of_nodes == 121 and s.number_of_time_levels == 33
+    assert s.spatial_step == s.channel.length / 120
+    s, _ = build_example()
+    assert (s.number_of_nodes, s.number_of_time_levels) == (21, 25)
+    assert s.depth.shape == (25, 21) and s.depth.flags["C_CONTIGUOUS"] and s.depth.dtype == np.float64
+
+
+def test_unsupported_configurations_are_rejected_not_emulated():
+    s, _ = build_example()
+    s.regularization = True
+    with pytest.raises(NotImplementedError):
+        flatten_solver(s)
+    s, _ = build_example()
+    s.channel.downstream_boundary.lumped_storage.capture_losses = True
+    with pytest.raises(NotImplementedError):
+        flatten_solver(s)
+
+    class Irregular:          # stands for the reference's IrregularSection (no trapezoid attributes)
+        z_min = 0.0
+
+    s, _ = build_example()
+    s.channel.xs_at_node[3] = Irregular()
+    with pytest.raises(NotImplementedError, match="TrapezoidalSection"):
+        flatten_solver(s)
+    s, _ = build_gerd(calibration=True)
+    s.channel.downstream_boundary.rating_curve.smooth = False
+    with pytest.raises(NotImplementedError):
+        flatten_solver(s)
+    with pytest.raises(ValueError, match="Invalid boundary condition"):
+        hydromodel.Boundary(condition="weir", chainage=0)
+    with pytest.raises(ValueError, match="Invalid interpolation method"):
+        hydromodel.Channel(hydromodel.Boundary("fixed_depth", 0, 0, 1), hydromodel.Boundary("fixed_depth", 10, 0, 1), 1.0,
+                           interpolation_method="spline")
+
+
+def test_install_registers_reference_import_names():
+    hydromodel.install()
+    from src.hydromodel.channel import Channel            # the import lines of cases/example/main.py:1-5
+    from src.hydromodel.preissmann import PreissmannSolver
+    import hydromodel as hm
+
+    assert Channel is hydromodel.Channel and PreissmannSolver is hydromodel.PreissmannSolver and hm is hydromodel
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.") or k.startswith("hydromodel")]:
+        del sys.modules[k]
+
+
+def test_roseires_fit_and_gate_state():
+    rc = gerd_roseires.RoseiresRatingCurve(initial_stage=487.0, initial_flow=2094.106301)
+    # one fully open spillway, a partial opening that rounds to 0.0 and therefore contributes nothing
+    # (quirk 10, roseires_rating_curve.py:167-173), no sluice
+    assert rc.closed_state == ([13, 0.0, 0, 0, 0, 0, 0], 0)
+    assert rc.open_state == ([13] * 7, 5)
+    assert abs(rc.discharge(487.0) - 2090.155184) < 1e-5      # low_release_rating_curve.csv, Y = 487
+    assert abs(rc.discharge(487.5) - rc.release(487.5, rc.open_state)) < 1e-9
+
+
+def test_long_reach_builder_shapes():
+    s, _ = akbari_firoozi.build_long_reach(n_nodes=501, n_steps=4)
+    assert s.number_of_nodes == 501 and s.number_of_time_levels == 5
+    assert np.allclose(s.channel.initial_conditions[:, 0], s.channel.initial_conditions[0, 0])
