@@ -1,17 +1,482 @@
-// pr_long_kernels.cuh - long-reach path (N > 249 nodes: state does not fit one warp's registers).
+// pr_long_kernels.cuh - long-reach path (N > 249 nodes: one member no longer fits one warp's registers).
+//
+// State (current iterate, level constants) lives in HBM; a reach is cut into TILES of 128 cells, one warp per
+// (member, tile), lane l owning 4 consecutive cells exactly as in the fused kernel.  One Newton iteration of
+// ALL members is three launches:
+//
+//   K1  pr_long_tile<CONDENSE>   per tile: node pass, cell pass, per-lane Schur condensation, warp tree-merge
+//                                -> ONE condensed cell per tile (10 doubles) + partial ||R||^2
+//   K2  pr_long_chain            per member (one warp): the <= 32*Kc tile cells + both boundary rows:
+//                                serial condensation per lane, parallel cyclic reduction, back-substitution
+//                                -> update of every tile-boundary node; convergence test, level/iteration
+//                                bookkeeping (the member's state machine lives here)
+//   K3  pr_long_tile<UPDATE>     per tile: re-assemble (recomputing is cheaper than storing 9 doubles per
+//                                node), solve the tile interior with its two end nodes known, x += delta;
+//                                when the level was accepted also write the stored level and refresh the
+//                                level constants
+//
+// Same algebra as pr_ensemble_kernel.cuh (cell_assemble / merge_cells / PCR); block cyclic reduction is
+// applied hierarchically: lane (4 cells) -> tile (32 lanes) -> chain (<= 32 x Kc tiles).
+// Algorithmic HBM traffic is 48 B per node per Newton iteration; this first version moves
+// 112 B (iterate read twice + 4 level constants per cell read twice + iterate written).
 #pragma once
 #include <atomic>
 #include <string>
+#include <vector>
 
-#include "pr_device.cuh"
+#include "pr_ensemble_kernel.cuh"
 
 namespace pr {
 
-inline int long_reach_run(const DevParams& p, bool, cudaStream_t, std::atomic<long long>&, std::string& err) {
-  char buf[160];
-  snprintf(buf, sizeof buf, "n_nodes=%d: the long-reach (multi-CTA block cyclic reduction) path is not built yet", p.N);
-  err = buf;
-  return PR_ERR_UNSUPPORTED;
+constexpr int kTileCells = 128;    // 32 lanes x 4 cells
+constexpr int kLongM = 4;
+constexpr int kChainMaxK = 64;     // tile cells per lane in the chain kernel -> N <= 32*64*128 + 1
+
+struct LongParams {
+  DevParams p;
+  const double* geo;   // derived geometry table [F_COUNT][N] (stage_geometry layout, NP = N)
+  double *xh, *xq;     // current iterate [M][N]
+  double* pc;          // level constants [M][4][N]
+  double* tcell;       // condensed tile cells [M][T][10]
+  double* dchain;      // updates of the tile-boundary nodes [M][T+1][2]
+  double* err2;        // [M] partial ||R||^2 (tiles)
+  int *level, *it, *active, *conv, *out_level;   // [M] per-member state machine
+  double *qprev_last, *stage_prev;               // [M] boundary bookkeeping
+  int* n_done;         // members finished so far
+  int T, Kc;
+};
+
+enum LongMode { LONG_INIT = 0, LONG_CONDENSE = 1, LONG_UPDATE = 2 };
+
+__global__ void pr_long_geometry(DevGeom g, int N, double* table) {
+  stage_geometry(g, N, N, table, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, [](int i) { return i; });
+}
+
+// PCR over the 32 lanes of a warp for block rows  [l | d | u] y = r  with rank-1 couplings (see the fused kernel).
+__device__ __forceinline__ void pcr32(double& l1, double& l2, double& d11, double& d12, double& d21, double& d22,
+                                      double& u1, double& u2, double& ra, double& rb, const int rows, const int lane,
+                                      double& y1, double& y2) {
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    if (s >= rows) break;
+    const double idet = fast_rcp(d11 * d22 - d12 * d21);
+    const double i11 = d22 * idet, i12 = -d12 * idet, i21 = -d21 * idet, i22 = d11 * idet;
+    const int up = (lane - s) & 31, dn = (lane + s) & 31;
+#define SH(v, src) __shfl_sync(kFull, v, src)
+    const double a1 = l1 * SH(i11, up) + l2 * SH(i21, up), a2 = l1 * SH(i12, up) + l2 * SH(i22, up);
+    const double b1 = u1 * SH(i11, dn) + u2 * SH(i21, dn), b2 = u1 * SH(i12, dn) + u2 * SH(i22, dn);
+    const double Pl1 = SH(l1, up), Pl2 = SH(l2, up), Pu1 = SH(u1, up), Pu2 = SH(u2, up), Pra = SH(ra, up), Prb = SH(rb, up);
+    const double Nl1 = SH(l1, dn), Nl2 = SH(l2, dn), Nu1 = SH(u1, dn), Nu2 = SH(u2, dn), Nra = SH(ra, dn), Nrb = SH(rb, dn);
+#undef SH
+    l1 = -a1 * Pl1;  l2 = -a1 * Pl2;
+    d11 -= a2 * Pu1; d12 -= a2 * Pu2;
+    ra -= a1 * Pra + a2 * Prb;
+    u1 = -b2 * Nu1;  u2 = -b2 * Nu2;
+    d21 -= b1 * Nl1; d22 -= b1 * Nl2;
+    rb -= b1 * Nra + b2 * Nrb;
+  }
+  const double idet = fast_rcp(d11 * d22 - d12 * d21);
+  y1 = (d22 * ra - d12 * rb) * idet;
+  y2 = (d11 * rb - d21 * ra) * idet;
+}
+
+__device__ __forceinline__ Cell shfl_cell(const Cell& c, int src) {
+  Cell o;
+  o.c1 = __shfl_sync(kFull, c.c1, src); o.c2 = __shfl_sync(kFull, c.c2, src); o.c3 = __shfl_sync(kFull, c.c3, src);
+  o.c4 = __shfl_sync(kFull, c.c4, src); o.rc = __shfl_sync(kFull, c.rc, src);
+  o.m1 = __shfl_sync(kFull, c.m1, src); o.m2 = __shfl_sync(kFull, c.m2, src); o.m3 = __shfl_sync(kFull, c.m3, src);
+  o.m4 = __shfl_sync(kFull, c.m4, src); o.rm = __shfl_sync(kFull, c.rm, src);
+  return o;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ LongParams q) {
+  const DevParams& p = q.p;
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)p.M * q.T) return;
+  const int m = (int)(w / q.T), t = (int)(w % q.T);
+  if (!q.active[m]) return;
+  const int N = p.N;
+  const int conv = (MODE == LONG_UPDATE) ? q.conv[m] : 0;
+  const int c0 = t * kTileCells + lane * kLongM;        // first cell / node of this lane
+  int nc = (N - 1) - c0;
+  nc = nc < 0 ? 0 : (nc > kLongM ? kLongM : nc);
+  const Rough rg = load_rough<0>(p.geo, 0);
+  double* xh = q.xh + (size_t)m * N;
+  double* xq = q.xq + (size_t)m * N;
+  double* pc = q.pc + (size_t)m * 4 * N;
+
+  double h[kLongM + 1], qq[kLongM + 1];
+#pragma unroll
+  for (int j = 0; j <= kLongM; ++j) {
+    const int nd = c0 + j < N ? c0 + j : N - 1;
+    h[j] = xh[nd];
+    qq[j] = xq[nd];
+  }
+  NodeVals nv[2];
+  node_eval<false, 0>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
+  double ss = 0.0;
+  Cell S;
+  Elim el[kLongM - 1];
+  double cand[kLongM][4];
+#pragma unroll
+  for (int j = 0; j < kLongM; ++j) {
+    const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
+    node_eval<false, 0>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
+    if (j < nc) {
+      const int c = c0 + j;
+      Cell e;
+      double cC = 0, cM = 0, cA = 0, cS = 0;
+      if (MODE != LONG_INIT) { cC = pc[c]; cM = pc[N + c]; cA = pc[2 * N + c]; cS = pc[3 * N + c]; }
+      ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, cC, cM, cA, cS, e, cand[j][0], cand[j][1], cand[j][2], cand[j][3]);
+      if (j == 0) S = e;
+      else merge_cells(S, e, el[j - 1]);
+    }
+  }
+
+  if (MODE == LONG_INIT) {
+    // level 0: store the initial state and build its level constants
+#pragma unroll
+    for (int j = 0; j < kLongM; ++j)
+      if (j < nc) { const int c = c0 + j; pc[c] = cand[j][0]; pc[N + c] = cand[j][1]; pc[2 * N + c] = cand[j][2]; pc[3 * N + c] = cand[j][3]; }
+    return;
+  }
+
+  if (MODE == LONG_CONDENSE) {
+    // warp tree-merge of the per-lane cells -> one cell for the tile
+    int cnt = nc;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const Cell R = shfl_cell(S, (lane + s) & 31);
+      const int rcnt = __shfl_sync(kFull, cnt, (lane + s) & 31);
+      if ((lane & (2 * s - 1)) == 0 && lane + s < 32 && rcnt > 0) {
+        if (cnt > 0) { Elim dummy; merge_cells(S, R, dummy); }
+        else S = R;
+        cnt += rcnt;
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(kFull, ss, s);
+    if (lane == 0) {
+      double* tc = q.tcell + ((size_t)m * q.T + t) * 10;
+      tc[0] = S.c1; tc[1] = S.c2; tc[2] = S.c3; tc[3] = S.c4; tc[4] = S.rc;
+      tc[5] = S.m1; tc[6] = S.m2; tc[7] = S.m3; tc[8] = S.m4; tc[9] = S.rm;
+      atomicAdd(q.err2 + m, ss);
+    }
+    return;
+  }
+
+  // ---------------- LONG_UPDATE: tile interior with both end nodes known ----------------
+  const double* dc = q.dchain + ((size_t)m * (q.T + 1) + t) * 2;
+  const double yL1 = dc[0], yL2 = dc[1], yR1 = dc[2], yR2 = dc[3];   // first node of this tile / of the next
+  const int lanes = (N - 1 - t * kTileCells + kLongM - 1) / kLongM;  // lanes of this tile that own cells
+  const int Lt = lanes < 32 ? lanes : 32;
+  double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
+  {
+    const Cell Pv = shfl_cell(S, (lane - 1) & 31);
+    if (lane == 0 || lane >= Lt) { l1 = l2 = 0.0; d11 = 1.0; d12 = 0.0; ra = (lane == 0) ? yL1 : 0.0; }
+    else { l1 = Pv.m1; l2 = Pv.m2; d11 = Pv.m3; d12 = Pv.m4; ra = Pv.rm; }
+    if (lane == 0 || lane >= Lt) { d21 = 0.0; d22 = 1.0; u1 = u2 = 0.0; rb = (lane == 0) ? yL2 : 0.0; }
+    else if (lane == Lt - 1) { d21 = S.c1; d22 = S.c2; u1 = u2 = 0.0; rb = S.rc - S.c3 * yR1 - S.c4 * yR2; }
+    else { d21 = S.c1; d22 = S.c2; u1 = S.c3; u2 = S.c4; rb = S.rc; }
+  }
+  double dh0, dq0;
+  pcr32(l1, l2, d11, d12, d21, d22, u1, u2, ra, rb, Lt, lane, dh0, dq0);
+  double dhR = __shfl_sync(kFull, dh0, (lane + 1) & 31), dqR = __shfl_sync(kFull, dq0, (lane + 1) & 31);
+  if (lane == Lt - 1 || lane == 31) { dhR = yR1; dqR = yR2; }
+  double dh[kLongM], dq[kLongM];
+  dh[0] = dh0; dq[0] = dq0;
+  {
+    double rh = dhR, rq = dqR;
+#pragma unroll
+    for (int j = kLongM - 1; j >= 1; --j) {
+      if (j < nc) {
+        const Elim& e = el[j - 1];
+        const double t1 = e.rm - e.m1 * dh0 - e.m2 * dq0;
+        const double t2 = e.rc - e.c3 * rh - p.th_dx * rq;
+        dh[j] = e.i11 * t1 + e.i12 * t2;
+        dq[j] = e.i21 * t1 + e.i22 * t2;
+        rh = dh[j]; rq = dq[j];
+      } else { dh[j] = 0.0; dq[j] = 0.0; }
+    }
+  }
+  // nodes written by this lane: its own cells' left nodes; the very last node N-1 is written by the lane whose
+  // last cell ends there
+  const int lvl = q.out_level[m];
+  const size_t orow = ((size_t)m * p.L + lvl) * (size_t)N;
+#pragma unroll
+  for (int j = 0; j < kLongM; ++j) {
+    if (j < nc) {
+      const int nd = c0 + j;
+      if (conv) {
+        if (p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[j]; if (p.out_q) p.out_q[orow + nd] = qq[j]; }
+        const int c = nd;
+        pc[c] = cand[j][0]; pc[N + c] = cand[j][1]; pc[2 * N + c] = cand[j][2]; pc[3 * N + c] = cand[j][3];
+      }
+      xh[nd] = h[j] + dh[j];
+      xq[nd] = qq[j] + dq[j];
+    }
+  }
+  if (nc > 0 && c0 + nc == N - 1) {      // this lane's last cell ends at the downstream boundary node
+    const int nd = N - 1;
+    if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[nc]; if (p.out_q) p.out_q[orow + nd] = qq[nc]; }
+    xh[nd] = h[nc] + yR1;
+    xq[nd] = qq[nc] + yR2;
+  }
+  if (conv && p.out_mode == PR_OUT_UPSTREAM && t == 0 && lane == 0) {
+    if (p.out_h) p.out_h[(size_t)m * p.L + lvl] = h[0];
+    if (p.out_q) p.out_q[(size_t)m * p.L + lvl] = qq[0];
+  }
+}
+
+// One warp per member: chain of tile cells + boundary rows, convergence and bookkeeping.
+// Shared memory per warp: Kc-1 elimination records x 10 doubles x 32 lanes.
+__global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ LongParams q) {
+  extern __shared__ double rec[];
+  const DevParams& p = q.p;
+  const int m = blockIdx.x, lane = threadIdx.x;
+  if (!q.active[m]) return;
+  const int N = p.N, L = p.L, T = q.T, Kc = q.Kc;
+  const int level = q.level[m];
+  const int it = q.it[m] + 1;
+  const double* xh = q.xh + (size_t)m * N;
+  const double* xq = q.xq + (size_t)m * N;
+  const Rough rg = load_rough<0>(p.geo, 0);
+#define REC(j, c) rec[((j)*10 + (c)) * 32 + lane]
+  // ---- per-lane serial condensation of Kc tile cells ----
+  const int t0 = lane * Kc;
+  int nt = T - t0;
+  nt = nt < 0 ? 0 : (nt > Kc ? Kc : nt);
+  Cell S;
+  for (int j = 0; j < nt; ++j) {
+    const double* tc = q.tcell + ((size_t)m * T + t0 + j) * 10;
+    Cell e;
+    e.c1 = tc[0]; e.c2 = tc[1]; e.c3 = tc[2]; e.c4 = tc[3]; e.rc = tc[4];
+    e.m1 = tc[5]; e.m2 = tc[6]; e.m3 = tc[7]; e.m4 = tc[8]; e.rm = tc[9];
+    if (j == 0) S = e;
+    else {
+      // generic merge record: the eliminated node sits between two CONDENSED cells, so c4 is not a constant
+      const double c4 = e.c4;
+      Elim el;
+      merge_cells(S, e, el);
+      REC(j - 1, 0) = el.i11; REC(j - 1, 1) = el.i12; REC(j - 1, 2) = el.i21; REC(j - 1, 3) = el.i22;
+      REC(j - 1, 4) = el.m1; REC(j - 1, 5) = el.m2; REC(j - 1, 6) = el.rm;
+      REC(j - 1, 7) = el.c3; REC(j - 1, 8) = el.rc; REC(j - 1, 9) = c4;
+    }
+  }
+  const int Lc = (T + Kc - 1) / Kc;      // lanes with tile cells; chain rows 0..Lc
+  // ---- boundary rows ----
+  BcRow U, D;
+  U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0;
+  D = U;
+  const double hyd_up = p.up.series ? p.up.series[(size_t)m * p.up.series_stride + level] : 0.0;
+  const double hyd_dn = p.dn.series ? p.dn.series[(size_t)m * p.dn.series_stride + level] : 0.0;
+  if (lane == 0) {
+    NodeVals nvb; NodeConv kc = {0.0, 0.0};
+    node_eval<false, 0, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
+    U = bc_eval(p.up, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, kc.K, kc.dKA, nvb.T);
+  }
+  if (lane == Lc) {
+    NodeVals nvb; NodeConv kc = {0.0, 0.0};
+    node_eval<false, 0, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
+    D = bc_eval(p.dn, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, kc.K, kc.dKA, nvb.T);
+  }
+  const double Ures = __shfl_sync(kFull, U.res, 0), Dres = __shfl_sync(kFull, D.res, Lc);
+  const double err = sqrt(q.err2[m] + Ures * Ures + Dres * Dres);
+  // ---- chain rows + PCR ----
+  double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
+  {
+    const Cell Pv = shfl_cell(S, (lane - 1) & 31);
+    if (lane == 0) { l1 = l2 = 0.0; d11 = U.dh; d12 = U.dq; ra = -U.res; }
+    else if (lane <= Lc) { l1 = Pv.m1; l2 = Pv.m2; d11 = Pv.m3; d12 = Pv.m4; ra = Pv.rm; }
+    else { l1 = l2 = 0.0; d11 = 1.0; d12 = 0.0; ra = 0.0; }
+    if (lane < Lc) { d21 = S.c1; d22 = S.c2; u1 = S.c3; u2 = S.c4; rb = S.rc; }
+    else if (lane == Lc) { d21 = D.dh; d22 = D.dq; u1 = u2 = 0.0; rb = -D.res; }
+    else { d21 = 0.0; d22 = 1.0; u1 = u2 = 0.0; rb = 0.0; }
+  }
+  double y1, y2;
+  pcr32(l1, l2, d11, d12, d21, d22, u1, u2, ra, rb, Lc + 1, lane, y1, y2);
+  const double yR1 = __shfl_sync(kFull, y1, (lane + 1) & 31), yR2 = __shfl_sync(kFull, y2, (lane + 1) & 31);
+  // ---- back-substitution over the lane's tile boundaries; write the chain-node updates ----
+  double* dc = q.dchain + (size_t)m * (T + 1) * 2;
+  if (lane <= Lc) {
+    const int node0 = lane < Lc ? t0 : T;      // chain node index of this lane's row (row Lc = last node)
+    dc[2 * node0] = y1; dc[2 * node0 + 1] = y2;
+  }
+  {
+    double rh = yR1, rq = yR2;
+    for (int j = nt - 1; j >= 1; --j) {
+      const double t1 = REC(j - 1, 6) - REC(j - 1, 4) * y1 - REC(j - 1, 5) * y2;
+      const double t2 = REC(j - 1, 8) - REC(j - 1, 7) * rh - REC(j - 1, 9) * rq;
+      const double a = REC(j - 1, 0) * t1 + REC(j - 1, 1) * t2;
+      const double b = REC(j - 1, 2) * t1 + REC(j - 1, 3) * t2;
+      dc[2 * (t0 + j)] = a; dc[2 * (t0 + j) + 1] = b;
+      rh = a; rq = b;
+    }
+  }
+#undef REC
+  // ---- the member's state machine (preissmann.py:122-161) ----
+  if (lane == 0) {
+    const bool converged = err < p.tol;
+    q.err2[m] = 0.0;
+    q.conv[m] = converged ? 1 : 0;
+    q.out_level[m] = level;
+    if (converged) {
+      if (p.iters) p.iters[(size_t)m * (L - 1) + (level - 1)] = it;
+      if (p.final_error) p.final_error[(size_t)m * (L - 1) + (level - 1)] = err;
+      q.it[m] = 0;
+      q.level[m] = level + 1;
+    } else {
+      q.it[m] = it;
+      if (it >= p.max_iter) {
+        if (p.iters) p.iters[(size_t)m * (L - 1) + (level - 1)] = it;
+        if (p.final_error) p.final_error[(size_t)m * (L - 1) + (level - 1)] = err;
+        if (p.status) p.status[m] = (err == err) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
+        if (p.fail_level) p.fail_level[m] = level;
+        q.active[m] = 2;           // failed: K3 of this iteration is skipped by the host-side finaliser
+        atomicAdd(q.n_done, 1);
+      }
+    }
+  }
+  if (lane == Lc) {
+    const bool converged = err < p.tol;
+    if (converged) {
+      q.qprev_last[m] = xq[N - 1];
+      if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE) {
+        q.stage_prev[m] = D.stage_rec;
+        if (p.storage_stage) p.storage_stage[(size_t)m * L + level] = D.stage_rec;
+      }
+    }
+  }
+}
+
+// After K3: retire members whose last level was just accepted.
+__global__ void pr_long_retire(const __grid_constant__ LongParams q) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= q.p.M) return;
+  if (q.active[m] == 1 && q.level[m] >= q.p.L) { q.active[m] = 0; atomicAdd(q.n_done, 1); }
+  if (q.active[m] == 2) q.active[m] = 0;
+}
+
+__global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
+  const DevParams& p = q.p;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.M * p.N;
+  if (i >= total) return;
+  const int m = (int)(i / p.N), nd = (int)(i % p.N);
+  const double h = p.ic_h[(size_t)m * p.ic_stride + nd], qv = p.ic_q[(size_t)m * p.ic_stride + nd];
+  q.xh[i] = h; q.xq[i] = qv;
+  if (p.out_mode == PR_OUT_FULL) {
+    if (p.out_h) p.out_h[(size_t)m * p.L * p.N + nd] = h;
+    if (p.out_q) p.out_q[(size_t)m * p.L * p.N + nd] = qv;
+  } else if (nd == 0) {
+    if (p.out_h) p.out_h[(size_t)m * p.L] = h;
+    if (p.out_q) p.out_q[(size_t)m * p.L] = qv;
+  }
+  if (nd == p.N - 1) {
+    q.qprev_last[m] = qv;
+    const double st = q.geo[F_Z * p.N + nd] + h;
+    q.stage_prev[m] = st;
+    if (p.storage_stage) p.storage_stage[(size_t)m * p.L] = st;
+    q.level[m] = 1; q.it[m] = 0; q.conv[m] = 0; q.out_level[m] = 0; q.err2[m] = 0.0;
+    q.active[m] = p.L > 1 ? 1 : 0;
+    if (p.status) p.status[m] = PR_STATUS_OK;
+    if (p.fail_level) p.fail_level[m] = 0;
+  }
+}
+
+// NaN-fill the levels a failed member never reached.
+__global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
+  const DevParams& p = q.p;
+  const int m = blockIdx.y;
+  if (!p.status || p.status[m] == PR_STATUS_OK) return;
+  const int fl = p.fail_level[m];
+  const size_t row = (p.out_mode == PR_OUT_FULL) ? (size_t)p.N : 1;
+  const size_t n = (size_t)(p.L - fl) * row;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = ((size_t)m * p.L + fl) * row + i;
+    if (p.out_h) p.out_h[o] = nan("");
+    if (p.out_q) p.out_q[o] = nan("");
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int k = fl + 1; k < p.L; ++k) {
+      if (p.iters) p.iters[(size_t)m * (p.L - 1) + (k - 1)] = 0;
+      if (p.final_error) p.final_error[(size_t)m * (p.L - 1) + (k - 1)] = nan("");
+    }
+    if (p.storage_stage) for (int k = fl; k < p.L; ++k) p.storage_stage[(size_t)m * p.L + k] = nan("");
+  }
+}
+
+inline int long_reach_run(const DevParams& p, bool has_curv, cudaStream_t s, std::atomic<long long>& launches,
+                          std::string& err) {
+  auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
+  if (has_curv) return fail(PR_ERR_UNSUPPORTED, "long-reach path: centre-line curvature is not supported");
+  if (p.geo.member_nm || p.geo.member_nfp)
+    return fail(PR_ERR_UNSUPPORTED, "long-reach path: per-member roughness overrides are not supported");
+  const int N = p.N, M = p.M;
+  const int T = (N - 1 + kTileCells - 1) / kTileCells;
+  const int Kc = (T + 30) / 31;           // tile cells per lane so that the chain has <= 32 rows
+  if (Kc > kChainMaxK) return fail(PR_ERR_UNSUPPORTED, "long-reach path: n_nodes exceeds 32*64*128");
+  LongParams q;
+  q.p = p;
+  q.T = T; q.Kc = Kc;
+  std::vector<void*> allocs;
+  cudaError_t e = cudaSuccess;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* d = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&d, bytes);
+    if (e == cudaSuccess) allocs.push_back(d);
+    return d;
+  };
+  double* geo = (double*)dalloc(sizeof(double) * F_COUNT * (size_t)N);
+  q.geo = geo;
+  q.xh = (double*)dalloc(sizeof(double) * (size_t)M * N);
+  q.xq = (double*)dalloc(sizeof(double) * (size_t)M * N);
+  q.pc = (double*)dalloc(sizeof(double) * (size_t)M * 4 * N);
+  q.tcell = (double*)dalloc(sizeof(double) * (size_t)M * T * 10);
+  q.dchain = (double*)dalloc(sizeof(double) * (size_t)M * (T + 1) * 2);
+  q.err2 = (double*)dalloc(sizeof(double) * M);
+  q.qprev_last = (double*)dalloc(sizeof(double) * M);
+  q.stage_prev = (double*)dalloc(sizeof(double) * M);
+  q.level = (int*)dalloc(sizeof(int) * M); q.it = (int*)dalloc(sizeof(int) * M);
+  q.active = (int*)dalloc(sizeof(int) * M); q.conv = (int*)dalloc(sizeof(int) * M);
+  q.out_level = (int*)dalloc(sizeof(int) * M);
+  q.n_done = (int*)dalloc(sizeof(int));
+  auto cleanup = [&]() { for (void* d : allocs) cudaFree(d); };
+  if (e != cudaSuccess) { cleanup(); return fail(PR_ERR_CUDA, std::string("long-reach workspace: ") + cudaGetErrorString(e)); }
+  cudaMemsetAsync(q.n_done, 0, sizeof(int), s);
+  cudaMemsetAsync(q.active, 0, sizeof(int) * M, s);
+
+  pr_long_geometry<<<(N + 255) / 256, 256, 0, s>>>(p.geo, N, geo);
+  const long long total = (long long)M * N;
+  pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
+  const long long warps = (long long)M * T;
+  const unsigned tile_grid = (unsigned)((warps + 3) / 4);
+  pr_long_tile<LONG_INIT><<<tile_grid, 128, 0, s>>>(q);
+  launches.fetch_add(3);
+  const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
+  e = cudaFuncSetAttribute(pr_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
+  int done = (p.L > 1) ? 0 : M;
+  const long long max_trips = (long long)(p.L - 1) * (p.max_iter > 0 ? p.max_iter : 1) + 1;
+  for (long long trip = 0; trip < max_trips && done < M && e == cudaSuccess; ++trip) {
+    pr_long_tile<LONG_CONDENSE><<<tile_grid, 128, 0, s>>>(q);
+    pr_long_chain<<<M, 32, chain_smem, s>>>(q);
+    pr_long_tile<LONG_UPDATE><<<tile_grid, 128, 0, s>>>(q);
+    pr_long_retire<<<(M + 127) / 128, 128, 0, s>>>(q);
+    launches.fetch_add(4);
+    e = cudaMemcpyAsync(&done, q.n_done, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  if (e == cudaSuccess) {
+    pr_long_nanfill<<<dim3(64, M), 256, 0, s>>>(q);
+    launches.fetch_add(1);
+    e = cudaStreamSynchronize(s);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) return fail(PR_ERR_CUDA, std::string("long-reach path: ") + cudaGetErrorString(e));
+  return PR_OK;
 }
 
 }  // namespace pr

@@ -297,10 +297,11 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   // nodes per lane: smallest M with ceil((N-1)/M) + 1 <= 32 chain rows
   const int need = (int)((N - 1 + 30) / 31);      // ceil((N-1)/31)
   int rc;
-  if (cfg->lanes_per_member != 0 && cfg->lanes_per_member != 32)
+  if (cfg->lanes_per_member != 0 && cfg->lanes_per_member != 32 && cfg->lanes_per_member != -1)
     return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: this build has the 32-lane instantiations", cfg->lanes_per_member);
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
-  if (need <= 1) rc = launch_family(pr::launch_ensemble_family<1, 12>(p, has_curv, s));
+  if (cfg->lanes_per_member == -1) rc = pr::long_reach_run(p, has_curv, s, g_launches, g_err);   // forced long-reach path
+  else if (need <= 1) rc = launch_family(pr::launch_ensemble_family<1, 12>(p, has_curv, s));
   else if (need <= 2) rc = launch_family(pr::launch_ensemble_family<2, 12>(p, has_curv, s));
   else if (need <= 4) rc = launch_family(pr::launch_ensemble_family<4, 12>(p, has_curv, s));
   else if (need <= 8) rc = launch_family(pr::launch_ensemble_family<8, 5>(p, has_curv, s));

@@ -1,0 +1,100 @@
+"""GPU tests of the long-reach path (N > 249: tiled block cyclic reduction over global state, BASELINE configs[4])
+against the CPU oracle, the reference golden of the 2001-node clone, and the fused kernel on the same inputs."""
+import copy
+
+import numpy as np
+import pytest
+
+import util
+from flow_sim_b200 import abi
+from flow_sim_b200.runner import run_flat
+
+pytestmark = pytest.mark.gpu
+
+
+def _vs_oracle(flat, M, what, lanes=0):
+    import oracle_py
+
+    ora = oracle_py.run(flat, n_members=M)
+    out = run_flat(flat, n_members=M, lanes=lanes)
+    assert np.array_equal(out["status"], ora["status"]), what
+    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], what)
+    assert np.array_equal(out["iters"], ora["iters"]), f"{what}: Newton iteration counts differ"
+    return out, ora
+
+
+def test_akbari_long_clone_matches_reference_golden():
+    """N = 2001, dx = 100 m, dt = 600 s, theta = 0.6, 16 steps: the reduced clone of config 5."""
+    flat = util.golden_inputs("akbari_long")
+    ref = util.golden_outputs("akbari_long")
+    out = run_flat(flat)
+    assert out["status"][0] == 0
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], "akbari_long")
+    assert np.array_equal(out["iters"][0], ref["iters"])
+
+
+@pytest.mark.parametrize("case", ["example", "akbari", "gerd_calib_m0", "gerd_calib_m65535"])
+def test_long_path_equals_fused_kernel_on_short_reaches(case):
+    """Forcing the tiled path on the shipped cases (storage, normal-depth and Roseires boundaries, compound
+    sections): same results as the fused kernel and as the reference."""
+    flat = util.golden_inputs(case)
+    ref = util.golden_outputs(case)
+    out = run_flat(flat, lanes=-1)
+    assert out["status"][0] == 0
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], case)
+    assert np.array_equal(out["iters"][0], ref["iters"])
+    if "storage_stage" in ref.files:
+        assert util.max_rel(out["storage_stage"][0], ref["storage_stage"]) <= util.RTOL
+
+
+@pytest.mark.parametrize("n_nodes", [250, 257, 385, 1000, 4098])
+def test_tile_and_chain_boundaries(n_nodes):
+    """Sizes around the tile (128 cells) and chain (31 lanes) boundaries, compound sections (slow linear
+    convergence: ~20 iterations per level)."""
+    from test_gpu_ensemble import _prismatic
+
+    _vs_oracle(_prismatic(kind="compound", n_nodes=n_nodes, levels=3), 1, f"N={n_nodes}")
+
+
+def test_inflow_scenarios_on_a_long_reach():
+    flat = util.golden_inputs("akbari_long")
+    M = 5
+    base = flat.up.series
+    peak = np.linspace(0.6, 1.4, M)[:, None]
+    flat.up.series = base[None, 0] + (base[None, :] - base[0]) * peak
+    out, ora = _vs_oracle(flat, M, "long-reach scenarios")
+    # members are independent: a member alone gives the same bits as inside the batch
+    one = copy.copy(flat); one.up = copy.copy(flat.up); one.up.series = flat.up.series[3:4]
+    solo = run_flat(one, n_members=1)
+    assert np.array_equal(solo["depth"][0], out["depth"][3]) and np.array_equal(solo["iters"][0], out["iters"][3])
+
+
+def test_non_convergence_on_the_long_path():
+    flat = util.golden_inputs("gerd_calib_m0")
+    flat.max_iter = 11
+    out, ora = None, None
+    import oracle_py
+
+    ora = oracle_py.run(flat)
+    out = run_flat(flat, lanes=-1)
+    assert out["status"][0] == abi.PR_STATUS_MAX_ITER and out["fail_level"][0] == ora["fail_level"][0] == 6
+    assert np.array_equal(np.isnan(out["depth"]), np.isnan(ora["depth"]))
+    assert np.array_equal(out["iters"], ora["iters"])
+
+
+def test_config5_size_two_steps():
+    """100 000 nodes (BASELINE configs[4]); 2 members x 2 steps, one of them against the oracle."""
+    import oracle_py
+    from flow_sim_b200.cases.akbari_firoozi import build_long_reach
+    from flow_sim_b200.flatten import flatten_solver
+
+    solver, kw = build_long_reach(n_nodes=100_000, n_steps=2)
+    flat = flatten_solver(solver, tolerance=kw["tolerance"])
+    s = flat.up.series
+    flat.up.series = np.stack([s, s[0] + (s - s[0]) * 1.5])
+    out = run_flat(flat, n_members=2, out_mode=abi.PR_OUT_FULL)
+    assert not out["status"].any()
+    one = copy.copy(flat); one.up = copy.copy(flat.up); one.up.series = flat.up.series[1]
+    ora = oracle_py.run(one, n_members=1)
+    util.assert_parity(out["depth"][1], out["flow"][1], ora["depth"][0], ora["flow"][0], "config 5")
+    assert np.array_equal(out["iters"][1], ora["iters"][0])
