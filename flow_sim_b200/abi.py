@@ -93,7 +93,7 @@ class pr_outputs(C.Structure):
 # ---------------------------------------------------------------------------------------------
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpreissmann_b200.so")
+LIB_PATH = os.environ.get("PR_B200_LIB") or os.path.join(_HERE, "csrc", "libpreissmann_b200.so")   # override: tuning builds
 
 #: every symbol include/preissmann_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["pr_abi_version", "pr_last_error", "pr_ensemble_run", "pr_gvf_initial_conditions",

@@ -130,7 +130,7 @@ __device__ inline void stage_geometry(const DevGeom& g, int N, int NP, double* s
     sg[F_B * NP + idx] = b;
     sg[F_M * NP + idx] = m;
     sg[F_SQM * NP + idx] = sqm;
-    sg[F_HB * NP + idx] = hb;
+    sg[F_HB * NP + idx] = g.kind[s] == PR_XS_COMPOUND ? hb : 1e300;
     sg[F_TB * NP + idx] = Tb;
     sg[F_WB * NP + idx] = g.Wb[s];
     sg[F_BL * NP + idx] = g.bl[s];
@@ -198,51 +198,52 @@ struct NodeConv {
 // One reciprocal of A*P*T yields 1/A and 1/(T P); the over-bank branch needs one more for the
 // floodplain hydraulic radii.  The expensive tail (reciprocal, cube root) is common to all branches, so
 // lanes of a warp that sit on different branches re-converge before it.
-template <bool CURV, int RM, bool WANT_K = false, class KP = DevParams>
+template <bool CURV, int RM, bool WANT_K = false, class KP = DevParams, bool CMP = true>
 __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const int NP, const int idx, const double h,
                                           const double Q, const Rough& rg, const KP& k, NodeVals& o,
                                           NodeConv* kc = nullptr) {
 #define GEO(f) sg[(f)*NP + idx]
-  const int kind = (int)GEO(F_KIND);
   const double z = GEO(F_Z), b = GEO(F_B);
   const double hw = z + h;        // Solver.water_level_at
   const double d = hw - z;        // depth = max(0, hw - z_bed); a dry node (d <= 0) ends in status NaN
+  // Branch-free section geometry: the in-bank (simple trapezoid; a rectangle is m = 0) and the over-bank
+  // expressions are both evaluated and selected, so that the whole node pass is straight-line code the
+  // scheduler can interleave with its neighbours.  Non-compound sections are staged with h_bank = 1e300.
+  // CMP = false: the reach has no compound section, only the in-bank expressions are compiled.
+  const double hb = CMP ? GEO(F_HB) : 0.0;
+  const bool over = CMP && d > hb;
   double A, P, T, dPdh, X = 0.0;
-  bool over = false;
-  if (kind == PR_XS_RECT) {
-    A = b * d;
-    P = b + 2.0 * d;
-    T = b;
-    dPdh = 2.0;
-  } else {
-    const double hb = GEO(F_HB);
-    if (kind == PR_XS_TRAPEZOID || d <= hb) {
-      const double m = GEO(F_M), sqm = GEO(F_SQM);
-      T = b + 2.0 * m * d;
-      A = (b + T) * 0.5 * d;
-      P = b + 2.0 * d * sqm;
-      dPdh = 2.0 * sqm;
-    } else {
-      over = true;
-      const double dfp = d - hb, mfp = GEO(F_MFP), sqfp = GEO(F_SQFP);
+  {
+    const double m = GEO(F_M), sqm = GEO(F_SQM);
+    const double Ti = b + 2.0 * m * d;
+    const double Ai = (b + Ti) * 0.5 * d;
+    const double Pi = b + 2.0 * d * sqm;
+    if (CMP) {
+      const double dfp = over ? d - hb : 1.0, mfp = GEO(F_MFP), sqfp = GEO(F_SQFP);
       const double bl = GEO(F_BL), br = GEO(F_BR);
       const double hm = 0.5 * mfp * dfp;
       const double Al = (bl + hm) * dfp, Pl = bl + dfp * sqfp;
       const double Ar = (br + hm) * dfp, Pr = br + dfp * sqfp;
       const double Amf = GEO(F_AMF);
-      A = Amf + Al + Ar;                                   // quirk 4: total area omits T_bank*dfp
-      P = GEO(F_PM) + Pl + Pr;
-      T = GEO(F_WB) + 2.0 * mfp * dfp;
-      dPdh = 2.0 * sqfp;
+      const double Ao = Amf + Al + Ar;                       // quirk 4: total area omits T_bank*dfp
+      const double Po = GEO(F_PM) + Pl + Pr;
+      const double To = GEO(F_WB) + 2.0 * mfp * dfp;
       // K_j^1.5 = A_j*sqrt(A_j) * (A_j/P_j) * n_j^-1.5   (cross_section.py:681-754, hydraulics.py:15-26)
-      const double Am = Amf + GEO(F_TB) * dfp;             // conveyance area includes the column (:694)
+      const double Am = Amf + GEO(F_TB) * dfp;               // conveyance area includes the column (:694)
       const double cnm = (RM & 1) ? rg.cnm : GEO(F_CNM);
       const double cnl = (RM & 2) ? rg.cnfp : GEO(F_CNL);
       const double cnr = (RM & 2) ? rg.cnfp : GEO(F_CNR);
-      const double w = fast_rcp(Pl * Pr);                  // Pl, Pr > 0 because dfp > 0
-      X = (Am * Am) * fast_sqrt(Am) * (GEO(F_INVPM) * cnm);
-      X = fma((Al * Al) * fast_sqrt(Al), (Pr * w) * cnl, X);
-      X = fma((Ar * Ar) * fast_sqrt(Ar), (Pl * w) * cnr, X);
+      const double w = fast_rcp(Pl * Pr);
+      double Xo = (Am * Am) * fast_sqrt(Am) * (GEO(F_INVPM) * cnm);
+      Xo = fma((Al * Al) * fast_sqrt(Al), (Pr * w) * cnl, Xo);
+      Xo = fma((Ar * Ar) * fast_sqrt(Ar), (Pl * w) * cnr, Xo);
+      A = over ? Ao : Ai;
+      P = over ? Po : Pi;
+      T = over ? To : Ti;
+      dPdh = 2.0 * (over ? sqfp : sqm);
+      X = Xo;
+    } else {
+      A = Ai; P = Pi; T = Ti; dPdh = 2.0 * sqm;
     }
   }
   const double PT = P * T;
@@ -278,7 +279,7 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       const double R = A * invP;
       const double rR = over ? fast_rcbrt(R) : r;           // R^(-1/3)
       const double cR = R * rR * rR;                        // R^(1/3)
-      const double n_eq = (kind == PR_XS_COMPOUND) ? A * (cR * cR) / K : nm;    // cross_section.py:710-739
+      const double n_eq = (GEO(F_KIND) == (double)PR_XS_COMPOUND) ? A * (cR * cR) / K : nm;    // cross_section.py:710-739
       const double rc = 1.0 / curv;
       const double V = Q / fmax(A, 1e-6), D = A / fmax(T, 1e-6);
       const double Fr = V / sqrt(k.g * fmax(D, 1e-6));

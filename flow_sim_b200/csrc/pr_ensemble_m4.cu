@@ -1,4 +1,7 @@
 // pr_ensemble_m4.cu - instantiations of the fused ensemble kernel with 4 node(s) per lane (12 warps per CTA).
 #include "pr_ensemble_kernel.cuh"
 
-PR_DEFINE_ENSEMBLE_FAMILY(4, 12)
+#ifndef PR_W4
+#define PR_W4 12
+#endif
+PR_DEFINE_ENSEMBLE_FAMILY(4, PR_W4)

@@ -17,11 +17,13 @@
 //
 // Same algebra as pr_ensemble_kernel.cuh (cell_assemble / merge_cells / PCR); block cyclic reduction is
 // applied hierarchically: lane (4 cells) -> tile (32 lanes) -> chain (<= 32 x Kc tiles).
+// The iterate is double-buffered (K3 reads a tile's right neighbour node while that neighbour's tile updates it).
 // Algorithmic HBM traffic is 48 B per node per Newton iteration; this first version moves
 // 112 B (iterate read twice + 4 level constants per cell read twice + iterate written).
 #pragma once
 #include <atomic>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pr_ensemble_kernel.cuh"
@@ -35,7 +37,9 @@ constexpr int kChainMaxK = 64;     // tile cells per lane in the chain kernel ->
 struct LongParams {
   DevParams p;
   const double* geo;   // derived geometry table [F_COUNT][N] (stage_geometry layout, NP = N)
-  double *xh, *xq;     // current iterate [M][N]
+  double *xh, *xq;     // current iterate [M][N] (read)
+  double *xh_out, *xq_out;   // next iterate (written by K3): tiles read their right neighbour's first node, so the
+                             // update cannot be done in place
   double* pc;          // level constants [M][4][N]
   double* tcell;       // condensed tile cells [M][T][10]
   double* dchain;      // updates of the tile-boundary nodes [M][T+1][2]
@@ -89,7 +93,7 @@ __device__ __forceinline__ Cell shfl_cell(const Cell& c, int src) {
   return o;
 }
 
-template <int MODE>
+template <int MODE, bool CMP>
 __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const int lane = threadIdx.x & 31;
@@ -103,8 +107,10 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
   int nc = (N - 1) - c0;
   nc = nc < 0 ? 0 : (nc > kLongM ? kLongM : nc);
   const Rough rg = load_rough<0>(p.geo, 0);
-  double* xh = q.xh + (size_t)m * N;
-  double* xq = q.xq + (size_t)m * N;
+  const double* xh = q.xh + (size_t)m * N;
+  const double* xq = q.xq + (size_t)m * N;
+  double* xh_out = q.xh_out + (size_t)m * N;
+  double* xq_out = q.xq_out + (size_t)m * N;
   double* pc = q.pc + (size_t)m * 4 * N;
 
   double h[kLongM + 1], qq[kLongM + 1];
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
     qq[j] = xq[nd];
   }
   NodeVals nv[2];
-  node_eval<false, 0>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
+  node_eval<false, 0, false, DevParams, CMP>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
   double ss = 0.0;
   Cell S;
   Elim el[kLongM - 1];
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
 #pragma unroll
   for (int j = 0; j < kLongM; ++j) {
     const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
-    node_eval<false, 0>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
+    node_eval<false, 0, false, DevParams, CMP>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
     if (j < nc) {
       const int c = c0 + j;
       Cell e;
@@ -214,15 +220,15 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
         const int c = nd;
         pc[c] = cand[j][0]; pc[N + c] = cand[j][1]; pc[2 * N + c] = cand[j][2]; pc[3 * N + c] = cand[j][3];
       }
-      xh[nd] = h[j] + dh[j];
-      xq[nd] = qq[j] + dq[j];
+      xh_out[nd] = h[j] + dh[j];
+      xq_out[nd] = qq[j] + dq[j];
     }
   }
   if (nc > 0 && c0 + nc == N - 1) {      // this lane's last cell ends at the downstream boundary node
     const int nd = N - 1;
     if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[nc]; if (p.out_q) p.out_q[orow + nd] = qq[nc]; }
-    xh[nd] = h[nc] + yR1;
-    xq[nd] = qq[nc] + yR2;
+    xh_out[nd] = h[nc] + yR1;
+    xq_out[nd] = qq[nc] + yR2;
   }
   if (conv && p.out_mode == PR_OUT_UPSTREAM && t == 0 && lane == 0) {
     if (p.out_h) p.out_h[(size_t)m * p.L + lvl] = h[0];
@@ -408,8 +414,9 @@ __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
   }
 }
 
-inline int long_reach_run(const DevParams& p, bool has_curv, cudaStream_t s, std::atomic<long long>& launches,
-                          std::string& err) {
+template <bool CMP>
+inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, std::atomic<long long>& launches,
+                            std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
   if (has_curv) return fail(PR_ERR_UNSUPPORTED, "long-reach path: centre-line curvature is not supported");
   if (p.geo.member_nm || p.geo.member_nfp)
@@ -433,6 +440,8 @@ inline int long_reach_run(const DevParams& p, bool has_curv, cudaStream_t s, std
   q.geo = geo;
   q.xh = (double*)dalloc(sizeof(double) * (size_t)M * N);
   q.xq = (double*)dalloc(sizeof(double) * (size_t)M * N);
+  q.xh_out = (double*)dalloc(sizeof(double) * (size_t)M * N);
+  q.xq_out = (double*)dalloc(sizeof(double) * (size_t)M * N);
   q.pc = (double*)dalloc(sizeof(double) * (size_t)M * 4 * N);
   q.tcell = (double*)dalloc(sizeof(double) * (size_t)M * T * 10);
   q.dchain = (double*)dalloc(sizeof(double) * (size_t)M * (T + 1) * 2);
@@ -453,18 +462,20 @@ inline int long_reach_run(const DevParams& p, bool has_curv, cudaStream_t s, std
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
   const long long warps = (long long)M * T;
   const unsigned tile_grid = (unsigned)((warps + 3) / 4);
-  pr_long_tile<LONG_INIT><<<tile_grid, 128, 0, s>>>(q);
+  pr_long_tile<LONG_INIT, CMP><<<tile_grid, 128, 0, s>>>(q);
   launches.fetch_add(3);
   const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
   e = cudaFuncSetAttribute(pr_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
   int done = (p.L > 1) ? 0 : M;
   const long long max_trips = (long long)(p.L - 1) * (p.max_iter > 0 ? p.max_iter : 1) + 1;
   for (long long trip = 0; trip < max_trips && done < M && e == cudaSuccess; ++trip) {
-    pr_long_tile<LONG_CONDENSE><<<tile_grid, 128, 0, s>>>(q);
+    pr_long_tile<LONG_CONDENSE, CMP><<<tile_grid, 128, 0, s>>>(q);
     pr_long_chain<<<M, 32, chain_smem, s>>>(q);
-    pr_long_tile<LONG_UPDATE><<<tile_grid, 128, 0, s>>>(q);
+    pr_long_tile<LONG_UPDATE, CMP><<<tile_grid, 128, 0, s>>>(q);
     pr_long_retire<<<(M + 127) / 128, 128, 0, s>>>(q);
     launches.fetch_add(4);
+    std::swap(q.xh, q.xh_out);
+    std::swap(q.xq, q.xq_out);
     e = cudaMemcpyAsync(&done, q.n_done, sizeof(int), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   }
@@ -477,6 +488,12 @@ inline int long_reach_run(const DevParams& p, bool has_curv, cudaStream_t s, std
   cleanup();
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, std::string("long-reach path: ") + cudaGetErrorString(e));
   return PR_OK;
+}
+
+inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, cudaStream_t s,
+                          std::atomic<long long>& launches, std::string& err) {
+  return has_compound ? long_reach_run_t<true>(p, has_curv, s, launches, err)
+                      : long_reach_run_t<false>(p, has_curv, s, launches, err);
 }
 
 }  // namespace pr

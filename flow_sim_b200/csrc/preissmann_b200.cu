@@ -18,6 +18,9 @@
 #include "pr_ensemble_kernel.cuh"
 #include "pr_long_kernels.cuh"
 
+#ifndef PR_W4
+#define PR_W4 12
+#endif
 namespace {
 
 thread_local std::string g_err;
@@ -275,6 +278,16 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   if (int rc = fetch(geom->z_bed, N, cfg->mem, zb)) return rc;
   bool has_curv = false;
   for (double c : curv) has_curv |= (c != 0.0);
+  bool has_compound = false;
+  {
+    std::vector<int32_t> kinds(N);
+    if (cfg->mem == PR_MEM_HOST) std::memcpy(kinds.data(), geom->kind, N * sizeof(int32_t));
+    else CUDA_TRY(cudaMemcpy(kinds.data(), geom->kind, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int32_t kd : kinds) {
+      if (kd < PR_XS_RECT || kd > PR_XS_COMPOUND) return fail(PR_ERR_ARG, "geom.kind holds an unknown section kind %d", kd);
+      has_compound |= (kd == PR_XS_COMPOUND);
+    }
+  }
 
   if (int rc = stage_geom(*cfg, geom, st, p.geo)) return rc;
   if (int rc = make_bc(*upstream, "upstream", false, *cfg, zb[0], st, p.up)) return rc;
@@ -300,12 +313,12 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   if (cfg->lanes_per_member != 0 && cfg->lanes_per_member != 32 && cfg->lanes_per_member != -1)
     return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: this build has the 32-lane instantiations", cfg->lanes_per_member);
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
-  if (cfg->lanes_per_member == -1) rc = pr::long_reach_run(p, has_curv, s, g_launches, g_err);   // forced long-reach path
+  if (cfg->lanes_per_member == -1) rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);   // forced long-reach path
   else if (need <= 1) rc = launch_family(pr::launch_ensemble_family<1, 12>(p, has_curv, s));
   else if (need <= 2) rc = launch_family(pr::launch_ensemble_family<2, 12>(p, has_curv, s));
-  else if (need <= 4) rc = launch_family(pr::launch_ensemble_family<4, 12>(p, has_curv, s));
+  else if (need <= 4) rc = launch_family(pr::launch_ensemble_family<4, PR_W4>(p, has_curv, s));
   else if (need <= 8) rc = launch_family(pr::launch_ensemble_family<8, 5>(p, has_curv, s));
-  else rc = pr::long_reach_run(p, has_curv, s, g_launches, g_err);
+  else rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);
   if (rc) return rc;
   cudaError_t e = st.finish();
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_ensemble_run: %s", cudaGetErrorString(e));

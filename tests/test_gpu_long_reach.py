@@ -47,7 +47,7 @@ def test_long_path_equals_fused_kernel_on_short_reaches(case):
         assert util.max_rel(out["storage_stage"][0], ref["storage_stage"]) <= util.RTOL
 
 
-@pytest.mark.parametrize("n_nodes", [250, 257, 385, 1000, 4098])
+@pytest.mark.parametrize("n_nodes", [250, 257, 385, 1000, 3969, 4098, 8066])
 def test_tile_and_chain_boundaries(n_nodes):
     """Sizes around the tile (128 cells) and chain (31 lanes) boundaries, compound sections (slow linear
     convergence: ~20 iterations per level)."""
