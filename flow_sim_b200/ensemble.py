@@ -112,23 +112,47 @@ def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
     return first, first + base + (1 if rank < extra else 0)
 
 
-def gather_members(local, total: int, rank: int, world: int):
-    """All ranks receive the per-member array of the whole ensemble, in member order.
-    `local` is this rank's block ([m_local, ...] torch tensor on the backend's device)."""
+def shard_members(total: int, rank: int, world: int, layout: str = "strided") -> np.ndarray:
+    """Member indices owned by `rank`.
+
+    "strided" (default): rank, rank + world, rank + 2*world, ...  A parameter sweep is usually ordered, and the
+    Newton iteration count grows with the roughness (409 -> 676 iterations across the gerd grid), so dealing
+    members out round-robin gives every GPU the same mix of cheap and expensive members.
+    "block": the contiguous block of shard_bounds()."""
+    if layout == "block":
+        a, b = shard_bounds(total, rank, world)
+        return np.arange(a, b)
+    if layout != "strided":
+        raise ValueError("layout must be 'strided' or 'block'")
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return np.arange(rank, total, world)
+
+
+def gather_members(local, total: int, rank: int, world: int, layout: str = "strided"):
+    """The single end-of-run collective: every rank receives the per-member array of the whole ensemble in member
+    order.  `local` is this rank's part ([m_local, ...] torch tensor on the backend's device), ordered as
+    shard_members() orders it."""
     import torch
     import torch.distributed as dist
 
     if world == 1:
         return local
-    sizes = [shard_bounds(total, r, world) for r in range(world)]
-    counts = [b - a for a, b in sizes]
+    counts = [len(shard_members(total, r, world, layout)) for r in range(world)]
     if len(set(counts)) == 1:
-        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous())
-        return out
-    pad = max(counts)
-    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    buf[: local.shape[0]] = local
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+        flat = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(flat, local.contiguous())
+        parts = list(flat.split(counts[0], dim=0))
+    else:
+        pad = max(counts)
+        buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        buf[: local.shape[0]] = local
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        parts = [p[:c] for p, c in zip(parts, counts)]
+    if layout == "block":
+        return torch.cat(parts, dim=0)
+    out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r, p in enumerate(parts):
+        out[r::world] = p
+    return out

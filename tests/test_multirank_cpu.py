@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import util
-from flow_sim_b200.ensemble import gather_members, shard_bounds
+from flow_sim_b200.ensemble import gather_members, shard_bounds, shard_members
 
 
 def test_shard_bounds_cover_the_ensemble_exactly_once():
@@ -25,6 +25,11 @@ def test_shard_bounds_cover_the_ensemble_exactly_once():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(4, 4, 4)
+    for layout in ("strided", "block"):
+        for total, world in ((5, 2), (65536, 8), (7, 3)):
+            idx = np.concatenate([shard_members(total, r, world, layout) for r in range(world)])
+            assert sorted(idx.tolist()) == list(range(total))
+    assert shard_members(10, 1, 4).tolist() == [1, 5, 9]
 
 
 def _free_port():
@@ -35,7 +40,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, total, out_path):
+def _worker(rank, world, port, total, layout, out_path):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
     import oracle_py
@@ -43,27 +48,27 @@ def _worker(rank, world, port, total, out_path):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     flat = util.golden_inputs("gerd_calib_m0")
     n_all = np.linspace(0.02, 0.06, total)
-    a, b = shard_bounds(total, rank, world)
-    flat.member_n_main = n_all[a:b]
-    h, q, _ = oracle_py.gvf(flat, flat.meta["initial_flow"], flat.meta["downstream_depth"], n_members=b - a)
+    mine = shard_members(total, rank, world, layout)
+    flat.member_n_main = n_all[mine]
+    h, q, _ = oracle_py.gvf(flat, flat.meta["initial_flow"], flat.meta["downstream_depth"], n_members=len(mine))
     flat.ic_depth, flat.ic_flow = h, q
-    res = oracle_py.run(flat, n_members=b - a, out_mode=1)
+    res = oracle_py.run(flat, n_members=len(mine), out_mode=1)
     lv, rm = oracle_py.objective(flat.n_levels, res["flow"], res["depth"], flat.meta["z0"],
                                  [1562.5, 3850, 6000, 10000, 14000, 21000], [497.5, 500, 502, 505, 507, 510])
-    rmse = gather_members(torch.from_numpy(rm), total, rank, world)
-    iters = gather_members(torch.from_numpy(res["iters"].astype(np.int32)), total, rank, world)
+    rmse = gather_members(torch.from_numpy(rm), total, rank, world, layout)
+    iters = gather_members(torch.from_numpy(res["iters"].astype(np.int32)), total, rank, world, layout)
     if rank == 0:
         np.savez(out_path, rmse=rmse.numpy(), iters=iters.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("total", [4, 5])
-def test_two_rank_gather_equals_single_process(tmp_path, total):
+@pytest.mark.parametrize("total,layout", [(4, "strided"), (5, "strided"), (5, "block")])
+def test_two_rank_gather_equals_single_process(tmp_path, total, layout):
     import oracle_py
 
     out = str(tmp_path / "gathered.npz")
-    mp.spawn(_worker, args=(2, _free_port(), total, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), total, layout, out), nprocs=2, join=True)
     got = np.load(out)
     flat = util.golden_inputs("gerd_calib_m0")
     flat.member_n_main = np.linspace(0.02, 0.06, total)

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Config 5 (BASELINE configs[4]): synthetic prismatic channel, N nodes x M inflow scenarios through the long-reach
+path.  Reports node-steps/s, node-iterations/s and the HBM roofline fraction (48 algorithmic bytes
+per node per Newton iteration).  Not the bench.py headline (that is config 4); a tool for DESIGN.md numbers.
+
+    python tools/bench_long.py [--nodes 100000] [--members 1024] [--steps 16] [--repeat 3]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nodes", type=int, default=100_000)
+    ap.add_argument("--members", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--check", type=int, default=1, help="members re-run on the CPU oracle")
+    a = ap.parse_args()
+    import torch
+
+    from flow_sim_b200 import abi
+    from flow_sim_b200.cases.akbari_firoozi import BASE_FLOW, build_long_reach, flood_wave
+    from flow_sim_b200.ensemble import EnsembleRunner
+    from flow_sim_b200.flatten import flatten_solver
+
+    t0 = time.time()
+    solver, kw = build_long_reach(n_nodes=a.nodes, n_steps=a.steps)
+    flat = flatten_solver(solver, tolerance=kw["tolerance"])
+    L = flat.n_levels
+    # Q_p,m = 100 + 200 m/(M-1)  
+    peaks = 100.0 + 200.0 * np.arange(a.members) / max(a.members - 1, 1)
+    series = np.empty((a.members, L))
+    for m, pk in enumerate(peaks):
+        f = flood_wave(peak_flow=pk)
+        series[m] = [f(k * flat.dt) for k in range(L)]
+    setup_s = time.time() - t0
+    dev = torch.device("cuda", 0)
+    runner = EnsembleRunner(flat, dev)
+    ser_dev = torch.from_numpy(series).to(dev)
+    times = []
+    for r in range(a.repeat + 1):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = runner.solve(a.members, up_series=ser_dev, out_mode=abi.PR_OUT_UPSTREAM)
+        e1.record()
+        torch.cuda.synchronize()
+        if r > 0:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    secs = float(np.mean(times))
+    iters = int(res["iters"].sum().item())
+    node_steps = a.members * a.nodes * (L - 1)
+    node_iters = iters * a.nodes
+    peaks_json = {}
+    try:
+        peaks_json = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks_json.get("hbm_gbs", 6650.0))
+    out = {
+        "workload": f"prismatic channel {a.nodes} nodes x {a.members} inflow scenarios x {L - 1} steps (dx=100 m, dt=600 s, theta=0.6)",
+        "seconds": secs, "node_steps_per_s": node_steps / secs, "node_iterations_per_s": node_iters / secs,
+        "newton_iterations_per_step": iters / (a.members * (L - 1)), "failed_members": int((res["status"] != 0).sum().item()),
+        "roofline": {"bound": "hbm", "algorithmic_bytes_per_node_iteration": 48, "achieved": node_iters * 48 / secs / 1e9,
+                     "peak": hbm, "unit": "GB/s", "frac": node_iters * 48 / secs / 1e9 / hbm,
+                     "moved_bytes_per_node_iteration_this_version": 112},
+        "host_setup_s": setup_s,
+    }
+    if a.check:
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import copy
+
+        import oracle_py
+
+        pick = np.linspace(0, a.members - 1, a.check).round().astype(int)
+        f2 = copy.copy(flat); f2.up = copy.copy(flat.up); f2.up.series = series[pick]
+        ora = oracle_py.run(f2, n_members=len(pick), out_mode=abi.PR_OUT_UPSTREAM)
+        gh, gq = res["depth"][pick].cpu().numpy(), res["flow"][pick].cpu().numpy()
+        out["parity"] = {"members": len(pick), "max_rel_depth": float(np.max(np.abs(gh - ora["depth"]) / np.abs(ora["depth"]))),
+                         "iterations_equal": bool(np.array_equal(res["iters"][pick].cpu().numpy(), ora["iters"]))}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
