@@ -97,7 +97,7 @@ LIB_PATH = os.environ.get("PR_B200_LIB") or os.path.join(_HERE, "csrc", "libprei
 
 #: every symbol include/preissmann_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["pr_abi_version", "pr_last_error", "pr_ensemble_run", "pr_gvf_initial_conditions",
-                    "pr_rating_objective", "pr_fp64_peak", "pr_launch_count"]
+                    "pr_rating_objective", "pr_fp64_peak", "pr_launch_count", "pr_math_probe"]
 
 _lib = None
 _lock = threading.Lock()
@@ -133,6 +133,8 @@ def load_library(path: str | None = None):
         lib.pr_fp64_peak.restype = C.c_int
         lib.pr_fp64_peak.argtypes = [C.c_double, c_double_p]
         lib.pr_launch_count.restype = C.c_int64
+        lib.pr_math_probe.restype = C.c_int
+        lib.pr_math_probe.argtypes = [c_double_p, C.c_int32, c_double_p]
         if lib.pr_abi_version() != PR_ABI_VERSION:
             raise PreissmannLibraryError(f"ABI mismatch: library {lib.pr_abi_version()} != python {PR_ABI_VERSION}")
         if path is None:

@@ -118,4 +118,21 @@ __global__ void __launch_bounds__(256) pr_dfma_kernel(double* sink, int iters, d
   if (s == 123.456) sink[0] = s;
 }
 
+// Accuracy probe of the FP64 primitives (tests/test_gpu_math.py): out[0..5][i] = fast_rcp, fast_sqrt, fast_rsqrt,
+// fast_rcbrt of x[i] and the raw SFU seeds of 1/x and x^-1/2.
+__global__ void pr_math_probe_kernel(const double* x, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = x[i];
+  double s0, s1;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s0) : "d"(a));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s1) : "d"(a));
+  out[i] = fast_rcp(a);
+  out[n + i] = fast_sqrt(a);
+  out[2 * n + i] = fast_rsqrt(a);
+  out[3 * n + i] = fast_rcbrt(a);
+  out[4 * n + i] = s0;
+  out[5 * n + i] = s1;
+}
+
 }  // namespace pr

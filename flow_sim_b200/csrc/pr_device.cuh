@@ -59,50 +59,37 @@ struct DevParams {
 // ---- FP64 primitives without slow-path branches ----------------------------------------------------
 // CUDA's IEEE division / sqrt / cbrt carry special-case branches (BSSY/BSYNC/CALL) that cost issue slots
 // and diverge.  The scheme only needs ~1e-15 relative accuracy on positive, normal arguments, so these use
-// the SFU seed (MUFU.RCP64H / RSQ64H, fp32 LG2/EX2) plus two Newton / Goldschmidt steps, all on the FMA pipe.
+// the SFU seed (MUFU.RCP64H / RSQ64H, fp32 LG2/EX2) plus one second-order correction, all on the FMA pipe.
 
+// Seeds are accurate to 2^-20 (measured, tests/test_gpu_math.py); ONE correction step that keeps the quadratic
+// term of the error series brings them to < 2^-58, i.e. full double precision up to the final rounding.
 __device__ __forceinline__ double fast_rcp(double a) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-  double e = fma(-a, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-a, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-a, r, 1.0);          // 1/a = r / (1 - e) = r (1 + e + e^2 + O(e^3))
+  return fma(r, fma(e, e, e), r);
 }
 
 __device__ __forceinline__ double fast_sqrt(double a) {   // a >= 0; sqrt(0) = 0 without a select:
   double y;                                               // the seed of a + tiny is finite, and 0 * finite = 0
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a + 1e-300));
-  double g = a * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  r = fma(-h, g, 0.5);
-  g = fma(g, r, g);
-  return g;
+  const double g = a * y;
+  const double e = fma(-g, y, 1.0);          // sqrt(a) = g (1 - e)^(-1/2) = g (1 + e/2 + 3e^2/8 + O(e^3))
+  return fma(g, e * fma(e, 0.375, 0.5), g);
 }
 
 __device__ __forceinline__ double fast_rsqrt(double a) {  // a > 0
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double e = fma(-a * y, y, 1.0);          // y <- y*(1 + e/2 + 3e^2/8)
-  y = fma(y * fma(0.375, e, 0.5), e, y);
-  e = fma(-a * y, y, 1.0);
-  y = fma(y * 0.5, e, y);
-  return y;
+  const double e = fma(-a * y, y, 1.0);
+  return fma(y, e * fma(e, 0.375, 0.5), y);
 }
 
 __device__ __forceinline__ double fast_rcbrt(double x) {  // x^(-1/3), x > 0 within float range
   const float xf = __double2float_rn(x);
-  double r = (double)exp2f(-0.33333334f * __log2f(xf));   // ~2^-21 relative
-  double r2 = r * r;
-  double t = fma(-x * r, r2, 1.0);                        // Newton on r^-3 = x: r <- r + r(1 - x r^3)/3
-  r = fma(r * (1.0 / 3.0), t, r);
-  r2 = r * r;
-  t = fma(-x * r, r2, 1.0);
-  r = fma(r * (1.0 / 3.0), t, r);
-  return r;
+  const double r = (double)exp2f(-0.33333334f * __log2f(xf));   // ~2^-20 relative
+  const double e = fma(-x * r, r * r, 1.0);  // x^(-1/3) = r (1 - e)^(-1/3) = r (1 + e/3 + 2e^2/9 + O(e^3))
+  return fma(r, e * fma(e, 2.0 / 9.0, 1.0 / 3.0), r);
 }
 
 // ---- per-node geometry staged in shared memory (SoA: field f of slot idx at sg[f*NP + idx]) -----------

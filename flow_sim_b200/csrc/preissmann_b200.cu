@@ -382,6 +382,21 @@ int pr_rating_objective(const pr_config* cfg, const double* up_flow, const doubl
   return PR_OK;
 }
 
+int pr_math_probe(const double* x_host, int32_t n, double* out_host) {
+  if (!x_host || !out_host || n < 1) return fail(PR_ERR_ARG, "pr_math_probe: NULL / empty input");
+  double *dx = nullptr, *dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dx, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&dout, sizeof(double) * 6 * (size_t)n));
+  CUDA_TRY(cudaMemcpy(dx, x_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+  pr::pr_math_probe_kernel<<<(n + 255) / 256, 256>>>(dx, n, dout);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaMemcpy(out_host, dout, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_math_probe: %s", cudaGetErrorString(e));
+  return PR_OK;
+}
+
 int pr_fp64_peak(double millis, double* tflops_out) {
   if (!tflops_out) return fail(PR_ERR_ARG, "tflops_out is NULL");
   int dev = 0, sms = 0;

@@ -201,6 +201,11 @@ int pr_rating_objective(const pr_config* cfg, const double* up_flow, const doubl
  * asks for.  Runs a register-resident DFMA kernel for about `millis` ms. */
 int pr_fp64_peak(double millis, double* tflops_out);
 
+/* Diagnostics: evaluates the device's branch-free FP64 primitives (reciprocal, square root, reciprocal square
+ * root, reciprocal cube root - csrc/pr_device.cuh) and their raw SFU seeds on n HOST values;
+ * out_host is [6][n].  Used by tests/test_gpu_math.py to bound their error against IEEE results. */
+int pr_math_probe(const double* x_host, int32_t n, double* out_host);
+
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t pr_launch_count(void);
 
