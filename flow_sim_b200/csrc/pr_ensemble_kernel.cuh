@@ -64,11 +64,23 @@ __device__ __forceinline__ void merge_cells(Cell& S, const Cell& E, Elim& el) {
   S = n;
 }
 
-// Residuals + Jacobian of one Preissmann cell (left node a, right node b) and the candidate level
-// constants.  (cC, cM, cA, cS) are the stored level's contributions; returns R_C^2 + R_M^2.
+// Level-k parts of the residuals of one cell, from the node values of the stored level:
+//   cC = -(A_i+A_i+1)/(2dt) + (1-theta)(Q_i+1-Q_i)/dx          cM = -(Q_i+Q_i+1)/(2dt) + (1-theta)(F_i+1-F_i)/dx
+//   cA = (1-theta)/2 (A_i+A_i+1)                               cS = (1-theta)(Y_i+1-Y_i)/dx + (1-theta)/2 (Se_i+Se_i+1)
+__device__ __forceinline__ void level_constants(const NodeVals& a, const NodeVals& b, const DevParams& k, double& nC,
+                                                double& nM, double& nA, double& nS) {
+  const double sA = b.A + a.A, dQ = b.Q - a.Q, sQ = b.Q + a.Q, dF = b.F - a.F, dY = b.Y - a.Y, sSe = b.Se + a.Se;
+  nC = fma(-sA, k.i2dt, k.omt_dx * dQ);
+  nM = fma(-sQ, k.i2dt, k.omt_dx * dF);
+  nA = k.homt * sA;
+  nS = fma(k.omt_dx, dY, k.homt * sSe);
+}
+
+// Residuals + Jacobian of one Preissmann cell (left node a, right node b).  (cC, cM, cA, cS) are the stored
+// level's contributions; returns R_C^2 + R_M^2.
 __device__ __forceinline__ double cell_assemble(const NodeVals& a, const NodeVals& b, const DevParams& k,
                                                 const double cC, const double cM, const double cA, const double cS,
-                                                Cell& e, double& nC, double& nM, double& nA, double& nS) {
+                                                Cell& e) {
   const double sA = b.A + a.A, dQ = b.Q - a.Q, sQ = b.Q + a.Q, dF = b.F - a.F, dY = b.Y - a.Y, sSe = b.Se + a.Se;
   // continuity_residual (preissmann.py:220-249): R_C = time_diff(A) + spatial_diff(Q);  e.rc = -R_C
   e.rc = fma(-sA, k.i2dt, fma(-k.th_dx, dQ, -cC));
@@ -77,11 +89,6 @@ __device__ __forceinline__ double cell_assemble(const NodeVals& a, const NodeVal
   const double slope = fma(k.th_dx, dY, fma(k.hth, sSe, cS));          // spatial_diff(z+h) + cell_avg(Se)
   const double ga = k.g * avgA;
   e.rm = fma(-ga, slope, fma(-sQ, k.i2dt, fma(-k.th_dx, dF, -cM)));
-  // level-(k) parts for the NEXT level, should this iterate be accepted
-  nC = fma(-sA, k.i2dt, k.omt_dx * dQ);
-  nM = fma(-sQ, k.i2dt, k.omt_dx * dF);
-  nA = k.homt * sA;
-  nS = fma(k.omt_dx, dY, k.homt * sSe);
   // dC_* (preissmann.py:407-494)
   e.c1 = a.T * k.i2dt;  e.c2 = -k.th_dx;  e.c3 = b.T * k.i2dt;  e.c4 = k.th_dx;
   // dM_dh_i / dM_dQ_i / dM_dh_ip1 / dM_dQ_ip1 (preissmann.py:496-733); spatial_diff(unit) = -/+ theta/dx
@@ -101,13 +108,13 @@ __device__ __forceinline__ double group_sum(double v) {
 }
 
 // Shared memory (doubles): [geometry F_COUNT x NP] then per warp
-//   level constants  2 x 4 x M x 32   (ping-pong: stored level / candidate)
+//   level constants  4 x M x 32       (of the stored level; rebuilt by one extra node pass when a level is accepted)
 //   elimination recs (M-1) x 9 x 32
-//   neighbour exchange 9 x 32         (first-node values handed to the lane on the left)
+//   neighbour exchange 8 x 32         (first-node values handed to the lane on the left)
 // every per-warp array is indexed [..][lane]: consecutive lanes, consecutive doubles, no bank conflicts.
-constexpr int kXch = 9;
+constexpr int kXch = 8;
 template <int M>
-__host__ __device__ constexpr int warp_smem_doubles() { return 32 * (8 * M + 9 * (M - 1) + kXch); }
+__host__ __device__ constexpr int warp_smem_doubles() { return 32 * (4 * M + 9 * (M - 1) + kXch); }
 
 template <int G, int M, int W>
 __host__ __device__ constexpr size_t ensemble_smem_bytes() {
@@ -123,7 +130,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   double* sg = smem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* pcw = smem + (size_t)F_COUNT * NP + (size_t)warp * warp_smem_doubles<M>();   // level constants
-  double* elw = pcw + 2 * 4 * M * 32;                                                    // elimination records
+  double* elw = pcw + 4 * M * 32;                                                    // elimination records
   double* xw = elw + (M - 1) * 9 * 32;                                                   // neighbour exchange
   // slot (j, gl) at index j*G + gl holds node gl*M + j
   stage_geometry(p.geo, p.N, NP, sg, threadIdx.x, blockDim.x, [](int idx) { return (idx % G) * M + idx / G; });
@@ -150,10 +157,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   // EXACT: (N-1) % M == 0, i.e. every lane owns either M cells or none.  Lanes without cells then run the
   // cell pass on padding (finite copies of the last node, zeroed scratch) instead of branching around it,
   // which leaves the node/cell/merge loop as straight-line code.
-  if (EXACT) {
-    for (int i = lane; i < warp_smem_doubles<M>(); i += 32) pcw[i] = 0.0;
-    __syncwarp();
-  }
+  static_assert(G == 32, "the level-constant refresh assumes one member per warp");
 
   // ---- state: initial conditions (Solver.initialize_t0, solver.py:61-63) ----
   double h[M], q[M];
@@ -208,21 +212,46 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   int level = 1, it = 0;
   bool active = member_valid && L > 1;
   int status = PR_STATUS_OK, fail_level = 0;
-  int buf = 0;             // which half of the ping-pong holds the stored level's constants
-  bool init_pass = true;   // first trip: only builds the level-0 constants from the initial state
   double hyd_up = 0.0, hyd_dn = 0.0;
 
-#define PC(b, c, j) pcw[(((b)*4 + (c)) * M + (j)) * 32 + lane]
+#define PC(c, j) pcw[((c)*M + (j)) * 32 + lane]
 #define EL(j, c) elw[((j)*9 + (c)) * 32 + lane]
 #define XW(c, l) xw[(c)*32 + (l)]
 
-  while (__any_sync(kFull, active) || init_pass) {
-    if (!init_pass && it == 0) {
+  // Node pass at the current state that only (re)builds the level constants: once for the initial state and once
+  // per accepted level.  Cheaper than producing candidates in every Newton iteration (one extra node pass per
+  // level against 4 stores + 9 flops per cell per iteration), and it halves the constants' shared memory.
+  auto refresh_level_constants = [&]() {
+    NodeVals left, right;
+    node_eval<CURV, RM>(sg, NP, gl, h[0], q[0], rg, k, left);
+    __syncwarp();
+    XW(0, lane) = left.Q;  XW(1, lane) = left.A;  XW(3, lane) = left.Y;  XW(4, lane) = left.Se;  XW(5, lane) = left.QA;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      if (j + 1 < M) {
+        node_eval<CURV, RM>(sg, NP, (j + 1) * G + gl, h[j + 1], q[j + 1], rg, k, right);
+      } else {
+        const int nl = (lane + 1) & 31;
+        right.Q = XW(0, nl);  right.A = XW(1, nl);  right.Y = XW(3, nl);  right.Se = XW(4, nl);
+        right.F = right.Q * XW(5, nl);
+      }
+      double nC, nM, nA, nS;
+      level_constants(left, right, k, nC, nM, nA, nS);
+      PC(0, j) = nC; PC(1, j) = nM; PC(2, j) = nA; PC(3, j) = nS;
+      left = right;
+    }
+    __syncwarp();
+  };
+  refresh_level_constants();
+
+  while (__any_sync(kFull, active)) {
+    if (it == 0) {
       // hydrograph samples at t = level*dt (preissmann.py:215,313)
       if (p.up.series) hyd_up = p.up.series[member * p.up.series_stride + (level < L ? level : L - 1)];
       if (p.dn.series) hyd_dn = p.dn.series[member * p.dn.series_stride + (level < L ? level : L - 1)];
     }
-    if (active && !init_pass) it += 1;
+    if (active) it += 1;
 
     // ------------------------------ node + cell pass ------------------------------
     NodeVals left, right;
@@ -230,7 +259,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     // hand the first node to the lane on the left: it closes that lane's last cell
     __syncwarp();
     XW(0, lane) = left.Q;  XW(1, lane) = left.A;  XW(2, lane) = left.T;  XW(3, lane) = left.Y;  XW(4, lane) = left.Se;
-    XW(5, lane) = left.F;  XW(6, lane) = left.QA; XW(7, lane) = left.w2; XW(8, lane) = left.w3;
+    XW(5, lane) = left.QA; XW(6, lane) = left.w2; XW(7, lane) = left.w3;
     __syncwarp();
 
     double ss = 0.0;
@@ -242,16 +271,15 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       } else {
         const int nl = (lane + 1) & 31;
         right.Q = XW(0, nl);  right.A = XW(1, nl);  right.T = XW(2, nl);  right.Y = XW(3, nl);  right.Se = XW(4, nl);
-        right.F = XW(5, nl);  right.QA = XW(6, nl); right.w2 = XW(7, nl); right.w3 = XW(8, nl);
+        right.QA = XW(5, nl); right.w2 = XW(6, nl); right.w3 = XW(7, nl);
+        right.F = right.Q * right.QA;
         right.w1 = (k.th_dx * right.QA) * (right.QA * right.T);
         right.w4 = k.th_dx2 * right.QA;
       }
       if (EXACT || j < nc) {
         Cell e;
-        double nC, nM, nA, nS;
-        const double r2 = cell_assemble(left, right, k, PC(buf, 0, j), PC(buf, 1, j), PC(buf, 2, j), PC(buf, 3, j), e, nC, nM, nA, nS);
+        const double r2 = cell_assemble(left, right, k, PC(0, j), PC(1, j), PC(2, j), PC(3, j), e);
         ss += (!EXACT || nc > 0) ? r2 : 0.0;
-        PC(buf ^ 1, 0, j) = nC; PC(buf ^ 1, 1, j) = nM; PC(buf ^ 1, 2, j) = nA; PC(buf ^ 1, 3, j) = nS;
         if (j == 0) S = e;
         else {
           Elim el;
@@ -262,12 +290,6 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
         }
       }
       left = right;
-    }
-
-    if (init_pass) {   // level-0 constants are now in buf^1
-      buf ^= 1;
-      init_pass = false;
-      continue;
     }
 
     // ------------------------------ boundary rows ------------------------------
@@ -396,8 +418,12 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
             if (p.storage_stage) p.storage_stage[(size_t)member * L + level] = D.stage_rec;
           }
         }
-        buf ^= 1;
       }
+    }
+    // the accepted iterate becomes the stored level: rebuild its constants before the update is applied
+    // (warp-uniform: one member per warp)
+    if (__any_sync(kFull, active && converged)) refresh_level_constants();
+    if (active) {
 #pragma unroll
       for (int j = 0; j < M; ++j) { h[j] += dh[j]; q[j] += dq[j]; }     // unknowns += delta
       if (converged) {

@@ -2,6 +2,6 @@
 #include "pr_ensemble_kernel.cuh"
 
 #ifndef PR_W4
-#define PR_W4 12
+#define PR_W4 16
 #endif
 PR_DEFINE_ENSEMBLE_FAMILY(4, PR_W4)

@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
       Cell e;
       double cC = 0, cM = 0, cA = 0, cS = 0;
       if (MODE != LONG_INIT) { cC = pc[c]; cM = pc[N + c]; cA = pc[2 * N + c]; cS = pc[3 * N + c]; }
-      ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, cC, cM, cA, cS, e, cand[j][0], cand[j][1], cand[j][2], cand[j][3]);
+      ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, cC, cM, cA, cS, e);
+      if (MODE == LONG_INIT || (MODE == LONG_UPDATE && conv))
+        level_constants(nv[j & 1], nv[(j + 1) & 1], p, cand[j][0], cand[j][1], cand[j][2], cand[j][3]);
       if (j == 0) S = e;
       else merge_cells(S, e, el[j - 1]);
     }

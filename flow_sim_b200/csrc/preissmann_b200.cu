@@ -19,7 +19,7 @@
 #include "pr_long_kernels.cuh"
 
 #ifndef PR_W4
-#define PR_W4 12
+#define PR_W4 16
 #endif
 namespace {
 
