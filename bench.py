@@ -382,7 +382,7 @@ def run_gpu_arm(args) -> dict | None:
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
                      "frac": achieved_tf / tf.value if tf.value > 0 else None, "traffic": traffic,
-                     "kernel": "pr_ensemble_kernel<32,4,false>",
+                     "kernel": "pr_ensemble_kernel<G=32, M=4, W=16, CURV=0, RM=1, EXACT=1>",
                      "flops_per_node_iteration": f_iter, "overbank_share": over,
                      "peak_source": "pr_fp64_peak: register-resident DFMA microbenchmark measured in this run "
                                     "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
