@@ -118,6 +118,124 @@ __global__ void __launch_bounds__(256) pr_dfma_kernel(double* sink, int iters, d
   if (s == 123.456) sink[0] = s;
 }
 
+// Derived result arrays for every (member, level, node): Solver.prepare_results (solver.py:65-98).
+//   level = depth + z_min, area, top_width (TrapezoidalSection.properties, cross_section.py:623-679),
+//   froude_number (hydraulics.froude_num with its 1e-6 clamps), velocity = Q/A, wave_celerity = V + sqrt(g A / T)
+// Pure streaming kernel: 16 B in, up to 48 B out per element, geometry table [F_COUNT][N] from L2.
+struct DerivedParams {
+  long long total;   // M * L * N
+  int N;
+  double g;
+  const double* geo;
+  const double *depth, *flow;
+  double *level, *area, *top_width, *froude, *velocity, *celerity;
+};
+
+__global__ void __launch_bounds__(256) pr_derived_kernel(const __grid_constant__ DerivedParams p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
+    const int nd = (int)(i % p.N);
+    const double h = p.depth[i], Q = p.flow[i];
+#define GEO(f) p.geo[(size_t)(f) * p.N + nd]
+    const double z = GEO(F_Z), b = GEO(F_B), hb = GEO(F_HB);
+    const double hw = z + h;
+    const double d = fmax(0.0, hw - z);
+    double A, T;
+    if (d <= hb) {               // rectangle / simple trapezoid / compound in bank (h_bank staged as 1e300 otherwise)
+      T = b + 2.0 * GEO(F_M) * d;
+      A = (b + T) / 2.0 * d;
+      if (d <= 0.0) { A = 0.0; T = 0.0; }
+    } else {
+      const double dfp = d - hb, mfp = GEO(F_MFP);
+      A = GEO(F_AMF) + (GEO(F_BL) + 0.5 * mfp * dfp) * dfp + (GEO(F_BR) + 0.5 * mfp * dfp) * dfp;
+      T = GEO(F_WB) + 2.0 * mfp * dfp;
+    }
+#undef GEO
+    const double V = Q / fmax(A, 1e-6), D = A / fmax(T, 1e-6);
+    if (p.level) p.level[i] = hw;
+    if (p.area) p.area[i] = A;
+    if (p.top_width) p.top_width[i] = T;
+    if (p.froude) p.froude[i] = V / sqrt(p.g * fmax(D, 1e-6));
+    const double vel = Q / A;
+    if (p.velocity) p.velocity[i] = vel;
+    if (p.celerity) p.celerity[i] = vel + sqrt(p.g * A / T);
+  }
+}
+
+// Steady uniform-flow initial state: Channel._steady_conditions (channel.py:296-305) = per node the root of
+// Q - K(hw) sqrt(S0) on [z_min, z_min + 100] by Brent's method (CrossSection.normal_depth, cross_section.py:184-202;
+// scipy.optimize.brentq, xtol = 2e-12, rtol = 4 eps, maxiter = 100).  One (member, node) per thread.
+struct NormalDepthParams {
+  int N, M;
+  double g;
+  const double* geo;        // derived geometry table [F_COUNT][N]
+  DevGeom raw;              // member roughness overrides
+  const double* bed_slope;  // [N]
+  const double* q0;
+  long long q0_stride;
+  double *ic_h, *ic_q;
+  double th_dx, hth, th_dx2;   // unused scheme constants node_eval reads (zero)
+};
+
+template <int RM>
+__device__ __forceinline__ double normal_flow_residual(const NormalDepthParams& p, int nd, double hw, double Qt,
+                                                       double S0, const Rough& rg) {
+  if (!(S0 > 0.0)) return Qt;                       // CrossSection.normal_flow returns 0 for a non-positive slope
+  const double z = p.geo[(size_t)F_Z * p.N + nd];
+  const double depth = hw - z;
+  if (!(depth > 0.0)) return Qt;                    // K(0) = 0
+  NodeVals nv;
+  NodeConv kc;
+  node_eval<false, RM, true, NormalDepthParams>(p.geo, p.N, nd, depth, 0.0, rg, p, nv, &kc);
+  return Qt - kc.K * sqrt(S0);
+}
+
+template <int RM>
+__global__ void __launch_bounds__(128) pr_normal_depth_kernel(const __grid_constant__ NormalDepthParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.M * p.N) return;
+  const int m = (int)(i / p.N), nd = (int)(i % p.N);
+  const Rough rg = load_rough<RM>(p.raw, m);
+  const double Qt = p.q0[m * p.q0_stride], S0 = p.bed_slope[nd];
+  const double z = p.geo[(size_t)F_Z * p.N + nd];
+  auto f = [&](double hw) { return normal_flow_residual<RM>(p, nd, hw, Qt, S0, rg); };
+  // Brent (scipy/optimize/Zeros/brentq.c)
+  const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+  double xpre = z, xcur = z + 100.0, xblk = 0.0, fpre = f(xpre), fcur = f(xcur), fblk = 0.0, spre = 0.0, scur = 0.0;
+  double root;
+  bool done = false;
+  if (fpre == 0.0) { root = xpre; done = true; }
+  else if (fcur == 0.0) { root = xcur; done = true; }
+  else if (signbit(fpre) == signbit(fcur)) {
+    // brentq raises ValueError -> normal_depth's fallbacks (cross_section.py:196-202)
+    root = (fpre < 0.0) ? z : (fcur > 0.0 ? z + 100.0 : z);
+    done = true;
+  }
+  for (int it = 0; it < 100 && !done; ++it) {
+    if (fpre != 0.0 && fcur != 0.0 && signbit(fpre) != signbit(fcur)) { xblk = xpre; fblk = fpre; spre = scur = xcur - xpre; }
+    if (fabs(fblk) < fabs(fcur)) { xpre = xcur; xcur = xblk; xblk = xpre; fpre = fcur; fcur = fblk; fblk = fpre; }
+    const double delta = (xtol + rtol * fabs(xcur)) / 2.0, sbis = (xblk - xcur) / 2.0;
+    if (fcur == 0.0 || fabs(sbis) < delta) { root = xcur; done = true; break; }
+    if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+      double stry;
+      if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);
+      else {
+        const double dpre = (fpre - fcur) / (xpre - xcur), dblk = (fblk - fcur) / (xblk - xcur);
+        stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+      }
+      if (2.0 * fabs(stry) < fmin(fabs(spre), 3.0 * fabs(sbis) - delta)) { spre = scur; scur = stry; }
+      else { spre = sbis; scur = sbis; }
+    } else { spre = sbis; scur = sbis; }
+    xpre = xcur; fpre = fcur;
+    if (fabs(scur) > delta) xcur += scur;
+    else xcur += (sbis > 0.0 ? delta : -delta);
+    fcur = f(xcur);
+  }
+  if (!done) root = xcur;
+  p.ic_h[i] = root - z;
+  p.ic_q[i] = Qt;
+}
+
 // Accuracy probe of the FP64 primitives (tests/test_gpu_math.py): out[0..5][i] = fast_rcp, fast_sqrt, fast_rsqrt,
 // fast_rcbrt of x[i] and the raw SFU seeds of 1/x and x^-1/2.
 __global__ void pr_math_probe_kernel(const double* x, int n, double* out) {

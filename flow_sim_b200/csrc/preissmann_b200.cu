@@ -237,6 +237,14 @@ int launch_gvf_rm(const pr::GvfParams& p, unsigned grid, size_t smem, cudaStream
   }
 }
 
+template <int RM>
+int launch_normal_depth(const pr::NormalDepthParams& p, cudaStream_t s) {
+  const long long total = (long long)p.M * p.N;
+  pr::pr_normal_depth_kernel<RM><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return PR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -379,6 +387,79 @@ int pr_rating_objective(const pr_config* cfg, const double* up_flow, const doubl
   CUDA_TRY(cudaGetLastError());
   cudaError_t e = st.finish();
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_rating_objective: %s", cudaGetErrorString(e));
+  return PR_OK;
+}
+
+int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* depth, const double* flow,
+                       double* level, double* area, double* top_width, double* froude, double* velocity,
+                       double* celerity, void* cuda_stream) {
+  if (int rc = check_config(cfg)) return rc;
+  if (!depth || !flow) return fail(PR_ERR_ARG, "derived results: depth / flow are NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t N = cfg->n_nodes, total = (size_t)cfg->n_members * cfg->n_levels * N;
+  Stage st(cfg->mem == PR_MEM_HOST, s);
+  pr::DevGeom dg;
+  if (int rc = stage_geom(*cfg, geom, st, dg)) return rc;
+  pr::DerivedParams p;
+  p.total = (long long)total; p.N = (int)N; p.g = cfg->g;
+  p.depth = st.in(depth, total); p.flow = st.in(flow, total);
+  p.level = st.out(level, total); p.area = st.out(area, total); p.top_width = st.out(top_width, total);
+  p.froude = st.out(froude, total); p.velocity = st.out(velocity, total); p.celerity = st.out(celerity, total);
+  double* table = nullptr;
+  if (st.err == cudaSuccess) st.err = cudaMalloc(&table, sizeof(double) * pr::F_COUNT * N);
+  if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
+  st.allocs.push_back(table);
+  p.geo = table;
+  pr::pr_long_geometry<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(dg, (int)N, table);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long want = (long long)((total + 255) / 256);
+  const unsigned grid = (unsigned)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+  pr::pr_derived_kernel<<<grid, 256, 0, s>>>(p);
+  g_launches.fetch_add(2);
+  CUDA_TRY(cudaGetLastError());
+  cudaError_t e = st.finish();
+  if (cfg->mem == PR_MEM_DEVICE && e == cudaSuccess) e = cudaStreamSynchronize(s);   // the table is freed on return
+  if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_derived_results: %s", cudaGetErrorString(e));
+  return PR_OK;
+}
+
+int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom, const double* bed_slope,
+                                       const double* q0, int64_t q0_member_stride, double* ic_depth,
+                                       double* ic_flow, void* cuda_stream) {
+  if (int rc = check_config(cfg)) return rc;
+  if (!bed_slope || !q0 || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "normal depth: NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t N = cfg->n_nodes, M = cfg->n_members;
+  Stage st(cfg->mem == PR_MEM_HOST, s);
+  pr::NormalDepthParams p;
+  std::memset(&p, 0, sizeof p);
+  p.N = (int)N; p.M = (int)M; p.g = cfg->g;
+  if (int rc = stage_geom(*cfg, geom, st, p.raw)) return rc;
+  p.bed_slope = st.in(bed_slope, N);
+  p.q0 = st.in(q0, q0_member_stride ? M * (size_t)q0_member_stride : 1);
+  p.q0_stride = q0_member_stride;
+  p.ic_h = st.out(ic_depth, M * N);
+  p.ic_q = st.out(ic_flow, M * N);
+  double* table = nullptr;
+  if (st.err == cudaSuccess) st.err = cudaMalloc(&table, sizeof(double) * pr::F_COUNT * N);
+  if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
+  st.allocs.push_back(table);
+  p.geo = table;
+  pr::pr_long_geometry<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(p.raw, (int)N, table);
+  int rc;
+  switch (pr::rough_mode(p.raw)) {
+    case 0: rc = launch_normal_depth<0>(p, s); break;
+    case 1: rc = launch_normal_depth<1>(p, s); break;
+    case 2: rc = launch_normal_depth<2>(p, s); break;
+    default: rc = launch_normal_depth<3>(p, s);
+  }
+  if (rc) return rc;
+  g_launches.fetch_add(2);
+  cudaError_t e = st.finish();
+  if (cfg->mem == PR_MEM_DEVICE && e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_normal_depth_initial_conditions: %s", cudaGetErrorString(e));
   return PR_OK;
 }
 

@@ -239,6 +239,8 @@ def flatten_solver(solver, tolerance: float = 1e-4, max_iter: int = 100) -> Flat
     if getattr(ds, "initial_depth", None) is not None:
         flat.meta["downstream_depth"] = float(ds.initial_depth)
     flat.meta["ic_method"] = str(getattr(ch, "interpolation_method", ""))
+    flat.meta["bed_slope"] = np.array([float("nan") if getattr(xs, "bed_slope", None) is None else float(xs.bed_slope)
+                                       for xs in ch.xs_at_node], dtype=np.float64)
     return flat
 
 

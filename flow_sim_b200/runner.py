@@ -187,3 +187,60 @@ def rating_objective(n_levels: int, up_flow, up_depth, z0: float, q_query, h_tar
     rc = lib.pr_rating_objective(C.byref(cfg), fq, fh, float(z0), qq, ht, nq, lp, rp, C.c_void_p(stream or 0))
     abi.check(lib, rc, "pr_rating_objective")
     return lv, rm
+
+
+def normal_depth_initial_conditions(flat: FlatCase, n_members: int, q0, bed_slope=None,
+                                    mem: int = abi.PR_MEM_HOST, device=None, stream=None):
+    """Channel._steady_conditions (channel.py:296-305) for every member on the device: Brent's method per node.
+    Returns (depth[M,N], flow[M,N])."""
+    lib = abi.load_library()
+    ar = abi.Arena(mem, device)
+    cfg = _config(flat, n_members, mem, device)
+    g = _geom_struct(flat, ar, n_members)
+    slope = flat.meta["bed_slope"] if bed_slope is None else bed_slope
+    if mem == abi.PR_MEM_HOST or not hasattr(q0, "data_ptr"):
+        q0 = np.atleast_1d(np.asarray(q0, dtype=np.float64))
+    n_q0 = q0.shape[0]
+    if n_q0 not in (1, n_members):
+        raise ValueError("q0 must have 1 or M entries")
+    sp, _ = ar.put(slope)
+    q0p, _ = ar.put(q0)
+    hp, h = ar.empty((n_members, flat.n_nodes))
+    qp, q = ar.empty((n_members, flat.n_nodes))
+    rc = lib.pr_normal_depth_initial_conditions(C.byref(cfg), C.byref(g), sp, q0p, 0 if n_q0 == 1 else 1, hp, qp,
+                                                C.c_void_p(stream or 0))
+    abi.check(lib, rc, "pr_normal_depth_initial_conditions")
+    return h, q
+
+
+DERIVED = ("level", "area", "top_width", "froude_number", "velocity", "wave_celerity")
+
+
+def derived_results(flat: FlatCase, depth, flow, mem: int = abi.PR_MEM_HOST, device=None, stream=None,
+                    want=DERIVED) -> dict:
+    """The array part of Solver.prepare_results (solver.py:65-98) for results shaped [M, levels, N]."""
+    lib = abi.load_library()
+    ar = abi.Arena(mem, device)
+    M, L, N = depth.shape
+    if (L, N) != (flat.n_levels, flat.n_nodes):
+        raise ValueError("depth must be [members, levels, nodes]")
+    cfg = _config(flat, M, mem, device, abi.PR_OUT_FULL)
+    g = _geom_struct(flat, ar, M) if flat.member_n_main is None and flat.member_n_fp is None else None
+    if g is None:
+        import copy
+
+        f2 = copy.copy(flat); f2.member_n_main = None; f2.member_n_fp = None   # geometry only, roughness is irrelevant here
+        g = _geom_struct(f2, ar, M)
+    dp, _ = ar.put(depth)
+    fp, _ = ar.put(flow)
+    ptrs, bufs = [], {}
+    for name in DERIVED:
+        if name in want:
+            p, b = ar.empty((M, L, N))
+            bufs[name] = b
+        else:
+            p = abi.c_double_p()
+        ptrs.append(p)
+    rc = lib.pr_derived_results(C.byref(cfg), C.byref(g), dp, fp, *ptrs, C.c_void_p(stream or 0))
+    abi.check(lib, rc, "pr_derived_results")
+    return bufs

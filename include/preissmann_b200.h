@@ -190,6 +190,20 @@ int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const d
                               int64_t q0_member_stride, double downstream_depth, double* ic_depth,
                               double* ic_flow, int32_t* status, void* cuda_stream);
 
+/* Replaces Channel._steady_conditions (channel.py:296-305): per member and node the normal depth for q0, i.e.
+ * the root of Q - K(hw) sqrt(S0) on [z_min, z_min+100] by Brent's method (CrossSection.normal_depth,
+ * cross_section.py:184-202 -> scipy.optimize.brentq).  bed_slope: [N] cross-section bed slopes.
+ * Writes ic_depth / ic_flow [M][N]. */
+int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom, const double* bed_slope,
+                                       const double* q0, int64_t q0_member_stride, double* ic_depth,
+                                       double* ic_flow, void* cuda_stream);
+
+/* Replaces the array part of Solver.prepare_results (solver.py:65-98) for [M][levels][N] results:
+ * level, area, top_width, froude_number, velocity, wave_celerity (any output pointer may be NULL). */
+int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* depth, const double* flow,
+                       double* level, double* area, double* top_width, double* froude, double* velocity,
+                       double* celerity, void* cuda_stream);
+
 /* Replaces the calibration objective of cases/gerd_roseires (model.py:105-113 + n_calibrate.py:55-63):
  * levels[m][j] = np.interp(Q[j], flow[m][:,0], depth[m][:,0] + z0);  rmse[m] = mean((levels-H)^2)^0.5.
  * up_flow/up_depth are [M][levels] (PR_OUT_UPSTREAM layout). */
