@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) pr_dfma_kernel(double* sink, int iters, d
 //   froude_number (hydraulics.froude_num with its 1e-6 clamps), velocity = Q/A, wave_celerity = V + sqrt(g A / T)
 // Pure streaming kernel: 16 B in, up to 48 B out per element, geometry table [F_COUNT][N] from L2.
 struct DerivedParams {
-  long long total;   // M * L * N
+  long long rows;    // M * L
   int N;
   double g;
   const double* geo;
@@ -131,26 +131,30 @@ struct DerivedParams {
   double *level, *area, *top_width, *froude, *velocity, *celerity;
 };
 
-__global__ void __launch_bounds__(256) pr_derived_kernel(const __grid_constant__ DerivedParams p) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
-    const int nd = (int)(i % p.N);
-    const double h = p.depth[i], Q = p.flow[i];
+// Thread = one node: its geometry is loaded once into registers, then the thread walks down the (member, level)
+// rows, so every load and store of a warp is a contiguous 256-byte segment.
+__global__ void __launch_bounds__(128) pr_derived_kernel(const __grid_constant__ DerivedParams p) {
+  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nd >= p.N) return;
 #define GEO(f) p.geo[(size_t)(f) * p.N + nd]
-    const double z = GEO(F_Z), b = GEO(F_B), hb = GEO(F_HB);
+  const double z = GEO(F_Z), b = GEO(F_B), hb = GEO(F_HB), m2 = 2.0 * GEO(F_M);
+  const double mfp = GEO(F_MFP), bl = GEO(F_BL), br = GEO(F_BR), amf = GEO(F_AMF), wb = GEO(F_WB);
+#undef GEO
+  for (long long r = blockIdx.y; r < p.rows; r += gridDim.y) {
+    const size_t i = (size_t)r * p.N + nd;
+    const double h = p.depth[i], Q = p.flow[i];
     const double hw = z + h;
     const double d = fmax(0.0, hw - z);
     double A, T;
     if (d <= hb) {               // rectangle / simple trapezoid / compound in bank (h_bank staged as 1e300 otherwise)
-      T = b + 2.0 * GEO(F_M) * d;
+      T = b + m2 * d;
       A = (b + T) / 2.0 * d;
       if (d <= 0.0) { A = 0.0; T = 0.0; }
     } else {
-      const double dfp = d - hb, mfp = GEO(F_MFP);
-      A = GEO(F_AMF) + (GEO(F_BL) + 0.5 * mfp * dfp) * dfp + (GEO(F_BR) + 0.5 * mfp * dfp) * dfp;
-      T = GEO(F_WB) + 2.0 * mfp * dfp;
+      const double dfp = d - hb;
+      A = amf + (bl + 0.5 * mfp * dfp) * dfp + (br + 0.5 * mfp * dfp) * dfp;
+      T = wb + 2.0 * mfp * dfp;
     }
-#undef GEO
     const double V = Q / fmax(A, 1e-6), D = A / fmax(T, 1e-6);
     if (p.level) p.level[i] = hw;
     if (p.area) p.area[i] = A;

@@ -401,7 +401,7 @@ int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* 
   pr::DevGeom dg;
   if (int rc = stage_geom(*cfg, geom, st, dg)) return rc;
   pr::DerivedParams p;
-  p.total = (long long)total; p.N = (int)N; p.g = cfg->g;
+  p.rows = (long long)cfg->n_members * cfg->n_levels; p.N = (int)N; p.g = cfg->g;
   p.depth = st.in(depth, total); p.flow = st.in(flow, total);
   p.level = st.out(level, total); p.area = st.out(area, total); p.top_width = st.out(top_width, total);
   p.froude = st.out(froude, total); p.velocity = st.out(velocity, total); p.celerity = st.out(celerity, total);
@@ -414,9 +414,11 @@ int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long want = (long long)((total + 255) / 256);
-  const unsigned grid = (unsigned)(want < (long long)sms * 16 ? want : (long long)sms * 16);
-  pr::pr_derived_kernel<<<grid, 256, 0, s>>>(p);
+  const unsigned gx = (unsigned)((N + 127) / 128);
+  long long gy = ((long long)sms * 16 + gx - 1) / gx;          // ~16 CTAs of 4 warps per SM in total
+  if (gy > p.rows) gy = p.rows;
+  if (gy > 65535) gy = 65535;
+  pr::pr_derived_kernel<<<dim3(gx, (unsigned)gy), 128, 0, s>>>(p);
   g_launches.fetch_add(2);
   CUDA_TRY(cudaGetLastError());
   cudaError_t e = st.finish();
