@@ -22,6 +22,9 @@
 // 112 B (iterate read twice + 4 level constants per cell read twice + iterate written).
 #pragma once
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <utility>
 #include <vector>
@@ -120,12 +123,14 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
     h[j] = xh[nd];
     qq[j] = xq[nd];
   }
+  // elimination records of the UPDATE pass live in shared memory ([record][field][lane] per warp)
+  extern __shared__ double long_smem[];
+  double* elw = long_smem + (size_t)(threadIdx.x >> 5) * ((kLongM - 1) * 9 * 32);
+#define LEL(j, c) elw[((j)*9 + (c)) * 32 + lane]
   NodeVals nv[2];
   node_eval<false, 0, false, DevParams, CMP>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
   double ss = 0.0;
   Cell S;
-  Elim el[kLongM - 1];
-  double cand[kLongM][4];
 #pragma unroll
   for (int j = 0; j < kLongM; ++j) {
     const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
@@ -136,20 +141,27 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
       double cC = 0, cM = 0, cA = 0, cS = 0;
       if (MODE != LONG_INIT) { cC = pc[c]; cM = pc[N + c]; cA = pc[2 * N + c]; cS = pc[3 * N + c]; }
       ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, cC, cM, cA, cS, e);
-      if (MODE == LONG_INIT || (MODE == LONG_UPDATE && conv))
-        level_constants(nv[j & 1], nv[(j + 1) & 1], p, cand[j][0], cand[j][1], cand[j][2], cand[j][3]);
+      if (MODE == LONG_INIT || (MODE == LONG_UPDATE && conv)) {
+        // this state is (becomes) the stored level: its level constants replace the old ones, which this lane
+        // has just consumed and nobody else reads
+        double nC, nM, nA, nS;
+        level_constants(nv[j & 1], nv[(j + 1) & 1], p, nC, nM, nA, nS);
+        pc[c] = nC; pc[N + c] = nM; pc[2 * N + c] = nA; pc[3 * N + c] = nS;
+      }
       if (j == 0) S = e;
-      else merge_cells(S, e, el[j - 1]);
+      else {
+        Elim el;
+        merge_cells(S, e, el);
+        if (MODE == LONG_UPDATE) {
+          LEL(j - 1, 0) = el.i11; LEL(j - 1, 1) = el.i12; LEL(j - 1, 2) = el.i21; LEL(j - 1, 3) = el.i22;
+          LEL(j - 1, 4) = el.m1;  LEL(j - 1, 5) = el.m2;  LEL(j - 1, 6) = el.rm;
+          LEL(j - 1, 7) = el.c3;  LEL(j - 1, 8) = el.rc;
+        }
+      }
     }
   }
 
-  if (MODE == LONG_INIT) {
-    // level 0: store the initial state and build its level constants
-#pragma unroll
-    for (int j = 0; j < kLongM; ++j)
-      if (j < nc) { const int c = c0 + j; pc[c] = cand[j][0]; pc[N + c] = cand[j][1]; pc[2 * N + c] = cand[j][2]; pc[3 * N + c] = cand[j][3]; }
-    return;
-  }
+  if (MODE == LONG_INIT) return;   // level 0: only the level constants of the initial state were needed
 
   if (MODE == LONG_CONDENSE) {
     // warp tree-merge of the per-lane cells -> one cell for the tile
@@ -200,11 +212,10 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
 #pragma unroll
     for (int j = kLongM - 1; j >= 1; --j) {
       if (j < nc) {
-        const Elim& e = el[j - 1];
-        const double t1 = e.rm - e.m1 * dh0 - e.m2 * dq0;
-        const double t2 = e.rc - e.c3 * rh - p.th_dx * rq;
-        dh[j] = e.i11 * t1 + e.i12 * t2;
-        dq[j] = e.i21 * t1 + e.i22 * t2;
+        const double t1 = LEL(j - 1, 6) - LEL(j - 1, 4) * dh0 - LEL(j - 1, 5) * dq0;
+        const double t2 = LEL(j - 1, 8) - LEL(j - 1, 7) * rh - p.th_dx * rq;
+        dh[j] = LEL(j - 1, 0) * t1 + LEL(j - 1, 1) * t2;
+        dq[j] = LEL(j - 1, 2) * t1 + LEL(j - 1, 3) * t2;
         rh = dh[j]; rq = dq[j];
       } else { dh[j] = 0.0; dq[j] = 0.0; }
     }
@@ -217,21 +228,22 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
   for (int j = 0; j < kLongM; ++j) {
     if (j < nc) {
       const int nd = c0 + j;
-      if (conv) {
-        if (p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[j]; if (p.out_q) p.out_q[orow + nd] = qq[j]; }
-        const int c = nd;
-        pc[c] = cand[j][0]; pc[N + c] = cand[j][1]; pc[2 * N + c] = cand[j][2]; pc[3 * N + c] = cand[j][3];
-      }
+      if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[j]; if (p.out_q) p.out_q[orow + nd] = qq[j]; }
       xh_out[nd] = h[j] + dh[j];
       xq_out[nd] = qq[j] + dq[j];
     }
   }
   if (nc > 0 && c0 + nc == N - 1) {      // this lane's last cell ends at the downstream boundary node
     const int nd = N - 1;
-    if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[nc]; if (p.out_q) p.out_q[orow + nd] = qq[nc]; }
-    xh_out[nd] = h[nc] + yR1;
-    xq_out[nd] = qq[nc] + yR2;
+    double hl = h[1], ql = qq[1];          // h[nc] without dynamic indexing of a register array
+#pragma unroll
+    for (int j = 2; j <= kLongM; ++j)
+      if (j == nc) { hl = h[j]; ql = qq[j]; }
+    if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = hl; if (p.out_q) p.out_q[orow + nd] = ql; }
+    xh_out[nd] = hl + yR1;
+    xq_out[nd] = ql + yR2;
   }
+#undef LEL
   if (conv && p.out_mode == PR_OUT_UPSTREAM && t == 0 && lane == 0) {
     if (p.out_h) p.out_h[(size_t)m * p.L + lvl] = h[0];
     if (p.out_q) p.out_q[(size_t)m * p.L + lvl] = qq[0];
@@ -416,6 +428,32 @@ __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
   }
 }
 
+// Grow-only device workspace of the long-reach path, kept between calls (allocating and freeing ~7 GB per call
+// costs 50-200 ms); released by pr_release_workspace() or at process exit by the driver.
+struct LongWorkspace {
+  static constexpr int kSlots = 16;
+  void* ptr[kSlots] = {};
+  size_t bytes[kSlots] = {};
+  int device = -1;
+  void release() {
+    for (int i = 0; i < kSlots; ++i) { if (ptr[i]) cudaFree(ptr[i]); ptr[i] = nullptr; bytes[i] = 0; }
+  }
+  void* get(int slot, size_t n, cudaError_t& e) {
+    if (e != cudaSuccess) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != device) { release(); device = dev; }
+    if (bytes[slot] < n) {
+      if (ptr[slot]) cudaFree(ptr[slot]);
+      ptr[slot] = nullptr; bytes[slot] = 0;
+      e = cudaMalloc(&ptr[slot], n);
+      if (e == cudaSuccess) bytes[slot] = n;
+    }
+    return ptr[slot];
+  }
+};
+inline LongWorkspace& long_workspace() { static LongWorkspace w; return w; }
+
 template <bool CMP>
 inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, std::atomic<long long>& launches,
                             std::string& err) {
@@ -427,17 +465,16 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
   const int T = (N - 1 + kTileCells - 1) / kTileCells;
   const int Kc = (T + 30) / 31;           // tile cells per lane so that the chain has <= 32 rows
   if (Kc > kChainMaxK) return fail(PR_ERR_UNSUPPORTED, "long-reach path: n_nodes exceeds 32*64*128");
+  const bool timing = std::getenv("PR_LONG_TIMING") != nullptr;     // diagnostics: phase times on stderr
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
   LongParams q;
   q.p = p;
   q.T = T; q.Kc = Kc;
-  std::vector<void*> allocs;
   cudaError_t e = cudaSuccess;
-  auto dalloc = [&](size_t bytes) -> void* {
-    void* d = nullptr;
-    if (e == cudaSuccess) e = cudaMalloc(&d, bytes);
-    if (e == cudaSuccess) allocs.push_back(d);
-    return d;
-  };
+  int slot = 0;
+  LongWorkspace& ws = long_workspace();
+  auto dalloc = [&](size_t bytes) -> void* { return ws.get(slot++, bytes, e); };
   double* geo = (double*)dalloc(sizeof(double) * F_COUNT * (size_t)N);
   q.geo = geo;
   q.xh = (double*)dalloc(sizeof(double) * (size_t)M * N);
@@ -454,8 +491,9 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
   q.active = (int*)dalloc(sizeof(int) * M); q.conv = (int*)dalloc(sizeof(int) * M);
   q.out_level = (int*)dalloc(sizeof(int) * M);
   q.n_done = (int*)dalloc(sizeof(int));
-  auto cleanup = [&]() { for (void* d : allocs) cudaFree(d); };
+  auto cleanup = [&]() {};   // the workspace is cached
   if (e != cudaSuccess) { cleanup(); return fail(PR_ERR_CUDA, std::string("long-reach workspace: ") + cudaGetErrorString(e)); }
+  const double t_alloc = now();
   cudaMemsetAsync(q.n_done, 0, sizeof(int), s);
   cudaMemsetAsync(q.active, 0, sizeof(int) * M, s);
 
@@ -464,16 +502,17 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
   const long long warps = (long long)M * T;
   const unsigned tile_grid = (unsigned)((warps + 3) / 4);
-  pr_long_tile<LONG_INIT, CMP><<<tile_grid, 128, 0, s>>>(q);
+  const size_t tile_smem = sizeof(double) * 4 * (kLongM - 1) * 9 * 32;   // elimination records, 4 warps per CTA
+  pr_long_tile<LONG_INIT, CMP><<<tile_grid, 128, tile_smem, s>>>(q);
   launches.fetch_add(3);
   const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
   e = cudaFuncSetAttribute(pr_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
   int done = (p.L > 1) ? 0 : M;
   const long long max_trips = (long long)(p.L - 1) * (p.max_iter > 0 ? p.max_iter : 1) + 1;
   for (long long trip = 0; trip < max_trips && done < M && e == cudaSuccess; ++trip) {
-    pr_long_tile<LONG_CONDENSE, CMP><<<tile_grid, 128, 0, s>>>(q);
+    pr_long_tile<LONG_CONDENSE, CMP><<<tile_grid, 128, tile_smem, s>>>(q);
     pr_long_chain<<<M, 32, chain_smem, s>>>(q);
-    pr_long_tile<LONG_UPDATE, CMP><<<tile_grid, 128, 0, s>>>(q);
+    pr_long_tile<LONG_UPDATE, CMP><<<tile_grid, 128, tile_smem, s>>>(q);
     pr_long_retire<<<(M + 127) / 128, 128, 0, s>>>(q);
     launches.fetch_add(4);
     std::swap(q.xh, q.xh_out);
@@ -487,7 +526,11 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
     e = cudaStreamSynchronize(s);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
+  const double t_loop = now();
   cleanup();
+  if (timing)
+    fprintf(stderr, "[pr_long] N=%d M=%d tiles=%d Kc=%d: workspace alloc %.2f ms, kernels %.2f ms, free %.2f ms\n", N, M, T, Kc,
+            t_alloc - t_start, t_loop - t_alloc, now() - t_loop);
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, std::string("long-reach path: ") + cudaGetErrorString(e));
   return PR_OK;
 }

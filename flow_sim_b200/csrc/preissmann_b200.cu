@@ -465,6 +465,11 @@ int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom
   return PR_OK;
 }
 
+int pr_release_workspace(void) {
+  pr::long_workspace().release();
+  return PR_OK;
+}
+
 int pr_math_probe(const double* x_host, int32_t n, double* out_host) {
   if (!x_host || !out_host || n < 1) return fail(PR_ERR_ARG, "pr_math_probe: NULL / empty input");
   double *dx = nullptr, *dout = nullptr;

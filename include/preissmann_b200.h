@@ -215,6 +215,10 @@ int pr_rating_objective(const pr_config* cfg, const double* up_flow, const doubl
  * asks for.  Runs a register-resident DFMA kernel for about `millis` ms. */
 int pr_fp64_peak(double millis, double* tflops_out);
 
+/* The long-reach path (n_nodes > 249) keeps its device workspace (iterate, level constants, tile cells) between
+ * calls; this frees it. */
+int pr_release_workspace(void);
+
 /* Diagnostics: evaluates the device's branch-free FP64 primitives (reciprocal, square root, reciprocal square
  * root, reciprocal cube root - csrc/pr_device.cuh) and their raw SFU seeds on n HOST values;
  * out_host is [6][n].  Used by tests/test_gpu_math.py to bound their error against IEEE results. */
