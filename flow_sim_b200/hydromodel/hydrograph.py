@@ -1,28 +1,49 @@
-"""``Hydrograph`` (hydrograph.py:3-33): an arbitrary callable f(t) or a (time, value) table."""
+"""``Hydrograph``: a time series given either as a callable f(t) or as a two-column (time [s], value) table
+(same constructor keywords and methods as the reference's class, hydrograph.py:3-33).
+
+The solver never interpolates inside the time loop: ``sample`` evaluates the hydrograph once at the grid times
+t = k*dt, which is all the reference ever asks of it (preissmann.py:215,313), and the resulting vector is what
+crosses the C ABI (``pr_bc.series``).
+"""
 from __future__ import annotations
+
+from typing import Callable, Optional
 
 import numpy as np
 
 
 class Hydrograph:
-    def __init__(self, function=None, table=None):
+    def __init__(self, function: Optional[Callable[[float], float]] = None, table: Optional[np.ndarray] = None):
         self.table = table
-        self.used_function = self.interpolate_hydrograph if function is None else function
+        self._fn = function
 
-    def interpolate_hydrograph(self, time):
+    # the reference exposes the active evaluator as an attribute; keep the name readable and writable
+    @property
+    def used_function(self) -> Callable[[float], float]:
+        return self._fn if self._fn is not None else self.interpolate_hydrograph
+
+    @used_function.setter
+    def used_function(self, fn) -> None:
+        self._fn = fn
+
+    def interpolate_hydrograph(self, time: float) -> float:
+        """Piecewise-linear look-up in the table, constant beyond its ends (numpy.interp)."""
         if self.table is None:
             raise ValueError("Hydrograph is not defined.")
-        return float(np.interp(time, self.table[:, 0], self.table[:, 1]))
+        t, v = np.asarray(self.table)[:, 0], np.asarray(self.table)[:, 1]
+        return float(np.interp(time, t, v))
 
-    def get_at(self, time):
+    def get_at(self, time: float) -> float:
         return self.used_function(time)
 
-    def set_table(self, table):
+    __call__ = get_at
+
+    def set_table(self, table: np.ndarray) -> None:
         self.table = table
 
-    def set_function(self, func):
-        self.used_function = func
+    def set_function(self, func: Callable[[float], float]) -> None:
+        self._fn = func
 
     def sample(self, n_levels: int, dt) -> np.ndarray:
-        """Values at t = k*dt, k = 0..n_levels-1: all the solver ever asks for (preissmann.py:215,313)."""
-        return np.array([float(self.get_at(k * dt)) for k in range(n_levels)], dtype=np.float64)
+        """Values on the time grid 0, dt, 2 dt, ... ((n_levels-1) dt)."""
+        return np.fromiter((float(self.get_at(k * dt)) for k in range(n_levels)), dtype=np.float64, count=n_levels)
