@@ -12,7 +12,7 @@ import threading
 
 import numpy as np
 
-PR_ABI_VERSION = 3
+PR_ABI_VERSION = 4
 PR_MAX_POLY = 12
 PR_MAX_GATES = 8
 
@@ -78,6 +78,11 @@ class pr_bc(C.Structure):
         ("rating", pr_rating),
         ("storage_area", C.c_double), ("storage_min_stage", C.c_double),
         ("storage_ymin", C.c_double), ("storage_ymax", C.c_double),
+        ("storage_curve_stage", c_double_p), ("storage_curve_area", c_double_p),
+        ("storage_curve_len", C.c_int32), ("storage_capture_losses", C.c_int32),
+        ("storage_alpha", C.c_double), ("storage_beta", C.c_double),
+        ("storage_reservoir_length", C.c_double), ("storage_Kq", C.c_double),
+        ("storage_outflow", pr_rating),
     ]
 
 

@@ -34,6 +34,12 @@ struct DevBC {
   long long series_stride;
   DevRating rc;
   double st_area, st_inv_area, st_min_stage;
+  // general lumped storage (lumped_storage.py:24-179): tabulated area curve, outflow rating curve, head losses
+  int st_general;                 // 0 = constant area, no outflow, no losses (closed form)
+  int st_curve_len, st_losses;
+  const double *st_curve_stage, *st_curve_area;
+  double st_alpha, st_beta, st_step, st_ymin, st_ymax, st_length, st_kq;
+  DevRating st_out;
 };
 
 struct DevGeom {
@@ -174,6 +180,8 @@ struct NodeVals {
 struct NodeConv {
   double K;     // conveyance                        (cross_section.py:741-754)
   double dKA;   // dK/dA                             (cross_section.py:756-764)
+  double A, Sf, dSfA, dSfQ;   // area and friction slope with its derivatives (hydraulics.py:42-92), for the
+                              // head losses of the lumped storage (lumped_storage.py:47-143)
 };
 
 // Node pass.  h = depth unknown, Q = discharge unknown, idx = node slot in shared memory.
@@ -308,6 +316,10 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
   if (WANT_K) {
     kc->K = K;
     kc->dKA = K * dKA_over_K;
+    kc->A = A;
+    kc->Sf = Sf;
+    kc->dSfA = -2.0 * Sf * dKA_over_K;
+    kc->dSfQ = 2.0 * absQ * invK2;
   }
 #undef GEO
 }
@@ -353,20 +365,112 @@ __device__ __forceinline__ double rating_dq(const DevRating& r, double stage) {
   }
 }
 
+// ---- Brent's method (scipy/optimize/Zeros/brentq.c: xtol = 2e-12, rtol = 4 eps, maxiter = 100) -----------------
+// sign_error mirrors brentq's ValueError when f(xa) and f(xb) have the same sign.
+template <class F>
+__device__ __forceinline__ double brent_root(F f, const double xa, const double xb, bool& sign_error) {
+  const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+  double xpre = xa, xcur = xb, xblk = 0.0, fpre = f(xpre), fcur = f(xcur), fblk = 0.0, spre = 0.0, scur = 0.0;
+  sign_error = false;
+  if (fpre == 0.0) return xpre;
+  if (fcur == 0.0) return xcur;
+  if (signbit(fpre) == signbit(fcur)) { sign_error = true; return nan(""); }
+  for (int it = 0; it < 100; ++it) {
+    if (fpre != 0.0 && fcur != 0.0 && signbit(fpre) != signbit(fcur)) { xblk = xpre; fblk = fpre; spre = scur = xcur - xpre; }
+    if (fabs(fblk) < fabs(fcur)) { xpre = xcur; xcur = xblk; xblk = xpre; fpre = fcur; fcur = fblk; fblk = fpre; }
+    const double delta = (xtol + rtol * fabs(xcur)) / 2.0, sbis = (xblk - xcur) / 2.0;
+    if (fcur == 0.0 || fabs(sbis) < delta) return xcur;
+    if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+      double stry;
+      if (xpre == xblk) stry = -fcur * (xcur - xpre) / (fcur - fpre);
+      else {
+        const double dpre = (fpre - fcur) / (xpre - xcur), dblk = (fblk - fcur) / (xblk - xcur);
+        stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+      }
+      if (2.0 * fabs(stry) < fmin(fabs(spre), 3.0 * fabs(sbis) - delta)) { spre = scur; scur = stry; }
+      else { spre = sbis; scur = sbis; }
+    } else { spre = sbis; scur = sbis; }
+    xpre = xcur; fpre = fcur;
+    if (fabs(scur) > delta) xcur += scur;
+    else xcur += (sbis > 0.0 ? delta : -delta);
+    fcur = f(xcur);
+  }
+  return xcur;
+}
+
+// numpy.interp on an increasing table
+__device__ __forceinline__ double table_interp(double x, const double* xp, const double* fp, int n) {
+  if (x != x) return x;
+  if (x > xp[n - 1]) return fp[n - 1];
+  if (x < xp[0]) return fp[0];
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if (x >= xp[mid]) lo = mid + 1; else hi = mid;
+  }
+  const int j = lo - 1;
+  if (j >= n - 1) return fp[n - 1];
+  if (xp[j] == x) return fp[j];
+  return (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]) * (x - xp[j]) + fp[j];
+}
+
+// forward declaration (rating curves are defined above bc_eval)
+__device__ __forceinline__ double rating_q(const DevRating& r, double stage);
+
+// LumpedStorage.area_at / net_vol_change / mass_balance (lumped_storage.py:24-45,155-179), general form
+__device__ __forceinline__ double storage_area_at(const DevBC& b, double stage) {
+  if (b.st_curve_len <= 0) return b.st_area;
+  return b.st_alpha * table_interp(stage + b.st_beta, b.st_curve_stage, b.st_curve_area, b.st_curve_len);
+}
+
+__device__ inline double storage_net_vol_change(const DevBC& b, double Y1, double Y2) {
+  if (b.st_curve_len <= 0) return (Y2 - Y1) * b.st_area;
+  const int n = (int)(fabs(Y2 - Y1) / b.st_step);
+  if (n > 2) {      // np.trapezoid over np.linspace(Y1, Y2, n)
+    const double dstep = (Y2 - Y1) / (n - 1);
+    double sum = 0.0, y_prev = Y1, a_prev = storage_area_at(b, Y1);
+    for (int i = 1; i < n; ++i) {
+      const double y = (i == n - 1) ? Y2 : i * dstep + Y1;
+      const double a = storage_area_at(b, y);
+      sum += (y - y_prev) * (a + a_prev) / 2.0;
+      y_prev = y; a_prev = a;
+    }
+    return sum;
+  }
+  return 0.5 * (storage_area_at(b, Y2) + storage_area_at(b, Y1)) * (Y2 - Y1);
+}
+
+__device__ inline double storage_mass_balance(const DevBC& b, double vol_in, double Y_old, double dt, bool& failed) {
+  const double q_old = b.st_out.type != PR_RC_NONE ? rating_q(b.st_out, Y_old) : 0.0;
+  auto f = [&](double Y_new) {
+    const double Q_out = b.st_out.type != PR_RC_NONE ? 0.5 * (q_old + rating_q(b.st_out, Y_new)) : 0.0;
+    return storage_net_vol_change(b, Y_old, Y_new) - (vol_in - Q_out * dt);
+  };
+  double Y = brent_root(f, b.st_ymin, b.st_ymax, failed);
+  if (Y < b.st_min_stage) Y = b.st_min_stage;
+  return Y;
+}
+
 // ---- boundary rows (Boundary.condition_residual / df_dh / df_dQ, boundary.py:56-242) --------------------
 
 struct BcRow {
   double res, dh, dq;
   double stage_rec;   // storage: reservoir stage recorded by this evaluation (boundary.py:126-131)
+  bool fail;          // the reference would raise here (brentq: "f(a) and f(b) must have different signs")
 };
 
 // level = time // dt; hyd = series sample at this level; q_prev = stored Q of the previous level at the node;
 // stage_prev = reservoir stage recorded for level-1.
+// GST: compile the general lumped-storage branch (Brent solve, area curve, losses).  It is rare and register-hungry,
+// so the kernels that do not need it (every shipped case) are instantiated without it.
+template <bool GST>
 __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int level, const double hyd, const double h,
                                          const double Q, const double q_prev, const double stage_prev,
-                                         const double dt, const double K, const double dKA, const double T) {
+                                         const double dt, const double g, const NodeConv& kc, const double T) {
+  const double K = kc.K, dKA = kc.dKA;
   BcRow o;
   o.stage_rec = 0.0;
+  o.fail = false;
   switch (bc.type) {
     case PR_BC_FLOW_HYDROGRAPH:
       o.res = Q - hyd; o.dh = 0.0; o.dq = 1.0;
@@ -391,18 +495,36 @@ __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int level, const
       break;
     }
     case PR_BC_FIXED_DEPTH_STORAGE: {
-      // LumpedStorage.mass_balance with constant area: the brentq root of
-      // (Y - Y_old)*A_s - vol_in is Y_old + vol_in/A_s, clamped at min_stage (lumped_storage.py:24-45)
       const double vol_in = 0.5 * (q_prev + Q) * dt;                       // preissmann.py:314
       const double y_old = (level == 1) ? h + bc.bed_level : stage_prev;    // quirk 9
-      double y_new = y_old + vol_in * bc.st_inv_area;
-      double dy_dvol = bc.st_inv_area;
-      if (y_new < bc.st_min_stage) y_new = bc.st_min_stage;
+      double y_new, dy_dvol;
+      if (!GST || !bc.st_general) {
+        // LumpedStorage.mass_balance with constant area: the brentq root of
+        // (Y - Y_old)*A_s - vol_in is Y_old + vol_in/A_s, clamped at min_stage (lumped_storage.py:24-45)
+        y_new = y_old + vol_in * bc.st_inv_area;
+        dy_dvol = bc.st_inv_area;
+        // brentq brackets the root in solution_boundaries and raises when it lies outside
+        o.fail = !(y_new >= bc.st_ymin && y_new <= bc.st_ymax);
+        if (y_new < bc.st_min_stage) y_new = bc.st_min_stage;
+      } else {
+        bool failed;
+        y_new = storage_mass_balance(bc, vol_in, y_old, dt, failed);       // brentq, as the reference
+        o.fail = failed;
+        dy_dvol = 1.0 / storage_area_at(bc, y_new);                        // dY_new_dvol_in, :37-45
+      }
       if (y_new <= bc.st_min_stage) dy_dvol = 0.0;
+      double hl = 0.0, dhl_dA = 0.0, dhl_dQ = 0.0;
+      if (GST && bc.st_losses) {
+        // friction over the reservoir length + empirical K_q V^2/2g (lumped_storage.py:47-143)
+        const double V = Q / kc.A, i2g = 1.0 / (2.0 * g);
+        hl = kc.Sf * bc.st_length + bc.st_kq * (V * V) * i2g;
+        dhl_dA = kc.dSfA * bc.st_length + bc.st_kq * 2.0 * V * (-Q / (kc.A * kc.A)) * i2g;
+        dhl_dQ = kc.dSfQ * bc.st_length + bc.st_kq * 2.0 * V * (1.0 / kc.A) * i2g;
+      }
       o.stage_rec = y_new;
-      o.res = h - (y_new - bc.bed_level);
-      o.dh = 1.0;
-      o.dq = 0.0 - dy_dvol * (0.5 * dt);
+      o.res = h - ((y_new + hl) - bc.bed_level);
+      o.dh = 1.0 - dhl_dA * T;
+      o.dq = 0.0 - (dy_dvol * (0.5 * dt) + dhl_dQ);
       break;
     }
     default:

@@ -121,7 +121,7 @@ __host__ __device__ constexpr size_t ensemble_smem_bytes() {
   return sizeof(double) * ((size_t)F_COUNT * G * M + (size_t)W * warp_smem_doubles<M>());
 }
 
-template <int G, int M, int W, bool CURV, int RM, bool EXACT>
+template <int G, int M, int W, bool CURV, int RM, bool EXACT, bool GST>
 __global__ void __launch_bounds__(W * 32, 1)
 pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ double smem[];
@@ -205,9 +205,19 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     last_node(hl, ql);
     q_prev_last = ql;                                                   // flow_at(k=-1, i=-1)
     stage_prev = sg[F_Z * NP + slot_last * G + owner_last] + hl;        // solver.py:101-108
+    if (GST && p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses && owns_last) {
+      NodeVals t;
+      NodeConv kc;
+      node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
+      const double V = ql / kc.A;
+      stage_prev -= kc.Sf * p.dn.st_length + p.dn.st_kq * (V * V) / (2.0 * p.g);     // initial stage = Y - energy_loss
+    }
   }
   if (member_valid && owns_last && p.storage_stage) p.storage_stage[(size_t)member * L] = stage_prev;
-  const bool up_normal = p.up.type == PR_BC_NORMAL_DEPTH, dn_normal = p.dn.type == PR_BC_NORMAL_DEPTH;
+  // conveyance / friction slope of a boundary node are only needed by the normal-depth condition and by the head
+  // losses of a lumped storage
+  const bool up_normal = p.up.type == PR_BC_NORMAL_DEPTH;
+  const bool dn_normal = p.dn.type == PR_BC_NORMAL_DEPTH || (GST && p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses);
 
   int level = 1, it = 0;
   bool active = member_valid && L > 1;
@@ -294,29 +304,29 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
     // ------------------------------ boundary rows ------------------------------
     BcRow U, D;
-    U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0;
+    U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0; U.fail = false;
     D = U;
     if (is_first) {
-      NodeConv kc = {0.0, 0.0};
+      NodeConv kc = {0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
       double T0 = 0.0;
-      if (up_normal) {     // conveyance of the boundary node is only needed by the normal-depth condition
+      if (up_normal) {
         NodeVals t;
         node_eval<CURV, RM, true>(sg, NP, gl, h[0], q[0], rg, k, t, &kc);
         T0 = t.T;
       }
-      U = bc_eval(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, kc.K, kc.dKA, T0);
+      U = bc_eval<false>(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, p.g, kc, T0);
     }
     if (owns_last) {
       double hl, ql;
       last_node(hl, ql);
-      NodeConv kc = {0.0, 0.0};
+      NodeConv kc = {0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
       double T0 = 0.0;
       if (dn_normal) {
         NodeVals t;
         node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
         T0 = t.T;
       }
-      D = bc_eval(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, kc.K, kc.dKA, T0);
+      D = bc_eval<GST>(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, p.g, kc, T0);
     }
     if (is_first) ss = fma(U.res, U.res, ss);
     if (owns_last) ss = fma(D.res, D.res, ss);
@@ -401,7 +411,9 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
 
     // ------------------------------ accept / update (preissmann.py:146-156) ------------------------------
-    const bool converged = err < p.tol;
+    // a boundary evaluation the reference would abort on (brentq without a sign change) fails the member at once
+    const bool bc_failed = __any_sync(kFull, (is_first && U.fail) || (owns_last && D.fail));
+    const bool converged = !bc_failed && err < p.tol;
     if (active) {
       if (converged) {
         store_level(level, false);                     // stored level = iterate BEFORE the update
@@ -429,8 +441,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       if (converged) {
         level += 1; it = 0;
         if (level >= L) active = false;
-      } else if (it >= p.max_iter) {
-        status = (err == err) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
+      } else if (it >= p.max_iter || bc_failed) {
+        status = (err == err && !bc_failed) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
         fail_level = level;
         if (is_first) {
           if (p.iters) p.iters[(size_t)member * (L - 1) + (level - 1)] = it;
@@ -464,16 +476,24 @@ int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
 
 #define PR_DEFINE_ENSEMBLE_FAMILY(M_, W_)                                                                    \
   namespace pr {                                                                                             \
-  template <bool CURV, int RM, bool EXACT>                                                                   \
-  static int launch_x_##M_(const DevParams& p, cudaStream_t s) {                                             \
+  template <bool CURV, int RM, bool EXACT, bool GST>                                                         \
+  static int launch_y_##M_(const DevParams& p, cudaStream_t s) {                                             \
     constexpr size_t smem = ensemble_smem_bytes<32, M_, W_>();                                               \
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");                                      \
-    auto kern = pr_ensemble_kernel<32, M_, W_, CURV, RM, EXACT>;                                             \
+    auto kern = pr_ensemble_kernel<32, M_, W_, CURV, RM, EXACT, GST>;                                        \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                     \
     const unsigned grid = (unsigned)((p.M + W_ - 1) / W_);                                                   \
     kern<<<grid, W_ * 32, smem, s>>>(p);                                                                     \
     return (int)cudaGetLastError();                                                                          \
+  }                                                                                                          \
+  template <bool CURV, int RM, bool EXACT>                                                                   \
+  static int launch_x_##M_(const DevParams& p, cudaStream_t s) {                                             \
+    /* general lumped storage (Brent solve / losses): built for the plain variants only (-4 = unsupported) */ \
+    const bool gst = p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && (p.dn.st_general || p.dn.st_losses);          \
+    if (!gst) return launch_y_##M_<CURV, RM, EXACT, false>(p, s);                                            \
+    if (CURV || RM != 0) return -4;                                                                          \
+    return launch_y_##M_<false, 0, EXACT, true>(p, s);                                                       \
   }                                                                                                          \
   template <bool CURV, int RM>                                                                               \
   static int launch_one_##M_(const DevParams& p, cudaStream_t s) {                                           \

@@ -288,21 +288,22 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   const int Lc = (T + Kc - 1) / Kc;      // lanes with tile cells; chain rows 0..Lc
   // ---- boundary rows ----
   BcRow U, D;
-  U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0;
+  U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0; U.fail = false;
   D = U;
   const double hyd_up = p.up.series ? p.up.series[(size_t)m * p.up.series_stride + level] : 0.0;
   const double hyd_dn = p.dn.series ? p.dn.series[(size_t)m * p.dn.series_stride + level] : 0.0;
   if (lane == 0) {
-    NodeVals nvb; NodeConv kc = {0.0, 0.0};
+    NodeVals nvb; NodeConv kc;
     node_eval<false, 0, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
-    U = bc_eval(p.up, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, kc.K, kc.dKA, nvb.T);
+    U = bc_eval<false>(p.up, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, p.g, kc, nvb.T);
   }
   if (lane == Lc) {
-    NodeVals nvb; NodeConv kc = {0.0, 0.0};
+    NodeVals nvb; NodeConv kc;
     node_eval<false, 0, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
-    D = bc_eval(p.dn, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, kc.K, kc.dKA, nvb.T);
+    D = bc_eval<true>(p.dn, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T);
   }
   const double Ures = __shfl_sync(kFull, U.res, 0), Dres = __shfl_sync(kFull, D.res, Lc);
+  const bool bc_failed = __any_sync(kFull, U.fail || D.fail);
   const double err = sqrt(q.err2[m] + Ures * Ures + Dres * Dres);
   // ---- chain rows + PCR ----
   double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
 #undef REC
   // ---- the member's state machine (preissmann.py:122-161) ----
   if (lane == 0) {
-    const bool converged = err < p.tol;
+    const bool converged = !bc_failed && err < p.tol;
     q.err2[m] = 0.0;
     q.conv[m] = converged ? 1 : 0;
     q.out_level[m] = level;
@@ -349,10 +350,10 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
       q.level[m] = level + 1;
     } else {
       q.it[m] = it;
-      if (it >= p.max_iter) {
+      if (it >= p.max_iter || bc_failed) {
         if (p.iters) p.iters[(size_t)m * (L - 1) + (level - 1)] = it;
         if (p.final_error) p.final_error[(size_t)m * (L - 1) + (level - 1)] = err;
-        if (p.status) p.status[m] = (err == err) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
+        if (p.status) p.status[m] = (err == err && !bc_failed) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
         if (p.fail_level) p.fail_level[m] = level;
         q.active[m] = 2;           // failed: K3 of this iteration is skipped by the host-side finaliser
         atomicAdd(q.n_done, 1);
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
     }
   }
   if (lane == Lc) {
-    const bool converged = err < p.tol;
+    const bool converged = !bc_failed && err < p.tol;
     if (converged) {
       q.qprev_last[m] = xq[N - 1];
       if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE) {
@@ -461,6 +462,8 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
   if (has_curv) return fail(PR_ERR_UNSUPPORTED, "long-reach path: centre-line curvature is not supported");
   if (p.geo.member_nm || p.geo.member_nfp)
     return fail(PR_ERR_UNSUPPORTED, "long-reach path: per-member roughness overrides are not supported");
+  if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses)
+    return fail(PR_ERR_UNSUPPORTED, "long-reach path: lumped-storage head losses are not supported");
   const int N = p.N, M = p.M;
   const int T = (N - 1 + kTileCells - 1) / kTileCells;
   const int Kc = (T + 30) / 31;           // tile cells per lane so that the chain has <= 32 rows

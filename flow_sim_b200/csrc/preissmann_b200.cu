@@ -170,10 +170,41 @@ int make_bc(const pr_bc& b, const char* which, bool downstream, const pr_config&
       break;
     case PR_BC_FIXED_DEPTH_STORAGE:
       if (!downstream) return fail(PR_ERR_UNSUPPORTED, "lumped storage at the upstream boundary");
-      if (!(b.storage_area > 0)) return fail(PR_ERR_ARG, "storage: surface area must be positive");
-      d.st_area = b.storage_area;
-      d.st_inv_area = 1.0 / b.storage_area;
       d.st_min_stage = b.storage_min_stage;
+      d.st_ymin = b.storage_ymin; d.st_ymax = b.storage_ymax;
+      d.st_curve_len = b.storage_curve_len;
+      if (b.storage_curve_len > 0) {
+        if (b.storage_curve_len < 2 || !b.storage_curve_stage || !b.storage_curve_area)
+          return fail(PR_ERR_ARG, "storage: area curve needs >= 2 rows and both columns");
+        std::vector<double> stg;
+        if (int rc = fetch(b.storage_curve_stage, (size_t)b.storage_curve_len, cfg.mem, stg)) return rc;
+        double step = INFINITY;
+        for (int i = 1; i < b.storage_curve_len; ++i) {
+          if (!(stg[i] > stg[i - 1])) return fail(PR_ERR_ARG, "storage: area curve stages must be increasing");
+          step = std::fmin(step, std::fabs(stg[i] - stg[i - 1]));     // lumped_storage.py:173
+        }
+        d.st_step = step;
+        d.st_curve_stage = st.in(b.storage_curve_stage, (size_t)b.storage_curve_len);
+        d.st_curve_area = st.in(b.storage_curve_area, (size_t)b.storage_curve_len);
+        d.st_alpha = b.storage_alpha; d.st_beta = b.storage_beta;
+      } else {
+        if (!(b.storage_area > 0)) return fail(PR_ERR_ARG, "storage: surface area must be positive");
+        d.st_area = b.storage_area;
+        d.st_inv_area = 1.0 / b.storage_area;
+      }
+      if (b.storage_outflow.type != PR_RC_NONE) {
+        if (b.storage_outflow.type == PR_RC_ROSEIRES) return fail(PR_ERR_UNSUPPORTED, "storage: gate-blend outflow curve");
+        if (int rc = make_rating(b.storage_outflow, d.st_out)) return rc;
+      }
+      d.st_general = (b.storage_curve_len > 0 || b.storage_outflow.type != PR_RC_NONE) ? 1 : 0;
+      if (d.st_general && !(b.storage_ymax > b.storage_ymin))
+        return fail(PR_ERR_ARG, "storage: solution_boundaries (ymin < ymax) are required");
+      d.st_losses = b.storage_capture_losses ? 1 : 0;
+      if (d.st_losses) {
+        if (b.bed_level != z_node)
+          return fail(PR_ERR_UNSUPPORTED, "storage head losses with bed_level (%g) != cross-section z_min (%g)", b.bed_level, z_node);
+        d.st_length = b.storage_reservoir_length; d.st_kq = b.storage_Kq;
+      }
       break;
     default:
       return fail(PR_ERR_ARG, "%s boundary: unknown type %d", which, b.type);
@@ -213,6 +244,9 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
 }
 
 int launch_family(int rc_cuda) {
+  if (rc_cuda == -4)
+    return fail(PR_ERR_UNSUPPORTED, "general lumped storage (area curve / outflow curve / head losses) together with "
+                                    "centre-line curvature or per-member roughness overrides");
   if (rc_cuda != 0) return fail(PR_ERR_CUDA, "ensemble kernel launch: %s", cudaGetErrorString((cudaError_t)rc_cuda));
   g_launches.fetch_add(1);
   return PR_OK;

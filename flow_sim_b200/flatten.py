@@ -39,6 +39,13 @@ class FlatBoundary:
     storage_min_stage: float = 0.0
     storage_ymin: float = 0.0
     storage_ymax: float = 0.0
+    storage_curve: np.ndarray | None = None   # [K, 2] (stage, area) of LumpedStorage.set_area_curve
+    storage_alpha: float = 1.0
+    storage_beta: float = 0.0
+    storage_losses: bool = False
+    storage_reservoir_length: float = 0.0
+    storage_Kq: float = 0.0
+    storage_outflow: dict | None = None       # flatten_rating() of LumpedStorage.rating_curve
 
 
 @dataclass
@@ -202,13 +209,27 @@ def flatten_boundary(b, n_levels: int, dt, downstream: bool) -> FlatBoundary:
         else:
             if not downstream:
                 raise NotImplementedError("lumped storage at the upstream boundary")
-            if ls.rating_curve is not None or ls.area_curve is not None or ls.capture_losses:
-                raise NotImplementedError("lumped storage with outflow rating curve / area curve / head losses "
-                                          "(SURVEY.md 8f-3); the device path has the constant-area form")
             fb.type = abi.PR_BC_FIXED_DEPTH_STORAGE
-            fb.storage_area = float(ls.surface_area)
+            fb.storage_area = float(ls.surface_area) if ls.surface_area is not None else 0.0
             fb.storage_min_stage = float(ls.min_stage)
             fb.storage_ymin, fb.storage_ymax = float(ls.Y_min), float(ls.Y_max)
+            if ls.area_curve is not None:
+                curve = np.asarray(ls.area_curve, dtype=np.float64)
+                if curve.ndim != 2 or curve.shape[0] < 2 or not np.all(np.diff(curve[:, 0]) > 0):
+                    raise ValueError("area curve must be a [K, 2] table with increasing stages")
+                fb.storage_curve = curve[:, :2].copy()
+                fb.storage_alpha, fb.storage_beta = float(ls.alpha), float(ls.beta)
+            elif ls.surface_area is None:
+                raise ValueError("lumped storage needs a surface area or an area curve")
+            if ls.rating_curve is not None:
+                fb.storage_outflow = flatten_rating(ls.rating_curve)
+                if fb.storage_outflow["type"] == abi.PR_RC_ROSEIRES:
+                    raise NotImplementedError("gate-blend rating curve as reservoir outflow")
+            if ls.capture_losses:
+                if ls.reservoir_length is None:
+                    raise ValueError("capture_losses needs reservoir_length")
+                fb.storage_losses = True
+                fb.storage_reservoir_length, fb.storage_Kq = float(ls.reservoir_length), float(ls.K_q)
     return fb
 
 
@@ -251,6 +272,13 @@ def flatten_solver(solver, tolerance: float = 1e-4, max_iter: int = 100) -> Flat
 def _bc_to_npz(prefix: str, b: FlatBoundary, out: dict) -> None:
     out[f"{prefix}_scalars"] = np.array([b.type, b.bed_level, b.bed_slope, b.fixed_depth, b.storage_area,
                                          b.storage_min_stage, b.storage_ymin, b.storage_ymax], dtype=np.float64)
+    out[f"{prefix}_storagex"] = np.array([b.storage_alpha, b.storage_beta, float(b.storage_losses),
+                                          b.storage_reservoir_length, b.storage_Kq], dtype=np.float64)
+    if b.storage_curve is not None:
+        out[f"{prefix}_storage_curve"] = np.asarray(b.storage_curve, dtype=np.float64)
+    if b.storage_outflow:
+        for k, v in b.storage_outflow.items():
+            out[f"{prefix}_outflow_{k}"] = np.asarray(v, dtype=np.float64)
     if b.series is not None:
         out[f"{prefix}_series"] = np.asarray(b.series, dtype=np.float64)
     if b.rating:
@@ -265,14 +293,26 @@ def _bc_from_npz(prefix: str, z) -> FlatBoundary:
                      storage_ymax=float(s[7]))
     if f"{prefix}_series" in z:
         b.series = np.array(z[f"{prefix}_series"])
-    rk = [k for k in z.files if k.startswith(f"{prefix}_rating_")]
-    if rk:
-        b.rating = {}
-        for k in rk:
+    if f"{prefix}_storagex" in z:
+        x = z[f"{prefix}_storagex"]
+        b.storage_alpha, b.storage_beta, b.storage_losses = float(x[0]), float(x[1]), bool(x[2])
+        b.storage_reservoir_length, b.storage_Kq = float(x[3]), float(x[4])
+    if f"{prefix}_storage_curve" in z:
+        b.storage_curve = np.array(z[f"{prefix}_storage_curve"])
+
+    def rating_from(tag):
+        keys = [k for k in z.files if k.startswith(f"{prefix}_{tag}_")]
+        if not keys:
+            return None
+        d = {}
+        for k in keys:
             v = np.array(z[k])
-            name = k[len(prefix) + 8:]
-            b.rating[name] = v if v.ndim else (int(v) if name in ("type", "n_gates", "sluices_open",
-                                                                  "sluices_closed") else float(v))
+            name = k[len(prefix) + len(tag) + 2:]
+            d[name] = v if v.ndim else (int(v) if name in ("type", "n_gates", "sluices_open", "sluices_closed") else float(v))
+        return d
+
+    b.rating = rating_from("rating")
+    b.storage_outflow = rating_from("outflow")
     return b
 
 

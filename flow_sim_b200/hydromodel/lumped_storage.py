@@ -1,8 +1,8 @@
 """``LumpedStorage`` (lumped_storage.py:7-179): 0-D reservoir behind the downstream node.
 
-The device path implements the constant-surface-area form without outflow rating curve or head losses
-(the only form a shipped case uses, cases/example/main.py:42-43); the area-curve / outflow / loss variants
-are recorded here so that ``flatten`` can reject them explicitly.
+The device path implements the constant-surface-area form (the one the shipped example uses,
+cases/example/main.py:42-43) in closed form, and the general form - tabulated area curve, outflow rating curve,
+head losses - with Brent's method on the device.
 """
 from __future__ import annotations
 
@@ -47,6 +47,13 @@ class LumpedStorage:
         return 0.5 * (self.area_at(Y2) + self.area_at(Y1)) * (Y2 - Y1)
 
     def energy_loss(self, entry_area, flow, roughness, hydraulic_radius, A_str=None):
+        """Head loss between the last node and the reservoir (lumped_storage.py:47-73): Manning friction over
+        reservoir_length + empirical K_q V^2/2g (+ a sudden-expansion term when A_str is given)."""
         if not self.capture_losses:
             return 0
-        raise NotImplementedError("capture_losses=True (head losses) is not on the device path (SURVEY.md 8f-3)")
+        from . import hydraulics
+
+        V = flow / entry_area
+        hf = hydraulics.Sf(A=entry_area, Q=flow, n=roughness, R=hydraulic_radius) * self.reservoir_length
+        h_exp = 0 if A_str is None else (1 - entry_area / A_str) ** 2 * V ** 2 / (2 * hydraulics.g)
+        return hf + h_exp + self.K_q * V ** 2 / (2 * hydraulics.g)

@@ -90,6 +90,15 @@ class PreparedCall:
         s.rating = abi.make_rating(b.rating)
         s.storage_area, s.storage_min_stage = b.storage_area, b.storage_min_stage
         s.storage_ymin, s.storage_ymax = b.storage_ymin, b.storage_ymax
+        if b.storage_curve is not None:
+            curve = b.storage_curve
+            s.storage_curve_stage = self.arena.put(np.ascontiguousarray(np.asarray(curve)[:, 0]))[0]
+            s.storage_curve_area = self.arena.put(np.ascontiguousarray(np.asarray(curve)[:, 1]))[0]
+            s.storage_curve_len = int(np.asarray(curve).shape[0])
+        s.storage_alpha, s.storage_beta = b.storage_alpha, b.storage_beta
+        s.storage_capture_losses = int(bool(b.storage_losses))
+        s.storage_reservoir_length, s.storage_Kq = b.storage_reservoir_length, b.storage_Kq
+        s.storage_outflow = abi.make_rating(b.storage_outflow)
         return s
 
     def args(self):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PR_ABI_VERSION 3
+#define PR_ABI_VERSION 4
 #define PR_MAX_POLY 12   /* max coefficients of a fitted numpy Polynomial rating curve */
 #define PR_MAX_GATES 8   /* Roseires: 7 spillway gates (roseires_rating_curve.py:11) */
 
@@ -142,9 +142,21 @@ typedef struct pr_bc {
   const double* series; /* [levels] or [M][levels]; flow or stage hydrograph samples */
   int64_t series_member_stride; /* 0 = shared by all members, else element stride between members */
   pr_rating rating;
-  /* lumped storage behind the boundary (lumped_storage.py:7-45; constant surface area, no outflow
+  /* lumped storage behind the boundary (lumped_storage.py:7-179).  Basic form: constant surface area, no outflow
    * rating curve, capture_losses = False) */
   double storage_area, storage_min_stage, storage_ymin, storage_ymax;
+  /* General form (all optional): tabulated area curve (LumpedStorage.set_area_curve, :145-179), outflow rating
+   * curve of the reservoir (mass_balance, :24-35) and head losses between the last node and the reservoir
+   * (capture_losses, :47-143: friction over reservoir_length + empirical K_q V^2/2g; the expansion term needs
+   * A_str, which the reference never passes).  The mass balance is then solved by Brent's method on
+   * [storage_ymin, storage_ymax] exactly as the reference does (scipy.optimize.brentq). */
+  const double* storage_curve_stage;  /* [storage_curve_len], increasing; NULL = constant area */
+  const double* storage_curve_area;   /* [storage_curve_len] */
+  int32_t storage_curve_len;
+  int32_t storage_capture_losses;
+  double storage_alpha, storage_beta; /* area_at(Y) = alpha * interp(Y + beta, stage, area) */
+  double storage_reservoir_length, storage_Kq;
+  pr_rating storage_outflow;          /* PR_RC_NONE = no outflow */
 } pr_bc;
 
 /* Initial conditions = Channel.initial_conditions (channel.py:123-138), split into two arrays. */

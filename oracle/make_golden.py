@@ -33,7 +33,7 @@ def calib_n(m: int) -> float:
     return 0.020 + 0.040 * m / 65535
 
 
-CASES = ["example", "akbari", "gerd_full", "akbari_long"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
+CASES = ["example", "akbari", "gerd_full", "akbari_long", "storage_general"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
 
 
 def build(case: str):
@@ -43,6 +43,8 @@ def build(case: str):
         return rh.build_example()
     if case == "akbari":
         return rh.build_akbari()
+    if case == "storage_general":
+        return rh.build_storage_general()
     if case == "akbari_long":
         # reduced clone of config 5: prismatic akbari channel, N=2001, dx=100, dt=600, theta=0.6
         return rh.build_akbari(length=200000, spatial_step=100, time_step=600, duration=16 * 600, theta=0.6)

@@ -387,19 +387,77 @@ double pr_oracle_brentq_poly(const double* c, int n, double xa, double xb, int* 
   return brentq(poly_f, &q, xa, xb, err);
 }
 
-/* LumpedStorage.mass_balance, lumped_storage.py:24-35 (constant area, no outflow rating curve) */
-typedef struct { double Y_old, area, vol_in; } mbctx;
+static double np_interp(double x, const double* xp, const double* fp, int n);
+
+/* LumpedStorage.mass_balance, lumped_storage.py:24-35 */
+/* LumpedStorage.area_at, lumped_storage.py:155-160 */
+static double st_area_at(const pr_bc* b, double stage) {
+  if (b->storage_curve_len <= 0) return b->storage_area;
+  return b->storage_alpha * np_interp(stage + b->storage_beta, b->storage_curve_stage, b->storage_curve_area, b->storage_curve_len);
+}
+
+/* LumpedStorage.net_vol_change, lumped_storage.py:171-179 */
+static double st_net_vol_change(const pr_bc* b, double Y1, double Y2) {
+  if (b->storage_curve_len <= 0) return (Y2 - Y1) * b->storage_area;
+  double step = INFINITY;
+  for (int i = 1; i < b->storage_curve_len; ++i) step = fmin(step, fabs(b->storage_curve_stage[i] - b->storage_curve_stage[i - 1]));
+  int n = (int)(fabs(Y2 - Y1) / step);
+  if (n > 2) {
+    /* ys = np.linspace(Y1, Y2, n); np.trapezoid([area_at(y) for y in ys], ys) */
+    double dstep = (Y2 - Y1) / (n - 1), sum = 0.0;
+    double y_prev = Y1, a_prev = st_area_at(b, Y1);
+    for (int i = 1; i < n; ++i) {
+      double y = (i == n - 1) ? Y2 : i * dstep + Y1;
+      double a = st_area_at(b, y);
+      sum += (y - y_prev) * (a + a_prev) / 2.0;
+      y_prev = y; a_prev = a;
+    }
+    return sum;
+  }
+  return 0.5 * (st_area_at(b, Y2) + st_area_at(b, Y1)) * (Y2 - Y1);
+}
+
+typedef struct { const pr_bc* b; double Y_old, vol_in, duration; } mbctx;
 static double mb_f(double Y_new, void* p) {
   mbctx* c = (mbctx*)p;
   double Q_out = 0.0;
-  double target_vol = c->vol_in - Q_out * 0.0;
-  return (Y_new - c->Y_old) * c->area - target_vol;     /* net_vol_change, :171-173 */
+  if (c->b->storage_outflow.type != PR_RC_NONE)
+    Q_out = 0.5 * (pr_oracle_rating_discharge(&c->b->storage_outflow, c->Y_old) + pr_oracle_rating_discharge(&c->b->storage_outflow, Y_new));
+  double target_vol = c->vol_in - Q_out * c->duration;
+  return st_net_vol_change(c->b, c->Y_old, Y_new) - target_vol;
 }
-static double storage_mass_balance(const pr_bc* b, double vol_in, double Y_old, int* err) {
-  mbctx c = {Y_old, b->storage_area, vol_in};
+static double storage_mass_balance(const pr_bc* b, double vol_in, double Y_old, double duration, int* err) {
+  mbctx c = {b, Y_old, vol_in, duration};
   double Y = brentq(mb_f, &c, b->storage_ymin, b->storage_ymax, err);
   if (Y < b->storage_min_stage) Y = b->storage_min_stage;
   return Y;
+}
+
+/* LumpedStorage.energy_loss / dhl_dA / dhl_dQ, lumped_storage.py:47-143 (A_str is never passed: no expansion term) */
+static double st_energy_loss(const pr_bc* b, double g, double A, double Q, double n, double R) {
+  if (!b->storage_capture_losses) return 0;
+  double K = hy_conveyance(A, n, R);
+  double hf = hy_Sf(Q, K) * b->storage_reservoir_length;
+  double V = Q / A;
+  double h_emp = b->storage_Kq * (V * V) / (2 * g);
+  return hf + 0 + h_emp;
+}
+static double st_dhl_dA(const pr_bc* b, double g, double A, double Q, double n, double R, double dR_dA) {
+  if (!b->storage_capture_losses) return 0;
+  double K = hy_conveyance(A, n, R);
+  double dK = (pow(R, TWO_THIRDS) + A * 2. / 3. * pow(R, M_ONE_THIRD) * dR_dA) / n;
+  double dhf = (-2 * hy_Sf(Q, K) * (dK / K)) * b->storage_reservoir_length;
+  double V = Q / A, dV_dA = -Q / (A * A);
+  double demp = b->storage_Kq * 2 * V * dV_dA / (2 * g);
+  return dhf + 0 + demp;
+}
+static double st_dhl_dQ(const pr_bc* b, double g, double A, double Q, double n, double R) {
+  if (!b->storage_capture_losses) return 0;
+  double K = hy_conveyance(A, n, R);
+  double dhf = (2 * fabs(Q) / (K * K)) * b->storage_reservoir_length;
+  double V = Q / A, dV_dQ = 1. / A;
+  double demp = b->storage_Kq * 2 * V * dV_dQ / (2 * g);
+  return dhf + 0 + demp;
 }
 
 /* ------------------------------- boundaries ------------------------------------------------ */
@@ -408,7 +466,7 @@ typedef struct {
   const pr_bc* bc;
   const xs_t* xs;
   int member, level;
-  double dt;
+  double dt, g;
   double* stage_record;   /* storage: [levels] of this member, entry k = stage recorded for level k */
 } bc_ctx;
 
@@ -434,8 +492,10 @@ static double bc_residual(const bc_ctx* c, double depth, double flow, double vol
     case PR_BC_FIXED_DEPTH_STORAGE: {
       int k = c->level;                                     /* time // duration */
       double Y_old = (k == 1) ? depth + b->bed_level : c->stage_record[k - 1];   /* quirk 9 */
-      double reservoir_stage = storage_mass_balance(b, vol_in, Y_old, err);
-      double head_loss = 0;                                  /* capture_losses False, lumped_storage.py:48 */
+      double reservoir_stage = storage_mass_balance(b, vol_in, Y_old, c->dt, err);
+      double A, P, R, T;
+      xs_properties(c->xs, hw, &A, &P, &R, &T);
+      double head_loss = st_energy_loss(b, c->g, A, flow, xs_equivalent_n(c->xs, hw), R);   /* boundary.py:117-122 */
       double interface_stage = reservoir_stage + head_loss;
       c->stage_record[k] = reservoir_stage;                  /* boundary.py:126-131 (overwritten each evaluation) */
       return depth - (interface_stage - b->bed_level);
@@ -447,7 +507,6 @@ static double bc_residual(const bc_ctx* c, double depth, double flow, double vol
 /* Boundary.df_dh, boundary.py:143-187 */
 static double bc_df_dh(const bc_ctx* c, double depth, double flow) {
   const pr_bc* b = c->bc;
-  (void)flow;
   if (b->type == PR_BC_FLOW_HYDROGRAPH) return 0;
   double hw = depth + b->bed_level;
   double A, P, R, T;
@@ -455,7 +514,10 @@ static double bc_df_dh(const bc_ctx* c, double depth, double flow) {
   double dA_dh = T;
   switch (b->type) {
     case PR_BC_FIXED_DEPTH: return 1 - 0 * dA_dh;
-    case PR_BC_FIXED_DEPTH_STORAGE: return 1 - 0 * dA_dh;    /* dhl_dA = 0, lumped_storage.py:105 */
+    case PR_BC_FIXED_DEPTH_STORAGE: {                        /* boundary.py:168-177 */
+      double dhl_dA = st_dhl_dA(b, c->g, A, flow, xs_equivalent_n(c->xs, hw), R, xs_dR_dA(c->xs, hw));
+      return 1 - dhl_dA * dA_dh;
+    }
     case PR_BC_NORMAL_DEPTH: {
       double dQ = xs_dK_dA(c->xs, hw) * pow(fabs(b->bed_slope), 0.5);   /* hydraulics.dQn_dA, :206-215 */
       if (b->bed_slope < 0) dQ = -dQ;
@@ -470,7 +532,6 @@ static double bc_df_dh(const bc_ctx* c, double depth, double flow) {
 /* Boundary.df_dQ, boundary.py:189-242 */
 static double bc_df_dQ(const bc_ctx* c, double depth, double flow, double vol_in, int* err) {
   const pr_bc* b = c->bc;
-  (void)flow;
   switch (b->type) {
     case PR_BC_FLOW_HYDROGRAPH: case PR_BC_NORMAL_DEPTH: case PR_BC_RATING_CURVE: return 1;
     case PR_BC_FIXED_DEPTH: return 0;
@@ -479,10 +540,13 @@ static double bc_df_dQ(const bc_ctx* c, double depth, double flow, double vol_in
       int k = c->level;
       /* NB: the residual of this iteration has already overwritten stage_record[k]; [k-1] is untouched */
       double Y_old = (k == 1) ? depth + b->bed_level : c->stage_record[k - 1];
-      double Y_new = storage_mass_balance(b, vol_in, Y_old, err);       /* dY_new_dvol_in, :37-45 */
-      double dY_new_dvol = (Y_new <= b->storage_min_stage) ? 0.0 : 1 / b->storage_area;
+      double Y_new = storage_mass_balance(b, vol_in, Y_old, c->dt, err);       /* dY_new_dvol_in, :37-45 */
+      double dY_new_dvol = (Y_new <= b->storage_min_stage) ? 0.0 : 1 / st_area_at(b, Y_new);
       double dvol_dQ = 0.5 * c->dt;
-      double dhl_dQ = 0;
+      double hw = depth + b->bed_level;
+      double A, P, R, T;
+      xs_properties(c->xs, hw, &A, &P, &R, &T);
+      double dhl_dQ = st_dhl_dQ(b, c->g, A, flow, xs_equivalent_n(c->xs, hw), R);    /* boundary.py:232-235 */
       return 0 - (dY_new_dvol * dvol_dQ + dhl_dQ);
     }
     default: return NAN;
@@ -669,8 +733,8 @@ int pr_oracle_newton_step(const pr_config* cfg, const pr_geom* geom, const pr_bc
   xs_t* xs = (xs_t*)malloc(sizeof(xs_t) * N);
   for (int i = 0; i < N; ++i) xs[i] = xs_load(geom, i, member);
   sch_t s = {N, cfg->theta, cfg->dt, cfg->dx, cfg->g, xs, h0, q0, h1, q1};
-  bc_ctx up = {up_bc, &xs[0], member, level, cfg->dt, stage_record};
-  bc_ctx dn = {dn_bc, &xs[N - 1], member, level, cfg->dt, stage_record};
+  bc_ctx up = {up_bc, &xs[0], member, level, cfg->dt, cfg->g, stage_record};
+  bc_ctx dn = {dn_bc, &xs[N - 1], member, level, cfg->dt, cfg->g, stage_record};
   int err = assemble(&s, &up, &dn, R, J);
   double(*B)[9] = (double(*)[9])calloc(n2, sizeof(double[9]));
   double* rhs = (double*)malloc(sizeof(double) * n2);
@@ -715,14 +779,19 @@ int pr_oracle_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* up_bc,
       x[2 * i] = h_ic[i]; x[2 * i + 1] = q_ic[i];
     }
     for (int k = 0; k < L; ++k) stage[k] = NAN;
-    stage[0] = xs[N - 1].z + h_ic[N - 1];                  /* solver.py:101-108 (energy_loss = 0) */
+    stage[0] = xs[N - 1].z + h_ic[N - 1];                  /* solver.py:101-108 */
+    if (dn_bc->type == PR_BC_FIXED_DEPTH_STORAGE && dn_bc->storage_capture_losses) {
+      double A, P, R, T, Y = stage[0];
+      xs_properties(&xs[N - 1], Y, &A, &P, &R, &T);
+      stage[0] = Y - st_energy_loss(dn_bc, cfg->g, A, q_ic[N - 1], xs_equivalent_n(&xs[N - 1], Y), R);
+    }
     int status = PR_STATUS_OK, fail_level = 0;
     for (int k = 1; k < L && status == PR_STATUS_OK; ++k) {
       double* hk0 = depth + (size_t)(k - 1) * N; double* qk0 = flow + (size_t)(k - 1) * N;
       double* hk1 = depth + (size_t)k * N;       double* qk1 = flow + (size_t)k * N;
       sch_t s = {N, cfg->theta, cfg->dt, cfg->dx, cfg->g, xs, hk0, qk0, hk1, qk1};
-      bc_ctx up = {up_bc, &xs[0], m, k, cfg->dt, stage};
-      bc_ctx dn = {dn_bc, &xs[N - 1], m, k, cfg->dt, stage};
+      bc_ctx up = {up_bc, &xs[0], m, k, cfg->dt, cfg->g, stage};
+      bc_ctx dn = {dn_bc, &xs[N - 1], m, k, cfg->dt, cfg->g, stage};
       int iteration = 0, converged = 0;
       double error = NAN;
       while (!converged) {

@@ -110,6 +110,25 @@ def build_example():
     return solver, dict(tolerance=1e-4, max_iter=100)
 
 
+def build_storage_general():
+    """Synthetic companion of config 1 for the general lumped-storage boundary: tabulated area
+    curve, polynomial outflow rating curve and head losses.  No shipped case exercises these branches
+    (lumped_storage.py:24-35,47-143,145-179), so the reference is run on this set-up to pin them."""
+    solver, kw = build_example()
+    from src.hydromodel.rating_curve import RatingCurve
+
+    ls = solver.channel.downstream_boundary.lumped_storage
+    stages = np.arange(0.0, 42.0, 2.0)
+    ls.set_area_curve(np.column_stack([stages, 1.25e6 * (1.0 + 0.05 * stages)]), alpha=1.0, beta=0.0)
+    rc = RatingCurve()
+    rc.set("polynomial", a=20.0, b=10.0, c=0.0)
+    ls.rating_curve = rc
+    ls.capture_losses = True
+    ls.reservoir_length = 2000.0
+    ls.K_q = 0.3
+    return solver, kw
+
+
 def build_akbari(peak_flow: float = 200.0, n_nodes_override: int | None = None, **over):
     """cases/akbari_firoozi/settings.py + main_preissmann.py:5-32 (config 2).
 

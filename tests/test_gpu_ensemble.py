@@ -181,3 +181,46 @@ def test_mirror_solver_run_matches_reference_golden():
     solver2, kw = build_example()
     with pytest.raises(ValueError, match="Convergence within 5 iterations couldn't be achieved."):
         solver2.run(verbose=0, tolerance=1e-4, max_iter=5)
+
+
+def test_general_lumped_storage_variants_vs_oracle():
+    """Area curve only / outflow curve only / everything, on the fused kernel; the full variant is
+    also pinned to the reference by test_cuda_vs_reference_golden[storage_general]."""
+    import copy
+
+    full = util.golden_inputs("storage_general")
+    a = copy.copy(full); a.down = copy.copy(full.down); a.down.storage_outflow = None; a.down.storage_losses = False
+    b = copy.copy(full); b.down = copy.copy(full.down); b.down.storage_curve = None; b.down.storage_area = 1.5e6
+    b.down.storage_losses = False
+    c = copy.copy(full); c.down = copy.copy(full.down); c.down.storage_curve = None; c.down.storage_area = 1.25e6
+    c.down.storage_outflow = None                      # constant area + losses only
+    a.down.storage_ymax = c.down.storage_ymax = 200.0   # without an outflow the pool rises past the 40 m bracket
+    for name, flat in (("area curve", a), ("outflow", b), ("losses", c), ("all", full)):
+        out, ora = _check(flat, 1, f"storage: {name}")
+        assert out["status"][0] == 0
+        assert util.max_rel(out["storage_stage"], ora["storage_stage"]) <= util.RTOL
+
+
+def test_storage_root_outside_solution_boundaries_fails_the_member():
+    """scipy's brentq raises when the mass balance has no sign change on solution_boundaries; the member stops at that
+    iteration with status NaN (the oracle does the same), for the closed-form and for the Brent variant."""
+    import copy
+
+    full = util.golden_inputs("storage_general")
+    a = copy.copy(full); a.down = copy.copy(full.down); a.down.storage_outflow = None; a.down.storage_losses = False
+    c = copy.copy(a); c.down = copy.copy(a.down); c.down.storage_curve = None; c.down.storage_area = 1.25e6
+    for flat in (a, c):
+        out, ora = _check(flat, 1, "storage bracket failure")
+        assert out["status"][0] == abi.PR_STATUS_NAN and out["fail_level"][0] > 1
+
+
+def test_mirror_general_storage_run_matches_reference():
+    from test_mirror_api import _storage_general_solver
+
+    ref = util.golden_outputs("storage_general")
+    solver, kw = _storage_general_solver()
+    solver.run(verbose=0, **kw)
+    util.assert_parity(solver.depth, solver.flow, ref["depth"], ref["flow"], "mirror storage_general")
+    assert np.array_equal(solver.iterations, ref["iters"])
+    assert util.max_rel(solver.storage_stage, ref["storage_stage"]) <= util.RTOL
+    assert np.all(np.isfinite(solver.storage_outflow))

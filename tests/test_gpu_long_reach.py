@@ -69,6 +69,19 @@ def test_inflow_scenarios_on_a_long_reach():
     assert np.array_equal(solo["depth"][0], out["depth"][3]) and np.array_equal(solo["iters"][0], out["iters"][3])
 
 
+def test_general_storage_on_the_long_path():
+    """Area curve + outflow curve through the tiled path; head losses are rejected there, not emulated."""
+    import copy
+
+    from flow_sim_b200.abi import PreissmannLibraryError
+
+    full = util.golden_inputs("storage_general")
+    with pytest.raises(PreissmannLibraryError, match="head losses"):
+        run_flat(full, lanes=-1)
+    a = copy.copy(full); a.down = copy.copy(full.down); a.down.storage_losses = False
+    _vs_oracle(a, 1, "general storage, long path", lanes=-1)
+
+
 def test_non_convergence_on_the_long_path():
     flat = util.golden_inputs("gerd_calib_m0")
     flat.max_iter = 11

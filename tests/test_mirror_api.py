@@ -47,6 +47,32 @@ def test_case_builders_reproduce_reference_inputs(case, builder):
     _same_flat(util.golden_inputs(case), flat)
 
 
+def _storage_general_solver():
+    """The general lumped-storage set-up of oracle/ref_harness.build_storage_general on the mirror API."""
+    solver, kw = build_example()
+    ls = solver.channel.downstream_boundary.lumped_storage
+    stages = np.arange(0.0, 42.0, 2.0)
+    ls.set_area_curve(np.column_stack([stages, 1.25e6 * (1.0 + 0.05 * stages)]), alpha=1.0, beta=0.0)
+    rc = hydromodel.RatingCurve()
+    rc.set("polynomial", a=20.0, b=10.0, c=0.0)
+    ls.rating_curve, ls.capture_losses, ls.reservoir_length, ls.K_q = rc, True, 2000.0, 0.3
+    return solver, kw
+
+
+def test_general_storage_flattens_like_the_reference(tmp_path):
+    solver, kw = _storage_general_solver()
+    flat = flatten_solver(solver, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
+    ref = util.golden_inputs("storage_general")
+    _same_flat(ref, flat)
+    for f in ("storage_alpha", "storage_beta", "storage_losses", "storage_reservoir_length", "storage_Kq"):
+        assert getattr(ref.down, f) == getattr(flat.down, f)
+    assert np.array_equal(ref.down.storage_curve, flat.down.storage_curve)
+    assert ref.down.storage_outflow["type"] == flat.down.storage_outflow["type"] == abi.PR_RC_POLY2
+    p = str(tmp_path / "s.npz")
+    save_flat(p, flat)
+    assert np.array_equal(load_flat(p).down.storage_curve, flat.down.storage_curve)
+
+
 def test_flat_roundtrip(tmp_path):
     solver, kw = build_gerd(n_main=0.03, calibration=True)
     flat = flatten_solver(solver, tolerance=kw["tolerance"])
@@ -72,8 +98,8 @@ def test_unsupported_configurations_are_rejected_not_emulated():
     with pytest.raises(NotImplementedError):
         flatten_solver(s)
     s, _ = build_example()
-    s.channel.downstream_boundary.lumped_storage.capture_losses = True
-    with pytest.raises(NotImplementedError):
+    s.channel.downstream_boundary.lumped_storage.capture_losses = True      # losses need a reservoir length
+    with pytest.raises(ValueError):
         flatten_solver(s)
 
     class Irregular:          # stands for the reference's IrregularSection (no trapezoid attributes)
