@@ -12,7 +12,7 @@ import threading
 
 import numpy as np
 
-PR_ABI_VERSION = 4
+PR_ABI_VERSION = 5
 PR_MAX_POLY = 12
 PR_MAX_GATES = 8
 
@@ -75,7 +75,7 @@ class pr_bc(C.Structure):
         ("type", C.c_int32), ("reserved", C.c_int32),
         ("bed_level", C.c_double), ("bed_slope", C.c_double), ("fixed_depth", C.c_double),
         ("series", c_double_p), ("series_member_stride", C.c_int64),
-        ("rating", pr_rating),
+        ("rating", pr_rating), ("member_ratings", C.POINTER(pr_rating)),
         ("storage_area", C.c_double), ("storage_min_stage", C.c_double),
         ("storage_ymin", C.c_double), ("storage_ymax", C.c_double),
         ("storage_curve_stage", c_double_p), ("storage_curve_area", c_double_p),
@@ -132,7 +132,7 @@ def load_library(path: str | None = None):
                                         C.POINTER(pr_state), C.POINTER(pr_outputs), C.c_void_p]
         lib.pr_gvf_initial_conditions.restype = C.c_int
         lib.pr_gvf_initial_conditions.argtypes = [C.POINTER(pr_config), C.POINTER(pr_geom), c_double_p, C.c_int64,
-                                                  C.c_double, c_double_p, c_double_p, c_int32_p, C.c_void_p]
+                                                  c_double_p, C.c_int64, c_double_p, c_double_p, c_int32_p, C.c_void_p]
         lib.pr_rating_objective.restype = C.c_int
         lib.pr_rating_objective.argtypes = [C.POINTER(pr_config), c_double_p, c_double_p, C.c_double, c_double_p,
                                             c_double_p, C.c_int32, c_double_p, c_double_p, C.c_void_p]

@@ -9,7 +9,9 @@ namespace pr {
 
 struct GvfParams {
   int N, M;
-  double dx, g, h_down;
+  double dx, g;
+  const double* h_down;
+  long long h_down_stride;
   double th_dx, hth, th_dx2;   // unused scheme constants node_eval reads (zero)
   DevGeom geo;
   const double* q0;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) pr_gvf_kernel(const __grid_constant__ Gvf
   double* oh = p.ic_h + (size_t)m * N;
   double* oq = p.ic_q + (size_t)m * N;
   int status = PR_STATUS_OK;
-  double h = p.h_down;
+  double h = p.h_down[m * p.h_down_stride];
   oh[N - 1] = h;
   oq[N - 1] = Q;
   for (int i = N - 2; i >= 0; --i) {

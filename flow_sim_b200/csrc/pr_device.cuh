@@ -33,6 +33,7 @@ struct DevBC {
   const double* series;
   long long series_stride;
   DevRating rc;
+  const DevRating* member_rc;     // release scenarios: one reduced curve per member (device), or nullptr
   double st_area, st_inv_area, st_min_stage;
   // general lumped storage (lumped_storage.py:24-179): tabulated area curve, outflow rating curve, head losses
   int st_general;                 // 0 = constant area, no outflow, no losses (closed form)
@@ -464,7 +465,7 @@ struct BcRow {
 // GST: compile the general lumped-storage branch (Brent solve, area curve, losses).  It is rare and register-hungry,
 // so the kernels that do not need it (every shipped case) are instantiated without it.
 template <bool GST>
-__device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int level, const double hyd, const double h,
+__device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int member, const int level, const double hyd, const double h,
                                          const double Q, const double q_prev, const double stage_prev,
                                          const double dt, const double g, const NodeConv& kc, const double T) {
   const double K = kc.K, dKA = kc.dKA;
@@ -489,8 +490,9 @@ __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int level, const
       break;
     case PR_BC_RATING_CURVE: {
       const double stage = bc.bed_level + h;
-      o.res = Q - rating_q(bc.rc, stage);
-      o.dh = 0.0 - rating_dq(bc.rc, stage);
+      const DevRating& rc = bc.member_rc ? bc.member_rc[member] : bc.rc;
+      o.res = Q - rating_q(rc, stage);
+      o.dh = 0.0 - rating_dq(rc, stage);
       o.dq = 1.0;
       break;
     }

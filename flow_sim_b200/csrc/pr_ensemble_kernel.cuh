@@ -314,7 +314,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
         node_eval<CURV, RM, true>(sg, NP, gl, h[0], q[0], rg, k, t, &kc);
         T0 = t.T;
       }
-      U = bc_eval<false>(p.up, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, p.g, kc, T0);
+      U = bc_eval<false>(p.up, member, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, p.g, kc, T0);
     }
     if (owns_last) {
       double hl, ql;
@@ -326,7 +326,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
         node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
         T0 = t.T;
       }
-      D = bc_eval<GST>(p.dn, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, p.g, kc, T0);
+      D = bc_eval<GST>(p.dn, member, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, p.g, kc, T0);
     }
     if (is_first) ss = fma(U.res, U.res, ss);
     if (owns_last) ss = fma(D.res, D.res, ss);

@@ -295,12 +295,12 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   if (lane == 0) {
     NodeVals nvb; NodeConv kc;
     node_eval<false, 0, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
-    U = bc_eval<false>(p.up, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, p.g, kc, nvb.T);
+    U = bc_eval<false>(p.up, m, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, p.g, kc, nvb.T);
   }
   if (lane == Lc) {
     NodeVals nvb; NodeConv kc;
     node_eval<false, 0, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
-    D = bc_eval<true>(p.dn, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T);
+    D = bc_eval<true>(p.dn, m, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T);
   }
   const double Ures = __shfl_sync(kFull, U.res, 0), Dres = __shfl_sync(kFull, D.res, Lc);
   const bool bc_failed = __any_sync(kFull, U.fail || D.fail);

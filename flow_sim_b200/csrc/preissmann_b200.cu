@@ -65,6 +65,16 @@ struct Stage {
     err = cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, stream);
     return static_cast<const T*>(d);
   }
+  // source is host memory whatever the call's mem mode; the copy is synchronous (the source may be a temporary)
+  template <class T>
+  const T* in_host(const T* p, size_t n) {
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, n * sizeof(T));
+    if (err != cudaSuccess) return nullptr;
+    allocs.push_back(d);
+    err = cudaMemcpy(d, p, n * sizeof(T), cudaMemcpyHostToDevice);
+    return static_cast<const T*>(d);
+  }
   template <class T>
   T* out(T* p, size_t n) {
     if (!p || !host) return p;
@@ -167,6 +177,12 @@ int make_bc(const pr_bc& b, const char* which, bool downstream, const pr_config&
     case PR_BC_RATING_CURVE:
       if (b.rating.type == PR_RC_NONE) return fail(PR_ERR_ARG, "%s boundary: rating_curve without a curve", which);
       if (int rc = make_rating(b.rating, d.rc)) return rc;
+      if (b.member_ratings) {          // release scenarios: reduce every member's curve on the host, ship the array
+        std::vector<pr::DevRating> all((size_t)cfg.n_members);
+        for (int64_t m = 0; m < cfg.n_members; ++m)
+          if (int rc = make_rating(b.member_ratings[m], all[(size_t)m])) return rc;
+        d.member_rc = st.in_host(all.data(), all.size());
+      }
       break;
     case PR_BC_FIXED_DEPTH_STORAGE:
       if (!downstream) return fail(PR_ERR_UNSUPPORTED, "lumped storage at the upstream boundary");
@@ -368,16 +384,16 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
 }
 
 int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const double* q0, int64_t q0_member_stride,
-                              double downstream_depth, double* ic_depth, double* ic_flow, int32_t* status,
-                              void* cuda_stream) {
+                              const double* downstream_depth, int64_t downstream_depth_member_stride,
+                              double* ic_depth, double* ic_flow, int32_t* status, void* cuda_stream) {
   if (int rc = check_config(cfg)) return rc;
-  if (!q0 || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "q0 / ic buffers are NULL");
+  if (!q0 || !downstream_depth || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "q0 / downstream_depth / ic buffers are NULL");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t N = cfg->n_nodes, M = cfg->n_members;
   Stage st(cfg->mem == PR_MEM_HOST, s);
   pr::GvfParams p;
   std::memset(&p, 0, sizeof p);
-  p.N = (int)N; p.M = (int)M; p.dx = cfg->dx; p.g = cfg->g; p.h_down = downstream_depth;
+  p.N = (int)N; p.M = (int)M; p.dx = cfg->dx; p.g = cfg->g;
   std::vector<double> curv;
   if (!geom || !geom->curvature) return fail(PR_ERR_ARG, "geom is incomplete");
   if (int rc = fetch(geom->curvature, N, cfg->mem, curv)) return rc;
@@ -386,6 +402,8 @@ int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const d
   if (int rc = stage_geom(*cfg, geom, st, p.geo)) return rc;
   p.q0 = st.in(q0, q0_member_stride ? M * (size_t)q0_member_stride : 1);
   p.q0_stride = q0_member_stride;
+  p.h_down = st.in(downstream_depth, downstream_depth_member_stride ? M * (size_t)downstream_depth_member_stride : 1);
+  p.h_down_stride = downstream_depth_member_stride;
   p.ic_h = st.out(ic_depth, M * N);
   p.ic_q = st.out(ic_flow, M * N);
   p.status = st.out(status, M);

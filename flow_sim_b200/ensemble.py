@@ -1,5 +1,5 @@
 """Ensemble entry point (additive to the reference API): many members of one reach -
-Manning-roughness calibration sweeps, inflow scenarios - advanced together on one GPU.
+Manning-roughness calibration sweeps, inflow and release scenarios - advanced together on one GPU.
 
 The reference runs members one after another (cases/gerd_roseires/n_calibrate.py:55-63 calls model.run
 per roughness value).  Here the member axis is the parallel axis: per-member inputs go to the device once,
@@ -13,7 +13,7 @@ import copy
 import numpy as np
 
 from . import abi
-from .flatten import FlatCase
+from .flatten import FlatCase, flatten_rating
 from .runner import PreparedCall, gvf_initial_conditions, rating_objective
 
 
@@ -46,11 +46,16 @@ class EnsembleRunner:
         return t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device, non_blocking=True)
 
     def solve(self, n_members: int, member_n_main=None, member_n_fp=None, up_series=None, ic_depth=None, ic_flow=None,
-              out_mode: int = abi.PR_OUT_UPSTREAM, stream=None, want_error: bool = False) -> dict:
+              out_mode: int = abi.PR_OUT_UPSTREAM, stream=None, want_error: bool = False, member_ratings=None) -> dict:
         """One pr_ensemble_run on device buffers; returns torch tensors (no synchronisation)."""
         f = copy.copy(self.flat)
         f.member_n_main = self._to_device(member_n_main)
         f.member_n_fp = self._to_device(member_n_fp)
+        if member_ratings is not None:
+            if f.down.type != abi.PR_BC_RATING_CURVE:
+                raise ValueError("member_ratings need a rating_curve downstream boundary")
+            f.down = copy.copy(f.down)
+            f.down.member_ratings = list(member_ratings)
         if up_series is not None:
             f.up = copy.copy(f.up)
             f.up.series = self._to_device(up_series)
@@ -88,6 +93,33 @@ class EnsembleRunner:
                                       self._to_device(q_query), self._to_device(h_target), abi.PR_MEM_DEVICE,
                                       self.device, stream)
             res["levels"], res["rmse"] = lv, rm
+        return res
+
+
+    def release_scenarios(self, rating_curves, n_main=None, n_fp=None, up_series=None, downstream_depth=None,
+                          q0=None, out_mode: int = abi.PR_OUT_UPSTREAM, stream=None) -> dict:
+        """Release-scenario ensemble: member m runs the reach against its own downstream rating curve
+        (rating_curves[m]: a rating-curve object - e.g. RoseiresRatingCurve with its own pool level, jammed gates,
+        blend buffer - or an already flattened dict), optionally with its own roughness and inflow series
+        (up_series [M, levels]).  The GVF initial profile is recomputed per member from the member's downstream
+        depth (default: the curve's initial stage above the boundary bed, as model.py:58-66 sets it) and initial
+        flow q0 (default: the case's)."""
+        ratings = [r if isinstance(r, dict) else flatten_rating(r) for r in rating_curves]
+        M = len(ratings)
+        if downstream_depth is None:
+            if all("stage0" in r for r in ratings):
+                downstream_depth = np.array([r["stage0"] - self.flat.down.bed_level for r in ratings])
+            else:
+                downstream_depth = float(self.flat.meta["downstream_depth"])
+        f = copy.copy(self.flat)
+        f.member_n_main, f.member_n_fp = self._to_device(n_main), self._to_device(n_fp)
+        q_init = self.flat.meta["initial_flow"] if q0 is None else q0
+        hd = self._to_device(np.atleast_1d(np.asarray(downstream_depth, dtype=np.float64)))
+        qi = q_init if hasattr(q_init, "data_ptr") else self._to_device(np.atleast_1d(np.asarray(q_init, dtype=np.float64)))
+        ich, icq, ic_status = gvf_initial_conditions(f, M, qi, hd, abi.PR_MEM_DEVICE, self.device, stream)
+        res = self.solve(M, member_n_main=f.member_n_main, member_n_fp=f.member_n_fp, up_series=up_series,
+                         ic_depth=ich, ic_flow=icq, out_mode=out_mode, stream=stream, member_ratings=ratings)
+        res["ic_status"] = ic_status
         return res
 
 

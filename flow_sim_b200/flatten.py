@@ -35,6 +35,7 @@ class FlatBoundary:
     fixed_depth: float = float("nan")
     series: np.ndarray | None = None          # [levels] or [M, levels]
     rating: dict | None = None
+    member_ratings: list | None = None        # release scenarios: one flatten_rating() dict per member
     storage_area: float = 0.0
     storage_min_stage: float = 0.0
     storage_ymin: float = 0.0

@@ -88,6 +88,12 @@ class PreparedCall:
             s.series_member_stride = self.L if two_d else 0
             s.series = self.arena.put(ser)[0]
         s.rating = abi.make_rating(b.rating)
+        if b.member_ratings is not None:
+            if len(b.member_ratings) != self.M:
+                raise ValueError("member_ratings must have one entry per member")
+            arr = (abi.pr_rating * self.M)(*[abi.make_rating(d) for d in b.member_ratings])   # host memory, always
+            self.arena.keep.append(arr)
+            s.member_ratings = C.cast(arr, C.POINTER(abi.pr_rating))
         s.storage_area, s.storage_min_stage = b.storage_area, b.storage_min_stage
         s.storage_ymin, s.storage_ymax = b.storage_ymin, b.storage_ymax
         if b.storage_curve is not None:
@@ -154,7 +160,7 @@ def _config(flat: FlatCase, M: int, mem: int, device, out_mode: int = abi.PR_OUT
                          theta=flat.theta, dt=flat.dt, dx=flat.dx, tol=flat.tol, g=flat.g)
 
 
-def gvf_initial_conditions(flat: FlatCase, n_members: int, q0, downstream_depth: float,
+def gvf_initial_conditions(flat: FlatCase, n_members: int, q0, downstream_depth,
                            mem: int = abi.PR_MEM_HOST, device=None, stream=None):
     """Channel._gvh_conditions (channel.py:307-378) for every member on the device.
     Returns (depth[M,N], flow[M,N], status[M])."""
@@ -164,15 +170,18 @@ def gvf_initial_conditions(flat: FlatCase, n_members: int, q0, downstream_depth:
     g = _geom_struct(flat, ar, n_members)
     if mem == abi.PR_MEM_HOST or not hasattr(q0, "data_ptr"):
         q0 = np.atleast_1d(np.asarray(q0, dtype=np.float64))
-    n_q0 = q0.shape[0]
-    if n_q0 not in (1, n_members):
-        raise ValueError("q0 must have 1 or M entries")
+    if mem == abi.PR_MEM_HOST or not hasattr(downstream_depth, "data_ptr"):
+        downstream_depth = np.atleast_1d(np.asarray(downstream_depth, dtype=np.float64))
+    n_q0, n_hd = q0.shape[0], downstream_depth.shape[0]
+    if n_q0 not in (1, n_members) or n_hd not in (1, n_members):
+        raise ValueError("q0 and downstream_depth must have 1 or M entries")
     q0p, _ = ar.put(q0)
+    hdp, _ = ar.put(downstream_depth)
     hp, h = ar.empty((n_members, flat.n_nodes))
     qp, q = ar.empty((n_members, flat.n_nodes))
     sp, st = ar.empty((n_members,), np.int32)
-    rc = lib.pr_gvf_initial_conditions(C.byref(cfg), C.byref(g), q0p, 0 if n_q0 == 1 else 1,
-                                       float(downstream_depth), hp, qp, sp, C.c_void_p(stream or 0))
+    rc = lib.pr_gvf_initial_conditions(C.byref(cfg), C.byref(g), q0p, 0 if n_q0 == 1 else 1, hdp,
+                                       0 if n_hd == 1 else 1, hp, qp, sp, C.c_void_p(stream or 0))
     abi.check(lib, rc, "pr_gvf_initial_conditions")
     return h, q, st
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PR_ABI_VERSION 4
+#define PR_ABI_VERSION 5
 #define PR_MAX_POLY 12   /* max coefficients of a fitted numpy Polynomial rating curve */
 #define PR_MAX_GATES 8   /* Roseires: 7 spillway gates (roseires_rating_curve.py:11) */
 
@@ -142,6 +142,10 @@ typedef struct pr_bc {
   const double* series; /* [levels] or [M][levels]; flow or stage hydrograph samples */
   int64_t series_member_stride; /* 0 = shared by all members, else element stride between members */
   pr_rating rating;
+  /* Release scenarios: one rating curve per ensemble member (different gate states, jammed gates, initial pool
+   * levels ... for the same geometry).  [n_members] array in HOST memory whatever cfg->mem is (the library
+   * reduces each curve to its device form before the launch), or NULL = `rating` for every member. */
+  const pr_rating* member_ratings;
   /* lumped storage behind the boundary (lumped_storage.py:7-179).  Basic form: constant surface area, no outflow
    * rating curve, capture_losses = False) */
   double storage_area, storage_min_stage, storage_ymin, storage_ymax;
@@ -196,10 +200,12 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
                     void* cuda_stream);
 
 /* Replaces Channel._gvh_conditions (channel.py:307-378) per member: backwater predictor-corrector
- * from the downstream depth.  q0: [1] or [M] initial flow (q0_member_stride 0/1).  Writes
+ * from the downstream depth.  q0 / downstream_depth: [1] or [M] (member stride 0/1; the downstream pool level is a
+ * per-member quantity in release-scenario ensembles).  Writes
  * ic_depth/ic_flow [M][N] and status [M] (PR_STATUS_SUPERCRITICAL mirrors the RuntimeError). */
 int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const double* q0,
-                              int64_t q0_member_stride, double downstream_depth, double* ic_depth,
+                              int64_t q0_member_stride, const double* downstream_depth,
+                              int64_t downstream_depth_member_stride, double* ic_depth,
                               double* ic_flow, int32_t* status, void* cuda_stream);
 
 /* Replaces Channel._steady_conditions (channel.py:296-305): per member and node the normal depth for q0, i.e.

@@ -33,7 +33,10 @@ def calib_n(m: int) -> float:
     return 0.020 + 0.040 * m / 65535
 
 
-CASES = ["example", "akbari", "gerd_full", "akbari_long", "storage_general"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
+# one release scenario (a member of a gate-state ensemble): lower pool, jammed gates, narrower blend buffer
+RELEASE_SCENARIO = dict(initial_roseires_level=486.2, rating_kwargs=dict(jammed_spillways=2, jammed_sluice_gates=1, buffer=0.3))
+
+CASES = ["example", "akbari", "gerd_full", "akbari_long", "storage_general", "gerd_release"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
 
 
 def build(case: str):
@@ -48,6 +51,8 @@ def build(case: str):
     if case == "akbari_long":
         # reduced clone of config 5: prismatic akbari channel, N=2001, dx=100, dt=600, theta=0.6
         return rh.build_akbari(length=200000, spatial_step=100, time_step=600, duration=16 * 600, theta=0.6)
+    if case == "gerd_release":
+        return rh.build_gerd(n_main=0.03, calibration=True, **RELEASE_SCENARIO)
     if case == "gerd_full":
         return rh.build_gerd(calibration=False)
     if case.startswith("gerd_calib_m"):

@@ -38,7 +38,7 @@ def lib():
         L.pr_oracle_newton_step.restype = C.c_int
         L.pr_oracle_gvf.restype = C.c_int
         L.pr_oracle_gvf.argtypes = [C.POINTER(abi.pr_config), C.POINTER(abi.pr_geom), abi.c_double_p, C.c_int64,
-                                    C.c_double, abi.c_double_p, abi.c_double_p, abi.c_int32_p]
+                                    abi.c_double_p, C.c_int64, abi.c_double_p, abi.c_double_p, abi.c_int32_p]
         L.pr_oracle_objective.restype = C.c_int
         L.pr_oracle_objective.argtypes = [C.POINTER(abi.pr_config), abi.c_double_p, abi.c_double_p, C.c_double,
                                           abi.c_double_p, abi.c_double_p, C.c_int32, abi.c_double_p, abi.c_double_p]
@@ -84,9 +84,10 @@ def gvf(flat, q0, downstream_depth, n_members=None):
     call = PreparedCall(flat, n_members, abi.PR_OUT_UPSTREAM, abi.PR_MEM_HOST)
     M, N = call.M, call.N
     q0 = np.ascontiguousarray(np.atleast_1d(q0), dtype=np.float64)
+    hd = np.ascontiguousarray(np.atleast_1d(downstream_depth), dtype=np.float64)
     h = np.empty((M, N)); q = np.empty((M, N)); st = np.empty(M, dtype=np.int32)
     rc = lib().pr_oracle_gvf(C.byref(call.cfg), C.byref(call.geom), _dp(q0), 0 if q0.size == 1 else 1,
-                             float(downstream_depth), _dp(h), _dp(q), st.ctypes.data_as(abi.c_int32_p))
+                             _dp(hd), 0 if hd.size == 1 else 1, _dp(h), _dp(q), st.ctypes.data_as(abi.c_int32_p))
     if rc != 0:
         raise RuntimeError(f"pr_oracle_gvf -> {rc}")
     return h, q, st

@@ -486,7 +486,7 @@ static double bc_residual(const bc_ctx* c, double depth, double flow, double vol
       if (b->bed_slope < 0) Qn = -Qn;
       return flow - Qn;
     }
-    case PR_BC_RATING_CURVE: return flow - pr_oracle_rating_discharge(&b->rating, b->bed_level + depth);
+    case PR_BC_RATING_CURVE: return flow - pr_oracle_rating_discharge(b->member_ratings ? &b->member_ratings[c->member] : &b->rating, b->bed_level + depth);
     case PR_BC_FIXED_DEPTH: return depth - b->fixed_depth;
     case PR_BC_STAGE_HYDROGRAPH: return depth - (bc_series(c) - b->bed_level);
     case PR_BC_FIXED_DEPTH_STORAGE: {
@@ -523,7 +523,7 @@ static double bc_df_dh(const bc_ctx* c, double depth, double flow) {
       if (b->bed_slope < 0) dQ = -dQ;
       return 0 - dQ * dA_dh;
     }
-    case PR_BC_RATING_CURVE: return 0 - pr_oracle_rating_dQdz(&b->rating, b->bed_level + depth);
+    case PR_BC_RATING_CURVE: return 0 - pr_oracle_rating_dQdz(b->member_ratings ? &b->member_ratings[c->member] : &b->rating, b->bed_level + depth);
     case PR_BC_STAGE_HYDROGRAPH: return 1;
     default: return NAN;
   }
@@ -863,7 +863,8 @@ static double gvf_dh_dx(const xs_t* xs, double g, double Q, double S0, double h_
 }
 
 int pr_oracle_gvf(const pr_config* cfg, const pr_geom* geom, const double* q0, int64_t q0_stride,
-                  double downstream_depth, double* ic_depth, double* ic_flow, int32_t* status_out) {
+                  const double* downstream_depth, int64_t hd_stride, double* ic_depth, double* ic_flow,
+                  int32_t* status_out) {
   int N = cfg->n_nodes, M = cfg->n_members;
   xs_t* xs = (xs_t*)malloc(sizeof(xs_t) * N);
   double dx = cfg->dx;                                    /* channel.py:308 == fitted spatial step */
@@ -872,7 +873,7 @@ int pr_oracle_gvf(const pr_config* cfg, const pr_geom* geom, const double* q0, i
     double Q = q0[(int64_t)m * q0_stride];
     double* hd = ic_depth + (size_t)m * N; double* qd = ic_flow + (size_t)m * N;
     int status = PR_STATUS_OK;
-    double h = downstream_depth;
+    double h = downstream_depth[(int64_t)m * hd_stride];
     hd[N - 1] = h; qd[N - 1] = Q;
     for (int i = N - 2; i >= 0; --i) {
       double S0 = (xs[i].z - xs[i + 1].z) / dx;           /* channel.py:344 (closure's loop index i) */

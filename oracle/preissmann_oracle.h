@@ -13,7 +13,8 @@ int pr_oracle_newton_step(const pr_config* cfg, const pr_geom* geom, const pr_bc
                           int member, int level, const double* h0, const double* q0, const double* h1,
                           const double* q1, double* stage_record, double* R, double* J, double* delta);
 int pr_oracle_gvf(const pr_config* cfg, const pr_geom* geom, const double* q0, int64_t q0_stride,
-                  double downstream_depth, double* ic_depth, double* ic_flow, int32_t* status);
+                  const double* downstream_depth, int64_t hd_stride, double* ic_depth, double* ic_flow,
+                  int32_t* status);
 int pr_oracle_objective(const pr_config* cfg, const double* up_flow, const double* up_depth, double z0,
                         const double* q_query, const double* h_target, int32_t n_query, double* levels_out,
                         double* rmse_out);

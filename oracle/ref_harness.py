@@ -210,8 +210,9 @@ def build_gerd(n_main=None, n_fp=None, calibration: bool = False, **over):
     up = Boundary(condition="flow_hydrograph", hydrograph=gerd, chainage=chain[0])
     down = Boundary(initial_depth=level0 - bed, bed_level=bed, condition="rating_curve",
                     rating_curve=RoseiresRatingCurve(initial_stage=level0, initial_flow=q0,
-                                                     jammed_sluice_gates=settings.JAMMED_SLUICEGATES,
-                                                     jammed_spillways=settings.JAMMED_SPILLWAYS),
+                                                     **{**dict(jammed_sluice_gates=settings.JAMMED_SLUICEGATES,
+                                                               jammed_spillways=settings.JAMMED_SPILLWAYS),
+                                                        **over.get("rating_kwargs", {})}),
                     chainage=chain[-1])
     ch = Channel(initial_flow=q0, upstream_boundary=up, downstream_boundary=down)
     if coords_path is not None:

@@ -224,3 +224,39 @@ def test_mirror_general_storage_run_matches_reference():
     assert np.array_equal(solver.iterations, ref["iters"])
     assert util.max_rel(solver.storage_stage, ref["storage_stage"]) <= util.RTOL
     assert np.all(np.isfinite(solver.storage_outflow))
+
+
+def test_release_scenarios_per_member_rating_curves_vs_reference_goldens():
+    """pr_bc.member_ratings: two members with different Roseires gate scenarios, pool levels and roughness in one
+    launch; each equals the reference run of its own scenario."""
+    flat, refs = util.release_ensemble()
+    out, _ = _check(flat, 2, "release scenarios")
+    for m, ref in enumerate(refs):
+        util.assert_parity(out["depth"][m], out["flow"][m], ref["depth"], ref["flow"], f"release member {m}")
+        assert np.array_equal(out["iters"][m], ref["iters"])
+
+
+def test_release_scenario_runner_builds_profiles_and_curves_per_member():
+    """EnsembleRunner.release_scenarios: 48 gate/pool-level scenarios from rating-curve objects, device GVF profile
+    from each member's own pool level, against the oracle fed the same flattened curves."""
+    import oracle_py
+    from flow_sim_b200.cases import gerd_roseires as gr
+    from flow_sim_b200.ensemble import EnsembleRunner, to_host
+    from flow_sim_b200.flatten import flatten_rating
+
+    flat = util.golden_inputs("gerd_release")
+    q0 = float(flat.meta["initial_flow"])
+    curves = [gr.RoseiresRatingCurve(initial_stage=485.5 + 0.05 * m, initial_flow=q0, jammed_spillways=m % 4,
+                                     jammed_sluice_gates=(m // 4) % 3, buffer=0.25 + 0.05 * (m % 5))
+              for m in range(48)]
+    res = to_host(EnsembleRunner(flat, "cuda:0").release_scenarios(curves, out_mode=abi.PR_OUT_FULL))
+    assert not res["ic_status"].any() and not res["status"].any()
+    ratings = [flatten_rating(c) for c in curves]
+    depth = np.array([r["stage0"] - flat.down.bed_level for r in ratings])
+    ho, qo, _ = oracle_py.gvf(flat, q0, depth, n_members=48)
+    flat.down.member_ratings = ratings
+    flat.ic_depth, flat.ic_flow = ho, qo
+    ora = oracle_py.run(flat, n_members=48)
+    util.assert_parity(res["depth"], res["flow"], ora["depth"], ora["flow"], "release scenarios (runner)")
+    assert np.array_equal(res["iters"], ora["iters"])
+    assert len({tuple(r) for r in res["iters"]}) > 8          # the scenarios really differ

@@ -75,6 +75,20 @@ def test_member_roughness_override_equals_reference_sections():
         assert pa == pb
 
 
+def test_release_scenario_ensemble_reproduces_both_reference_runs():
+    """Per-member rating curves (pr_bc.member_ratings): each member must equal the reference run of its own scenario."""
+    flat, refs = util.release_ensemble()
+    out = oracle_py.run(flat, n_members=2)
+    for m, ref in enumerate(refs):
+        assert out["status"][m] == abi.PR_STATUS_OK
+        util.assert_parity(out["depth"][m], out["flow"][m], ref["depth"], ref["flow"], f"release member {m}")
+        assert np.array_equal(out["iters"][m], ref["iters"])
+    # and the initial profiles come from the per-member downstream depth
+    depth = [flat.down.member_ratings[m]["stage0"] - flat.down.bed_level for m in range(2)]
+    h, q, st = oracle_py.gvf(flat, flat.meta["initial_flow"], depth, n_members=2)
+    assert not st.any() and util.max_rel(h, flat.ic_depth) <= 1e-12
+
+
 def test_roseires_release_curves_known_answers():
     """The reference's low/high_release_rating_curve.csv (10 printed digits)."""
     from flow_sim_b200.cases.gerd_roseires import RoseiresRatingCurve

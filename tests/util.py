@@ -11,7 +11,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL = 1e-9
 
 CALIB_MEMBERS = [0, 8191, 21845, 30000, 36408, 43690, 54321, 65535]
-SMALL_CASES = ["example", "akbari", "storage_general"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
+SMALL_CASES = ["example", "akbari", "storage_general", "gerd_release"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
 
 
 def calib_n(m):
@@ -47,3 +47,16 @@ def assert_parity(got_depth, got_flow, ref_depth, ref_flow, what, rtol=RTOL):
     assert ed <= rtol, f"{what}: depth rel err {ed:.3e} > {rtol}"
     assert eq <= rtol, f"{what}: flow rel err {eq:.3e} > {rtol}"
     return ed, eq
+
+
+def release_ensemble():
+    """Two-member release-scenario ensemble assembled from two reference goldens: member 0 = gerd_release
+    (pool 486.2 m, jammed gates, buffer 0.3, n = 0.03), member 1 = gerd_calib_m0 (the stock curve, n = 0.02).
+    Returns (flat, [ref outputs member 0, member 1])."""
+    a, b = golden_inputs("gerd_release"), golden_inputs("gerd_calib_m0")
+    flat = a
+    flat.down.member_ratings = [a.down.rating, b.down.rating]
+    flat.member_n_main = np.array([0.03, calib_n(0)])
+    flat.ic_depth = np.stack([a.ic_depth, b.ic_depth])
+    flat.ic_flow = np.stack([a.ic_flow, b.ic_flow])
+    return flat, [golden_outputs("gerd_release"), golden_outputs("gerd_calib_m0")]
