@@ -65,8 +65,9 @@ class pr_rating(C.Structure):
         ("spill", C.c_double * 6), ("sluice", C.c_double * 6),
         ("twl", C.c_double),
         ("open_state", C.c_double * PR_MAX_GATES), ("closed_state", C.c_double * PR_MAX_GATES),
-        ("n_gates", C.c_int32), ("sluices_open", C.c_int32), ("sluices_closed", C.c_int32), ("reserved", C.c_int32),
+        ("n_gates", C.c_int32), ("sluices_open", C.c_int32), ("sluices_closed", C.c_int32), ("gate_control", C.c_int32),
         ("stage0", C.c_double), ("buffer", C.c_double), ("q_hydro", C.c_double), ("dY", C.c_double),
+        ("max_cooldown", C.c_double), ("initially_open", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -212,7 +213,7 @@ def make_rating(d: dict | None) -> pr_rating:
         r.type = PR_RC_NONE
         return r
     r.type = int(d["type"])
-    for k in ("a", "b", "c", "stage_shift", "off", "scl", "twl", "stage0", "buffer", "q_hydro", "dY"):
+    for k in ("a", "b", "c", "stage_shift", "off", "scl", "twl", "stage0", "buffer", "q_hydro", "dY", "max_cooldown"):
         setattr(r, k, float(d.get(k, 0.0)))
     coef = list(np.asarray(d.get("coef", []), dtype=np.float64))
     dcoef = list(np.asarray(d.get("dcoef", []), dtype=np.float64))
@@ -236,4 +237,6 @@ def make_rating(d: dict | None) -> pr_rating:
     r.n_gates = int(d.get("n_gates", 0))
     r.sluices_open = int(d.get("sluices_open", 0))
     r.sluices_closed = int(d.get("sluices_closed", 0))
+    r.gate_control = int(d.get("gate_control", 0))
+    r.initially_open = int(d.get("initially_open", 0))
     return r

@@ -118,7 +118,8 @@ class RoseiresRatingCurve(RatingCurve):
     TAIL_WATER_LEVEL_RANGE = (440, 455)
 
     def __init__(self, initial_stage=None, initial_flow=None, initially_open=False, jammed_spillways=0,
-                 jammed_sluice_gates=0, smooth=True, buffer=0.5, deep_sluices_active=True, dY=0.001):
+                 jammed_sluice_gates=0, max_cooldown=3600 * 5, smooth=True, buffer=0.5, deep_sluices_active=True,
+                 dY=0.001):
         super().__init__()
         self.defined, self.type = True, "roseires"
         b = bundle()
@@ -138,6 +139,8 @@ class RoseiresRatingCurve(RatingCurve):
         self.tail_water_level = float(np.average(self.TAIL_WATER_LEVEL_RANGE))
         self.closed_state = self._closed_state(initial_flow)
         self.open = bool(initially_open)
+        # gate-control state (smooth=False): the device keeps one copy per member, seeded from these
+        self.max_cooldown, self.cooldown, self.prev_time, self.current_stage = max_cooldown, 0, None, initial_stage
 
     @staticmethod
     def _surface(c, s, o):
@@ -176,15 +179,34 @@ class RoseiresRatingCurve(RatingCurve):
         s = (stage - self.initial_stage) / self.buffer
         return 3 * s ** 2 - 2 * s ** 3
 
-    def discharge(self, stage, time=None, smooth=None, **_):
+    def gate_control(self, time):
+        """Open above initial_stage + 0.5, close below initial_stage - 1, at most once per max_cooldown seconds;
+        judged on the stage seen by the previous call (roseires_rating_curve.py:111-130)."""
+        if self.prev_time is not None:
+            self.cooldown = max(0, self.cooldown - (time - self.prev_time))
+        self.prev_time = time
+        if self.cooldown > 0:
+            return
+        if self.current_stage >= self.initial_stage + 0.5 and not self.open:
+            self.cooldown, self.open = self.max_cooldown, True
+        elif self.current_stage <= self.initial_stage - 1 and self.open:
+            self.cooldown, self.open = self.max_cooldown, False
+
+    def discharge(self, stage, time=None, update_stage=True, update_gate_state=True, smooth=None):
         if not (self.smooth if smooth is None else smooth):
-            return self.release(stage, self.open_state if self.open else self.closed_state)
+            if update_gate_state:
+                self.gate_control(time)
+            q = self.release(stage, self.open_state if self.open else self.closed_state)
+            if update_stage:
+                self.current_stage = stage
+            return q
         a = self.alpha_smooth(stage)
         return (1.0 - a) * self.release(stage, self.closed_state) + a * self.release(stage, self.open_state)
 
     def dQ_dz(self, stage, time=None, dY=None):
         dY = self.dY if dY is None else dY
-        return (self.discharge(stage + dY) - self.discharge(stage - dY)) / (2 * dY)
+        frozen = dict(time=time, update_stage=False, update_gate_state=False)
+        return (self.discharge(stage + dY, **frozen) - self.discharge(stage - dY, **frozen)) / (2 * dY)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -25,6 +25,15 @@ struct DevRating {
   //   Q_state(s) = q[0] + u*(q[1] + u*q[2]),  u = s - stage0
   double lo[3], hi[3], dlt[3];   // dlt = hi - lo
   double stage0, buffer, inv_buffer, dY, inv_2dY;
+  // gate_control = 1: RoseiresRatingCurve(smooth=False), per-member GateState
+  int gate_control, initially_open;
+  double max_cooldown;
+};
+
+// Per-member gate state of a gate-controlled Roseires curve (roseires_rating_curve.py:38-55); lives as long as the run.
+struct GateState {
+  double cooldown, prev_time, cur_stage;
+  int open, have_prev;
 };
 
 struct DevBC {
@@ -33,6 +42,7 @@ struct DevBC {
   const double* series;
   long long series_stride;
   DevRating rc;
+  int gated;                      // some member's curve is gate-controlled (stateful): needs the GST kernels
   const DevRating* member_rc;     // release scenarios: one reduced curve per member (device), or nullptr
   double st_area, st_inv_area, st_min_stage;
   // general lumped storage (lumped_storage.py:24-179): tabulated area curve, outflow rating curve, head losses
@@ -344,6 +354,27 @@ __device__ __forceinline__ double roseires_q(const DevRating& r, double stage) {
   return fma(alpha, dl, lo);                                // (1 - alpha) lo + alpha hi
 }
 
+__device__ __forceinline__ void gate_init(GateState& g, const DevRating& r) {
+  g.cooldown = 0.0; g.prev_time = 0.0; g.cur_stage = r.stage0; g.open = r.initially_open; g.have_prev = 0;
+}
+
+// RoseiresRatingCurve.gate_control (roseires_rating_curve.py:111-130): the decision uses the stage stored by the
+// PREVIOUS residual evaluation; 0.5 / 1.0 are the reference's hard-coded thresholds.
+__device__ __forceinline__ void gate_control(GateState& g, const DevRating& r, double time) {
+  if (g.have_prev) g.cooldown = fmax(0.0, g.cooldown - (time - g.prev_time));
+  g.prev_time = time; g.have_prev = 1;
+  if (g.cooldown > 0.0) return;
+  if (g.cur_stage >= r.stage0 + 0.5 && !g.open) { g.cooldown = r.max_cooldown; g.open = 1; }
+  else if (g.cur_stage <= r.stage0 - 1.0 && g.open) { g.cooldown = r.max_cooldown; g.open = 0; }
+}
+
+// total_release with the gates in their current position
+__device__ __forceinline__ double roseires_gated_q(const DevRating& r, int open, double stage) {
+  const double u = stage - r.stage0;
+  const double* c = open ? r.hi : r.lo;
+  return c[0] + u * (c[1] + u * c[2]);
+}
+
 // RatingCurve.discharge (rating_curve.py:32-63)
 __device__ __forceinline__ double rating_q(const DevRating& r, double stage) {
   switch (r.type) {
@@ -467,7 +498,8 @@ struct BcRow {
 template <bool GST>
 __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int member, const int level, const double hyd, const double h,
                                          const double Q, const double q_prev, const double stage_prev,
-                                         const double dt, const double g, const NodeConv& kc, const double T) {
+                                         const double dt, const double g, const NodeConv& kc, const double T,
+                                         GateState* gate = nullptr) {
   const double K = kc.K, dKA = kc.dKA;
   BcRow o;
   o.stage_rec = 0.0;
@@ -491,6 +523,15 @@ __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int member, cons
     case PR_BC_RATING_CURVE: {
       const double stage = bc.bed_level + h;
       const DevRating& rc = bc.member_rc ? bc.member_rc[member] : bc.rc;
+      if (GST && rc.type == PR_RC_ROSEIRES && rc.gate_control) {
+        // discharge(update_gate_state=True, update_stage=True) then dQ_dz with the state frozen (:65-81, :202-208)
+        gate_control(*gate, rc, level * dt);
+        o.res = Q - roseires_gated_q(rc, gate->open, stage);
+        gate->cur_stage = stage;
+        o.dh = 0.0 - (roseires_gated_q(rc, gate->open, stage + rc.dY) - roseires_gated_q(rc, gate->open, stage - rc.dY)) * rc.inv_2dY;
+        o.dq = 1.0;
+        break;
+      }
       o.res = Q - rating_q(rc, stage);
       o.dh = 0.0 - rating_dq(rc, stage);
       o.dq = 1.0;

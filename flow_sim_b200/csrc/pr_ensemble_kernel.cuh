@@ -214,6 +214,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
   }
   if (member_valid && owns_last && p.storage_stage) p.storage_stage[(size_t)member * L] = stage_prev;
+  GateState gate;
+  if (GST) gate_init(gate, p.dn.member_rc ? p.dn.member_rc[member] : p.dn.rc);
   // conveyance / friction slope of a boundary node are only needed by the normal-depth condition and by the head
   // losses of a lumped storage
   const bool up_normal = p.up.type == PR_BC_NORMAL_DEPTH;
@@ -326,7 +328,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
         node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
         T0 = t.T;
       }
-      D = bc_eval<GST>(p.dn, member, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, p.g, kc, T0);
+      D = bc_eval<GST>(p.dn, member, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, p.g, kc, T0, GST ? &gate : nullptr);
     }
     if (is_first) ss = fma(U.res, U.res, ss);
     if (owns_last) ss = fma(D.res, D.res, ss);
@@ -489,11 +491,13 @@ int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
   }                                                                                                          \
   template <bool CURV, int RM, bool EXACT>                                                                   \
   static int launch_x_##M_(const DevParams& p, cudaStream_t s) {                                             \
-    /* general lumped storage (Brent solve / losses): built for the plain variants only (-4 = unsupported) */ \
-    const bool gst = p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && (p.dn.st_general || p.dn.st_losses);          \
+    /* general lumped storage (Brent solve / losses) and gate-controlled rating curves: built without the  */ \
+    /* floodplain-roughness override and the straight-line variant (-4 = unsupported)                      */ \
+    const bool gst = (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && (p.dn.st_general || p.dn.st_losses)) ||      \
+                     (p.dn.type == PR_BC_RATING_CURVE && p.dn.gated);                                        \
     if (!gst) return launch_y_##M_<CURV, RM, EXACT, false>(p, s);                                            \
-    if (CURV || RM != 0) return -4;                                                                          \
-    return launch_y_##M_<false, 0, EXACT, true>(p, s);                                                       \
+    if (RM > 1) return -4;                                                                                   \
+    return launch_y_##M_<CURV, (RM & 1), false, true>(p, s);                                                 \
   }                                                                                                          \
   template <bool CURV, int RM>                                                                               \
   static int launch_one_##M_(const DevParams& p, cudaStream_t s) {                                           \

@@ -49,6 +49,7 @@ struct LongParams {
   double* err2;        // [M] partial ||R||^2 (tiles)
   int *level, *it, *active, *conv, *out_level;   // [M] per-member state machine
   double *qprev_last, *stage_prev;               // [M] boundary bookkeeping
+  GateState* gate;                               // [M] gate-controlled rating curve state
   int* n_done;         // members finished so far
   int T, Kc;
 };
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   if (lane == Lc) {
     NodeVals nvb; NodeConv kc;
     node_eval<false, 0, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
-    D = bc_eval<true>(p.dn, m, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T);
+    D = bc_eval<true>(p.dn, m, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T, &q.gate[m]);
   }
   const double Ures = __shfl_sync(kFull, U.res, 0), Dres = __shfl_sync(kFull, D.res, Lc);
   const bool bc_failed = __any_sync(kFull, U.fail || D.fail);
@@ -399,6 +400,7 @@ __global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
     q.qprev_last[m] = qv;
     const double st = q.geo[F_Z * p.N + nd] + h;
     q.stage_prev[m] = st;
+    gate_init(q.gate[m], p.dn.member_rc ? p.dn.member_rc[m] : p.dn.rc);
     if (p.storage_stage) p.storage_stage[(size_t)m * p.L] = st;
     q.level[m] = 1; q.it[m] = 0; q.conv[m] = 0; q.out_level[m] = 0; q.err2[m] = 0.0;
     q.active[m] = p.L > 1 ? 1 : 0;
@@ -432,7 +434,7 @@ __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
 // Grow-only device workspace of the long-reach path, kept between calls (allocating and freeing ~7 GB per call
 // costs 50-200 ms); released by pr_release_workspace() or at process exit by the driver.
 struct LongWorkspace {
-  static constexpr int kSlots = 16;
+  static constexpr int kSlots = 32;
   void* ptr[kSlots] = {};
   size_t bytes[kSlots] = {};
   int device = -1;
@@ -441,6 +443,7 @@ struct LongWorkspace {
   }
   void* get(int slot, size_t n, cudaError_t& e) {
     if (e != cudaSuccess) return nullptr;
+    if (slot < 0 || slot >= kSlots) { e = cudaErrorInvalidValue; return nullptr; }
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != device) { release(); device = dev; }
@@ -490,6 +493,7 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
   q.err2 = (double*)dalloc(sizeof(double) * M);
   q.qprev_last = (double*)dalloc(sizeof(double) * M);
   q.stage_prev = (double*)dalloc(sizeof(double) * M);
+  q.gate = (GateState*)dalloc(sizeof(GateState) * M);
   q.level = (int*)dalloc(sizeof(int) * M); q.it = (int*)dalloc(sizeof(int) * M);
   q.active = (int*)dalloc(sizeof(int) * M); q.conv = (int*)dalloc(sizeof(int) * M);
   q.out_level = (int*)dalloc(sizeof(int) * M);

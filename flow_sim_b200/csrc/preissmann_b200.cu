@@ -143,6 +143,10 @@ int make_rating(const pr_rating& r, pr::DevRating& d) {
     for (int i = 0; i < 3; ++i) { d.lo[i] = (double)lo[i]; d.hi[i] = (double)hi[i]; d.dlt[i] = (double)(hi[i] - lo[i]); }
     d.stage0 = r.stage0; d.buffer = r.buffer; d.inv_buffer = 1.0 / r.buffer;
     d.dY = r.dY; d.inv_2dY = 1.0 / (2 * r.dY);
+    d.gate_control = r.gate_control ? 1 : 0;
+    d.initially_open = r.initially_open ? 1 : 0;
+    d.max_cooldown = r.max_cooldown;
+    if (d.gate_control && !(r.max_cooldown >= 0)) return fail(PR_ERR_ARG, "rating: max_cooldown must be >= 0");
   }
   if (r.type < PR_RC_NONE || r.type > PR_RC_ROSEIRES) return fail(PR_ERR_ARG, "rating: unknown type %d", r.type);
   return PR_OK;
@@ -177,12 +181,16 @@ int make_bc(const pr_bc& b, const char* which, bool downstream, const pr_config&
     case PR_BC_RATING_CURVE:
       if (b.rating.type == PR_RC_NONE) return fail(PR_ERR_ARG, "%s boundary: rating_curve without a curve", which);
       if (int rc = make_rating(b.rating, d.rc)) return rc;
+      d.gated = d.rc.gate_control;
       if (b.member_ratings) {          // release scenarios: reduce every member's curve on the host, ship the array
         std::vector<pr::DevRating> all((size_t)cfg.n_members);
         for (int64_t m = 0; m < cfg.n_members; ++m)
           if (int rc = make_rating(b.member_ratings[m], all[(size_t)m])) return rc;
+        d.gated = 0;
+        for (const auto& r : all) d.gated |= r.gate_control;
         d.member_rc = st.in_host(all.data(), all.size());
       }
+      if (d.gated && !downstream) return fail(PR_ERR_UNSUPPORTED, "gate-controlled rating curve at the upstream boundary");
       break;
     case PR_BC_FIXED_DEPTH_STORAGE:
       if (!downstream) return fail(PR_ERR_UNSUPPORTED, "lumped storage at the upstream boundary");
@@ -261,8 +269,8 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
 
 int launch_family(int rc_cuda) {
   if (rc_cuda == -4)
-    return fail(PR_ERR_UNSUPPORTED, "general lumped storage (area curve / outflow curve / head losses) together with "
-                                    "centre-line curvature or per-member roughness overrides");
+    return fail(PR_ERR_UNSUPPORTED, "general lumped storage (area curve / outflow curve / head losses) or a gate-controlled "
+                                    "rating curve together with per-member floodplain roughness overrides");
   if (rc_cuda != 0) return fail(PR_ERR_CUDA, "ensemble kernel launch: %s", cudaGetErrorString((cudaError_t)rc_cuda));
   g_launches.fetch_add(1);
   return PR_OK;

@@ -154,8 +154,10 @@ def flatten_rating(rc) -> dict | None:
         return None
     # Roseires-style gate curve (reference class or this package's mirror)
     if hasattr(rc, "spillway_model") or hasattr(rc, "spill_coef"):
-        if not getattr(rc, "smooth", True):
-            raise NotImplementedError("RoseiresRatingCurve(smooth=False) (stateful gate control) is SURVEY.md 8f-3")
+        gated = not getattr(rc, "smooth", True)
+        if gated and (getattr(rc, "prev_time", None) is not None or rc.cooldown != 0
+                      or rc.current_stage != rc.initial_stage):
+            raise NotImplementedError("gate-controlled rating curve that has already been stepped (only a fresh one is supported)")
         if hasattr(rc, "spill_coef"):
             spill, sluice = np.asarray(rc.spill_coef, float), np.asarray(rc.sluice_coef, float)
             q_hydro = float(rc.hydropower_q)
@@ -171,7 +173,9 @@ def flatten_rating(rc) -> dict | None:
         return dict(type=abi.PR_RC_ROSEIRES, spill=spill, sluice=sluice, twl=float(rc.tail_water_level),
                     open_state=pad(open_gates), closed_state=pad(closed_gates), n_gates=n_gates,
                     sluices_open=int(open_sl), sluices_closed=int(closed_sl),
-                    stage0=float(rc.initial_stage), buffer=float(rc.buffer), q_hydro=q_hydro, dY=dY)
+                    stage0=float(rc.initial_stage), buffer=float(rc.buffer), q_hydro=q_hydro, dY=dY,
+                    gate_control=int(gated), initially_open=int(bool(rc.open)) if gated else 0,
+                    max_cooldown=float(getattr(rc, "max_cooldown", 0.0)))
     if not getattr(rc, "defined", False):
         raise ValueError("Rating curve is undefined.")
     shift = float(getattr(rc, "stage_shift", 0) or 0)
@@ -309,7 +313,7 @@ def _bc_from_npz(prefix: str, z) -> FlatBoundary:
         for k in keys:
             v = np.array(z[k])
             name = k[len(prefix) + len(tag) + 2:]
-            d[name] = v if v.ndim else (int(v) if name in ("type", "n_gates", "sluices_open", "sluices_closed") else float(v))
+            d[name] = v if v.ndim else (int(v) if name in ("type", "n_gates", "sluices_open", "sluices_closed", "gate_control", "initially_open") else float(v))
         return d
 
     b.rating = rating_from("rating")

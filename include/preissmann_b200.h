@@ -120,15 +120,22 @@ typedef struct pr_rating {
   double a, b, c, stage_shift;                 /* POLY2 / POWER */
   double coef[PR_MAX_POLY], dcoef[PR_MAX_POLY]; /* POLYNOMIAL: p and p' series in the mapped variable */
   double off, scl;                              /* POLYNOMIAL: u = off + scl*x (Polynomial.mapparms) */
-  /* ROSEIRES (smooth=True only): Q = (1-a) Q_closed + a Q_open, a = smoothstep((stage-stage0)/buffer)
+  /* ROSEIRES, gate_control = 0 (smooth=True, the default): Q = (1-a) Q_closed + a Q_open,
+   *   a = smoothstep((stage-stage0)/buffer).
+   * gate_control = 1 (smooth=False, roseires_rating_curve.py:65-81,111-142): Q = Q_open or Q_closed by a per-member
+   *   gate state: at every residual evaluation the cool-down runs down by the time since the last one, then the
+   *   gates open when the stage seen at the previous evaluation is >= stage0 + 0.5 (close when <= stage0 - 1) and
+   *   the cool-down restarts at max_cooldown; the state lives for the whole run.
    * Q_state = sum_{opening_j>0} spill(stage, opening_j) + n_sluices*sluice(stage, twl) + q_hydro
    * spill/sluice(s, o) = c[0] + c[1] s + c[2] o + c[3] s^2 + c[4] s o + c[5] o^2
    *   (sklearn PolynomialFeatures(2, include_bias=False) + LinearRegression: intercept_, coef_) */
   double spill[6], sluice[6];
   double twl;
   double open_state[PR_MAX_GATES], closed_state[PR_MAX_GATES];
-  int32_t n_gates, sluices_open, sluices_closed, reserved;
+  int32_t n_gates, sluices_open, sluices_closed, gate_control;
   double stage0, buffer, q_hydro, dY;           /* dY = 1e-3: central-difference step of dQ_dz */
+  double max_cooldown;                           /* gate_control = 1: seconds (reference default 18000) */
+  int32_t initially_open, reserved;
 } pr_rating;
 
 /* One boundary (boundary.py:7-247).  `series` = Hydrograph.get_at(k*dt) sampled for k = 0..levels-1

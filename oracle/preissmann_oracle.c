@@ -303,6 +303,29 @@ static double ro_discharge(const pr_rating* r, double stage) {
   return (1.0 - alpha) * low_Q + alpha * high_Q;
 }
 
+/* RoseiresRatingCurve(smooth=False): stateful gate control, roseires_rating_curve.py:65-81,111-142.
+ * `time` is the solver's time_level*time_step (boundary.py:95). */
+typedef struct { int open, have_prev; double cooldown, prev_time, current_stage; } gate_t;
+
+static void gate_init(gate_t* g, const pr_rating* r) {
+  g->open = r->initially_open ? 1 : 0; g->have_prev = 0; g->cooldown = 0; g->prev_time = 0; g->current_stage = r->stage0;
+}
+
+static double ro_discharge_gated(const pr_rating* r, gate_t* g, double stage, double time, int update) {
+  if (update) {                                   /* gate_control(time), :111-124 */
+    if (g->have_prev) { double c = g->cooldown - (time - g->prev_time); g->cooldown = c > 0 ? c : 0; }
+    g->prev_time = time; g->have_prev = 1;
+    if (!(g->cooldown > 0)) {
+      if (g->current_stage >= r->stage0 + 0.5 && !g->open) { g->cooldown = r->max_cooldown; g->open = 1; }
+      else if (g->current_stage <= r->stage0 - 1 && g->open) { g->cooldown = r->max_cooldown; g->open = 0; }
+    }
+  }
+  double Q = g->open ? ro_total_release(r, stage, r->open_state, r->sluices_open)
+                     : ro_total_release(r, stage, r->closed_state, r->sluices_closed);
+  if (update) g->current_stage = stage;
+  return Q;
+}
+
 static double polyval(const double* c, int n, double x) {   /* numpy.polynomial.polynomial.polyval (Horner) */
   double c0 = c[n - 1];
   for (int i = 2; i <= n; ++i) c0 = c[n - i] + c0 * x;
@@ -468,7 +491,16 @@ typedef struct {
   int member, level;
   double dt, g;
   double* stage_record;   /* storage: [levels] of this member, entry k = stage recorded for level k */
+  gate_t* gate;           /* Roseires gate state of this member (gate_control = 1), persists over the whole run */
 } bc_ctx;
+
+static const pr_rating* bc_rating(const bc_ctx* c) {
+  return c->bc->member_ratings ? &c->bc->member_ratings[c->member] : &c->bc->rating;
+}
+static int bc_gated(const bc_ctx* c) {
+  const pr_rating* r = bc_rating(c);
+  return r->type == PR_RC_ROSEIRES && r->gate_control && c->gate;
+}
 
 static double bc_series(const bc_ctx* c) {
   return c->bc->series[(int64_t)c->member * c->bc->series_member_stride + c->level];
@@ -486,7 +518,9 @@ static double bc_residual(const bc_ctx* c, double depth, double flow, double vol
       if (b->bed_slope < 0) Qn = -Qn;
       return flow - Qn;
     }
-    case PR_BC_RATING_CURVE: return flow - pr_oracle_rating_discharge(b->member_ratings ? &b->member_ratings[c->member] : &b->rating, b->bed_level + depth);
+    case PR_BC_RATING_CURVE:
+      if (bc_gated(c)) return flow - ro_discharge_gated(bc_rating(c), c->gate, b->bed_level + depth, c->level * c->dt, 1);
+      return flow - pr_oracle_rating_discharge(bc_rating(c), b->bed_level + depth);
     case PR_BC_FIXED_DEPTH: return depth - b->fixed_depth;
     case PR_BC_STAGE_HYDROGRAPH: return depth - (bc_series(c) - b->bed_level);
     case PR_BC_FIXED_DEPTH_STORAGE: {
@@ -523,7 +557,15 @@ static double bc_df_dh(const bc_ctx* c, double depth, double flow) {
       if (b->bed_slope < 0) dQ = -dQ;
       return 0 - dQ * dA_dh;
     }
-    case PR_BC_RATING_CURVE: return 0 - pr_oracle_rating_dQdz(b->member_ratings ? &b->member_ratings[c->member] : &b->rating, b->bed_level + depth);
+    case PR_BC_RATING_CURVE: {
+      const pr_rating* r = bc_rating(c);
+      double stage = b->bed_level + depth;
+      if (bc_gated(c)) {                          /* dQ_dz with update_stage = update_gate_state = False, :202-208 */
+        double fp = ro_discharge_gated(r, c->gate, stage + r->dY, 0, 0), fm = ro_discharge_gated(r, c->gate, stage - r->dY, 0, 0);
+        return 0 - (fp - fm) / (2 * r->dY);
+      }
+      return 0 - pr_oracle_rating_dQdz(r, stage);
+    }
     case PR_BC_STAGE_HYDROGRAPH: return 1;
     default: return NAN;
   }
@@ -733,8 +775,8 @@ int pr_oracle_newton_step(const pr_config* cfg, const pr_geom* geom, const pr_bc
   xs_t* xs = (xs_t*)malloc(sizeof(xs_t) * N);
   for (int i = 0; i < N; ++i) xs[i] = xs_load(geom, i, member);
   sch_t s = {N, cfg->theta, cfg->dt, cfg->dx, cfg->g, xs, h0, q0, h1, q1};
-  bc_ctx up = {up_bc, &xs[0], member, level, cfg->dt, cfg->g, stage_record};
-  bc_ctx dn = {dn_bc, &xs[N - 1], member, level, cfg->dt, cfg->g, stage_record};
+  bc_ctx up = {up_bc, &xs[0], member, level, cfg->dt, cfg->g, stage_record, NULL};
+  bc_ctx dn = {dn_bc, &xs[N - 1], member, level, cfg->dt, cfg->g, stage_record, NULL};
   int err = assemble(&s, &up, &dn, R, J);
   double(*B)[9] = (double(*)[9])calloc(n2, sizeof(double[9]));
   double* rhs = (double*)malloc(sizeof(double) * n2);
@@ -786,12 +828,15 @@ int pr_oracle_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* up_bc,
       stage[0] = Y - st_energy_loss(dn_bc, cfg->g, A, q_ic[N - 1], xs_equivalent_n(&xs[N - 1], Y), R);
     }
     int status = PR_STATUS_OK, fail_level = 0;
+    gate_t gate_up, gate_dn;
+    gate_init(&gate_up, up_bc->member_ratings ? &up_bc->member_ratings[m] : &up_bc->rating);
+    gate_init(&gate_dn, dn_bc->member_ratings ? &dn_bc->member_ratings[m] : &dn_bc->rating);
     for (int k = 1; k < L && status == PR_STATUS_OK; ++k) {
       double* hk0 = depth + (size_t)(k - 1) * N; double* qk0 = flow + (size_t)(k - 1) * N;
       double* hk1 = depth + (size_t)k * N;       double* qk1 = flow + (size_t)k * N;
       sch_t s = {N, cfg->theta, cfg->dt, cfg->dx, cfg->g, xs, hk0, qk0, hk1, qk1};
-      bc_ctx up = {up_bc, &xs[0], m, k, cfg->dt, cfg->g, stage};
-      bc_ctx dn = {dn_bc, &xs[N - 1], m, k, cfg->dt, cfg->g, stage};
+      bc_ctx up = {up_bc, &xs[0], m, k, cfg->dt, cfg->g, stage, &gate_up};
+      bc_ctx dn = {dn_bc, &xs[N - 1], m, k, cfg->dt, cfg->g, stage, &gate_dn};
       int iteration = 0, converged = 0;
       double error = NAN;
       while (!converged) {

@@ -260,3 +260,33 @@ def test_release_scenario_runner_builds_profiles_and_curves_per_member():
     util.assert_parity(res["depth"], res["flow"], ora["depth"], ora["flow"], "release scenarios (runner)")
     assert np.array_equal(res["iters"], ora["iters"])
     assert len({tuple(r) for r in res["iters"]}) > 8          # the scenarios really differ
+
+
+def test_gate_controlled_rating_curve_state_per_member():
+    """RoseiresRatingCurve(smooth=False): every member carries its own gate state (open flag, cool-down, last stage).
+    Members differ in initial gate position, cool-down, roughness and inflow scale; one of them stops converging
+    when its gates slam shut - all against the oracle, which reproduces the reference's gated run (gerd_gated)."""
+    flat = util.golden_inputs("gerd_gated")
+    base = np.array(flat.up.series)
+    variants = [(1.0, 7200.0, 1, 0.030), (1.0, 18000.0, 0, 0.030), (4.0, 7200.0, 1, 0.025), (3.0, 3600.0, 0, 0.040),
+                (6.0, 3600.0, 1, 0.030), (2.0, 0.0, 1, 0.035)]
+    M = len(variants)
+    flat.up.series = np.stack([base[0] + (base - base[0]) * v[0] for v in variants])
+    flat.down.member_ratings = [dict(flat.down.rating, max_cooldown=v[1], initially_open=v[2]) for v in variants]
+    flat.member_n_main = np.array([v[3] for v in variants])
+    out, ora = _check(flat, M, "gate-controlled ensemble")
+    assert out["status"].tolist().count(abi.PR_STATUS_MAX_ITER) >= 1 and out["status"][0] == abi.PR_STATUS_OK
+    ref = util.golden_outputs("gerd_gated")
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], "gated member 0 vs reference")
+    # mixed launch: gated and smooth members side by side
+    flat.down.member_ratings[1] = dict(flat.down.rating, gate_control=0)
+    _check(flat, M, "gated + smooth members")
+
+
+def test_gate_controlled_curve_on_the_long_reach_path():
+    flat = util.golden_inputs("gerd_gated")
+    ref = util.golden_outputs("gerd_gated")
+    out = run_flat(flat, n_members=3, lanes=-1)
+    for m in range(3):
+        util.assert_parity(out["depth"][m], out["flow"][m], ref["depth"], ref["flow"], "gated, tiled path")
+        assert np.array_equal(out["iters"][m], ref["iters"])

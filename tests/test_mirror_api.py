@@ -110,8 +110,11 @@ def test_unsupported_configurations_are_rejected_not_emulated():
     with pytest.raises(NotImplementedError, match="TrapezoidalSection"):
         flatten_solver(s)
     s, _ = build_gerd(calibration=True)
-    s.channel.downstream_boundary.rating_curve.smooth = False
-    with pytest.raises(NotImplementedError):
+    rc = s.channel.downstream_boundary.rating_curve
+    rc.smooth = False
+    assert flatten_solver(s).down.rating["gate_control"] == 1          # a fresh gate-controlled curve is supported ...
+    rc.discharge(stage=rc.initial_stage + 0.7, time=3600)               # ... one that has already been stepped is not
+    with pytest.raises(NotImplementedError, match="already been stepped"):
         flatten_solver(s)
     with pytest.raises(ValueError, match="Invalid boundary condition"):
         hydromodel.Boundary(condition="weir", chainage=0)
