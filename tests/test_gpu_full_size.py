@@ -1,0 +1,61 @@
+"""BASELINE.json's full sizes on the GPU, checked through what does not depend on a CPU re-run of the whole job:
+the reference's own goldens for the members it was run on, permutation invariance of the ensemble, and an oracle
+re-run of single members (config 4: 65 536 members x 121 nodes x 32 steps; config 5: 100 001 nodes x 1024
+scenarios x 16 steps)."""
+import numpy as np
+import pytest
+
+import util
+from flow_sim_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+Q_QUERY = [1562.5, 3850, 6000, 10000, 14000, 21000]
+H_TARGET = [497.5, 500, 502, 505, 507, 510]
+
+
+def test_config4_full_ensemble_reference_members_and_permutation_invariance():
+    from flow_sim_b200.ensemble import EnsembleRunner, to_host
+
+    flat = util.golden_inputs("gerd_calib_m0")
+    M = 65536
+    n_main = 0.020 + 0.040 * np.arange(M) / 65535
+    runner = EnsembleRunner(flat, "cuda:0")
+    res = to_host(runner.roughness_sweep(n_main, q_query=Q_QUERY, h_target=H_TARGET))
+    assert not res["status"].any() and not res["ic_status"].any()
+    for m in util.CALIB_MEMBERS:                       # the members the live reference was run on
+        ref = util.golden_outputs(f"gerd_calib_m{m}")
+        util.assert_parity(res["depth"][m], res["flow"][m], ref["depth"][:, 0], ref["flow"][:, 0], f"member {m}")
+        assert np.array_equal(res["iters"][m], ref["iters"]), f"member {m}: iteration counts"
+        assert abs(res["rmse"][m] - float(ref["calib_rmse"])) <= util.RTOL * float(ref["calib_rmse"])
+        assert util.max_rel(res["levels"][m], ref["calib_levels"]) <= util.RTOL
+    # the objective is smooth in n and the iteration count grows with it (409 -> 676 over the grid)
+    tot = res["iters"].sum(axis=1)
+    assert tot[0] == 409 and tot[-1] == 676 and np.all(np.abs(np.diff(res["rmse"])) < 1e-3)
+    # a member's result does not depend on where it sits in the launch: bit-identical under a permutation
+    perm = np.random.default_rng(5).permutation(M)
+    res2 = to_host(runner.roughness_sweep(n_main[perm], q_query=Q_QUERY, h_target=H_TARGET))
+    for k in ("depth", "flow", "iters", "rmse"):
+        assert np.array_equal(res2[k], res[k][perm]), k
+
+
+def test_config5_full_long_reach_members_vs_oracle():
+    import oracle_py
+    from flow_sim_b200.cases.akbari_firoozi import build_long_reach, flood_wave
+    from flow_sim_b200.ensemble import EnsembleRunner, to_host
+    from flow_sim_b200.flatten import flatten_solver
+
+    N, M, steps = 100_001, 1024, 16
+    solver, kw = build_long_reach(n_nodes=N, n_steps=steps)
+    flat = flatten_solver(solver, tolerance=kw["tolerance"])
+    L = flat.n_levels
+    peaks = 100.0 + 200.0 * np.arange(M) / (M - 1)
+    series = np.array([[flood_wave(peak_flow=pk)(k * flat.dt) for k in range(L)] for pk in peaks])
+    res = to_host(EnsembleRunner(flat, "cuda:0").solve(M, up_series=series, out_mode=abi.PR_OUT_UPSTREAM))
+    assert not res["status"].any()
+    assert np.all(np.diff(res["depth"][:, -1]) > 0)                     # a larger flood peak -> a higher upstream stage
+    for m in (0, 1023):
+        flat.up.series = series[m]
+        ora = oracle_py.run(flat, n_members=1, out_mode=abi.PR_OUT_UPSTREAM)
+        util.assert_parity(res["depth"][m], res["flow"][m], ora["depth"][0], ora["flow"][0], f"scenario {m}")
+        assert np.array_equal(res["iters"][m], ora["iters"][0])
