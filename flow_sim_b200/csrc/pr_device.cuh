@@ -522,19 +522,23 @@ __device__ __forceinline__ BcRow bc_eval(const DevBC& bc, const int member, cons
       break;
     case PR_BC_RATING_CURVE: {
       const double stage = bc.bed_level + h;
-      const DevRating& rc = bc.member_rc ? bc.member_rc[member] : bc.rc;
-      if (GST && rc.type == PR_RC_ROSEIRES && rc.gate_control) {
-        // discharge(update_gate_state=True, update_stage=True) then dQ_dz with the state frozen (:65-81, :202-208)
-        gate_control(*gate, rc, level * dt);
-        o.res = Q - roseires_gated_q(rc, gate->open, stage);
-        gate->cur_stage = stage;
-        o.dh = 0.0 - (roseires_gated_q(rc, gate->open, stage + rc.dY) - roseires_gated_q(rc, gate->open, stage - rc.dY)) * rc.inv_2dY;
+      // two instantiations on purpose: the shared curve is read straight from the kernel-parameter constant bank,
+      // the per-member one from global memory
+      auto rows = [&](const DevRating& rc) {
+        if (GST && rc.type == PR_RC_ROSEIRES && rc.gate_control) {
+          // discharge(update_gate_state=True, update_stage=True) then dQ_dz with the state frozen (:65-81, :202-208)
+          gate_control(*gate, rc, level * dt);
+          o.res = Q - roseires_gated_q(rc, gate->open, stage);
+          gate->cur_stage = stage;
+          o.dh = 0.0 - (roseires_gated_q(rc, gate->open, stage + rc.dY) - roseires_gated_q(rc, gate->open, stage - rc.dY)) * rc.inv_2dY;
+        } else {
+          o.res = Q - rating_q(rc, stage);
+          o.dh = 0.0 - rating_dq(rc, stage);
+        }
         o.dq = 1.0;
-        break;
-      }
-      o.res = Q - rating_q(rc, stage);
-      o.dh = 0.0 - rating_dq(rc, stage);
-      o.dq = 1.0;
+      };
+      if (bc.member_rc) rows(bc.member_rc[member]);
+      else rows(bc.rc);
       break;
     }
     case PR_BC_FIXED_DEPTH_STORAGE: {

@@ -380,10 +380,10 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
     return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: this build has the 32-lane instantiations", cfg->lanes_per_member);
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
   if (cfg->lanes_per_member == -1) rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);   // forced long-reach path
-  else if (need <= 1) rc = launch_family(pr::launch_ensemble_family<1, 12>(p, has_curv, s));
-  else if (need <= 2) rc = launch_family(pr::launch_ensemble_family<2, 12>(p, has_curv, s));
+  else if (need <= 1) rc = launch_family(pr::launch_ensemble_family<1, 16>(p, has_curv, s));
+  else if (need <= 2) rc = launch_family(pr::launch_ensemble_family<2, 16>(p, has_curv, s));
   else if (need <= 4) rc = launch_family(pr::launch_ensemble_family<4, PR_W4>(p, has_curv, s));
-  else if (need <= 8) rc = launch_family(pr::launch_ensemble_family<8, 5>(p, has_curv, s));
+  else if (need <= 8) rc = launch_family(pr::launch_ensemble_family<8, 7>(p, has_curv, s));
   else rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);
   if (rc) return rc;
   cudaError_t e = st.finish();

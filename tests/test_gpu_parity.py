@@ -10,7 +10,7 @@ from flow_sim_b200.runner import run_flat
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case", util.SMALL_CASES + ["gerd_full"])
+@pytest.mark.parametrize("case", util.SMALL_CASES + ["gerd_full", "gerd_gated_full"])
 def test_cuda_vs_reference_golden(case):
     if not util.has_golden_outputs(case):
         pytest.skip("golden outputs not generated")

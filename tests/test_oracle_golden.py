@@ -12,7 +12,7 @@ import util
 from flow_sim_b200 import abi
 
 
-@pytest.mark.parametrize("case", util.SMALL_CASES + ["gerd_full", "akbari_long"])
+@pytest.mark.parametrize("case", util.SMALL_CASES + ["gerd_full", "akbari_long", "gerd_gated_full"])
 def test_oracle_reproduces_reference_run(case):
     flat = util.golden_inputs(case)
     ref = util.golden_outputs(case)
