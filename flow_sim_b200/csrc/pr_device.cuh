@@ -347,7 +347,9 @@ __device__ __forceinline__ double roseires_q(const DevRating& r, double stage) {
   // RoseiresRatingCurve.alpha_smooth + effective_release (roseires_rating_curve.py:87-109)
   // alpha = 0 below stage0, 1 above stage0 + buffer, smoothstep between: clamping s does all three
   const double u = stage - r.stage0;
-  const double s = fmin(fmax(u * r.inv_buffer, 0.0), 1.0);
+  double s = u * r.inv_buffer;
+  s = s > 0.0 ? s : 0.0;                                    // (cheaper than fmin/fmax; a NaN stage still ends in NaN)
+  s = s < 1.0 ? s : 1.0;
   const double alpha = s * s * (3.0 - 2.0 * s);
   const double lo = r.lo[0] + u * (r.lo[1] + u * r.lo[2]);
   const double dl = r.dlt[0] + u * (r.dlt[1] + u * r.dlt[2]);

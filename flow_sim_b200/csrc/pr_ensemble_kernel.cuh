@@ -221,6 +221,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   const bool up_normal = p.up.type == PR_BC_NORMAL_DEPTH;
   const bool dn_normal = p.dn.type == PR_BC_NORMAL_DEPTH || (GST && p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses);
 
+  const bool roseires3 = !GST && G == 32 && p.dn.type == PR_BC_RATING_CURVE && !p.dn.member_rc && p.dn.rc.type == PR_RC_ROSEIRES;
+
   int level = 1, it = 0;
   bool active = member_valid && L > 1;
   int status = PR_STATUS_OK, fail_level = 0;
@@ -318,7 +320,18 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       }
       U = bc_eval<false>(p.up, member, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, p.g, kc, T0);
     }
-    if (owns_last) {
+    if (roseires3) {
+      // Shared Roseires curve: dQ/dz is a central difference (quirk 10), i.e. three curve evaluations per iteration on
+      // a single lane.  Run them on three lanes at once instead: owner (stage), owner+1 (stage + dY), owner+2 (- dY).
+      double hl, ql;
+      last_node(hl, ql);
+      const double stage = p.dn.bed_level + __shfl_sync(kFull, hl, owner_last, G);
+      const int role = (gl - owner_last) & (G - 1);
+      const double qv = roseires_q(p.dn.rc, stage + (role == 1 ? p.dn.rc.dY : role == 2 ? -p.dn.rc.dY : 0.0));
+      const double qp = __shfl_sync(kFull, qv, (owner_last + 1) & (G - 1), G);
+      const double qm = __shfl_sync(kFull, qv, (owner_last + 2) & (G - 1), G);
+      if (owns_last) { D.res = ql - qv; D.dh = 0.0 - (qp - qm) * p.dn.rc.inv_2dY; D.dq = 1.0; }
+    } else if (owns_last) {
       double hl, ql;
       last_node(hl, ql);
       NodeConv kc = {0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
