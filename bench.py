@@ -321,9 +321,11 @@ def run_gpu_arm(args) -> dict | None:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     out_bytes = M * L * 16.0 + M * (L - 1) * 4.0 + M * 8.0    # boundary series + iteration counts + status
-    traffic = None
+    traffic, pipe_pct = None, None
     try:
-        traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("ensemble_kernel_dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+        traffic = prof.get("ensemble_kernel_dram_bytes_per_launch")
+        pipe_pct = prof.get("ensemble_kernel_fp64_pipe_pct_ncu")
     except Exception:
         pass
 
@@ -384,6 +386,8 @@ def run_gpu_arm(args) -> dict | None:
                      "frac": achieved_tf / tf.value if tf.value > 0 else None, "traffic": traffic,
                      "kernel": "pr_ensemble_kernel<G=32, M=4, W=16, CURV=0, RM=1, EXACT=1>",
                      "flops_per_node_iteration": f_iter, "overbank_share": over,
+                     "fp64_pipe_pct_ncu": pipe_pct,     # from the committed ncu capture (profiles/), not this run
+
                      "peak_source": "pr_fp64_peak: register-resident DFMA microbenchmark measured in this run "
                                     "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
                      "hbm_view": {"algorithmic_bytes_per_launch": out_bytes, "achieved_gbs": out_bytes / solve_s / 1e9,
