@@ -4,6 +4,11 @@ path.  Reports node-steps/s, node-iterations/s and the HBM roofline fraction (SU
 per node per Newton iteration).  Not the bench.py headline (that is config 4); a tool for DESIGN.md numbers.
 
     python tools/bench_long.py [--nodes 100000] [--members 1024] [--steps 16] [--repeat 3]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_long.py   # N GPUs
+
+Under torchrun every rank runs --members scenarios of the global peak-flow grid (weak scaling, round-robin deal,
+no traffic in the time loop) and the upstream stage series are gathered once at the end; the time is the max
+over ranks of the CUDA-event time.
 """
 import argparse
 import json
@@ -26,10 +31,18 @@ def main():
     ap.add_argument("--check", type=int, default=1, help="members re-run on the CPU oracle")
     a = ap.parse_args()
     import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from flow_sim_b200 import abi
     from flow_sim_b200.cases.akbari_firoozi import BASE_FLOW, build_long_reach, flood_wave
-    from flow_sim_b200.ensemble import EnsembleRunner
+    from flow_sim_b200.ensemble import EnsembleRunner, gather_members, shard_members
     from flow_sim_b200.flatten import flatten_solver
 
     t0 = time.time()
@@ -37,13 +50,14 @@ def main():
     flat = flatten_solver(solver, tolerance=kw["tolerance"])
     L = flat.n_levels
     # Q_p,m = 100 + 200 m/(M-1)  
-    peaks = 100.0 + 200.0 * np.arange(a.members) / max(a.members - 1, 1)
+    total = a.members * world
+    peaks = 100.0 + 200.0 * shard_members(total, rank, world) / max(total - 1, 1)
     series = np.empty((a.members, L))
     for m, pk in enumerate(peaks):
         f = flood_wave(peak_flow=pk)
         series[m] = [f(k * flat.dt) for k in range(L)]
     setup_s = time.time() - t0
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", local)
     runner = EnsembleRunner(flat, dev)
     ser_dev = torch.from_numpy(series).to(dev)
     times = []
@@ -51,14 +65,27 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
         res = runner.solve(a.members, up_series=ser_dev, out_mode=abi.PR_OUT_UPSTREAM)
+        if world > 1:
+            stage_all = gather_members(res["depth"], total, rank, world)      # the one collective
         e1.record()
         torch.cuda.synchronize()
         if r > 0:
-            times.append(e0.elapsed_time(e1) * 1e-3)
+            t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
     secs = float(np.min(times))          # best of --repeat: the call includes host-side workspace management
-    iters = int(res["iters"].sum().item())
-    node_steps = a.members * a.nodes * (L - 1)
+    it_t = res["iters"].sum().double().reshape(1)
+    bad_t = (res["status"] != 0).sum().double().reshape(1)
+    if world > 1:
+        dist.all_reduce(it_t); dist.all_reduce(bad_t)
+    iters = int(it_t.item())
+    node_steps = total * a.nodes * (L - 1)
     node_iters = iters * a.nodes
     peaks_json = {}
     try:
@@ -67,14 +94,20 @@ def main():
         pass
     hbm = float(peaks_json.get("hbm_gbs", 6650.0))
     out = {
-        "workload": f"prismatic channel {a.nodes} nodes x {a.members} inflow scenarios x {L - 1} steps (dx=100 m, dt=600 s, theta=0.6)",
+        "workload": f"prismatic channel {a.nodes} nodes x {a.members} inflow scenarios per GPU x {L - 1} steps (dx=100 m, dt=600 s, theta=0.6)",
         "seconds": secs, "node_steps_per_s": node_steps / secs, "node_iterations_per_s": node_iters / secs,
-        "newton_iterations_per_step": iters / (a.members * (L - 1)), "failed_members": int((res["status"] != 0).sum().item()),
-        "roofline": {"bound": "hbm", "algorithmic_bytes_per_node_iteration": 48, "achieved": node_iters * 48 / secs / 1e9,
-                     "peak": hbm, "unit": "GB/s", "frac": node_iters * 48 / secs / 1e9 / hbm,
+        "newton_iterations_per_step": iters / (total * (L - 1)), "failed_members": int(bad_t.item()),
+        "n_gpus": world, "scaling": "weak", "scenarios_total": total,
+        "roofline": {"bound": "hbm", "algorithmic_bytes_per_node_iteration": 48, "achieved": node_iters * 48 / secs / 1e9 / world,
+                     "peak": hbm, "unit": "GB/s per GPU", "frac": node_iters * 48 / secs / 1e9 / hbm / world,
                      "moved_bytes_per_node_iteration_this_version": 112},
         "host_setup_s": setup_s,
     }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     if a.check:
         sys.path.insert(0, os.path.join(REPO, "oracle"))
         import copy
