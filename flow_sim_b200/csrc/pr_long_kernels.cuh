@@ -101,29 +101,39 @@ template <int MODE, bool CMP>
 __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const int lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= (long long)p.M * q.T) return;
-  const int m = (int)(w / q.T), t = (int)(w % q.T);
-  if (!q.active[m]) return;
+  // grid = (tiles, ceil(M / 4)): the four warps of a CTA work on the SAME tile of four members, so the tile's
+  // geometry lines are fetched into L1 once per CTA
+  const int t = blockIdx.x;
+  const int m = blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (m >= p.M) return;
   const int N = p.N;
-  const int conv = (MODE == LONG_UPDATE) ? q.conv[m] : 0;
   const int c0 = t * kTileCells + lane * kLongM;        // first cell / node of this lane
   int nc = (N - 1) - c0;
   nc = nc < 0 ? 0 : (nc > kLongM ? kLongM : nc);
-  const Rough rg = load_rough<0>(p.geo, 0);
   const double* xh = q.xh + (size_t)m * N;
   const double* xq = q.xq + (size_t)m * N;
   double* xh_out = q.xh_out + (size_t)m * N;
   double* xq_out = q.xq_out + (size_t)m * N;
   double* pc = q.pc + (size_t)m * 4 * N;
-
-  double h[kLongM + 1], qq[kLongM + 1];
+  // Every global load of this warp's state is issued here, before anything depends on one of them, so the warp pays
+  // the DRAM latency once instead of once per dependent group of loads.
+  const int act = q.active[m];
+  const int conv = (MODE == LONG_UPDATE) ? q.conv[m] : 0;
+  double h[kLongM + 1], qq[kLongM + 1], pcv[kLongM][4];
 #pragma unroll
   for (int j = 0; j <= kLongM; ++j) {
     const int nd = c0 + j < N ? c0 + j : N - 1;
     h[j] = xh[nd];
     qq[j] = xq[nd];
   }
+#pragma unroll
+  for (int j = 0; j < kLongM; ++j) {
+    const int c = c0 + j < N - 1 ? c0 + j : N - 2;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) pcv[j][f] = (MODE != LONG_INIT) ? pc[(size_t)f * N + c] : 0.0;
+  }
+  if (!act) return;
+  const Rough rg = load_rough<0>(p.geo, 0);
   // elimination records of the UPDATE pass live in shared memory ([record][field][lane] per warp)
   extern __shared__ double long_smem[];
   double* elw = long_smem + (size_t)(threadIdx.x >> 5) * ((kLongM - 1) * 9 * 32);
@@ -139,9 +149,7 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
     if (j < nc) {
       const int c = c0 + j;
       Cell e;
-      double cC = 0, cM = 0, cA = 0, cS = 0;
-      if (MODE != LONG_INIT) { cC = pc[c]; cM = pc[N + c]; cA = pc[2 * N + c]; cS = pc[3 * N + c]; }
-      ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, cC, cM, cA, cS, e);
+      ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, pcv[j][0], pcv[j][1], pcv[j][2], pcv[j][3], e);
       if (MODE == LONG_INIT || (MODE == LONG_UPDATE && conv)) {
         // this state is (becomes) the stored level: its level constants replace the old ones, which this lane
         // has just consumed and nobody else reads
@@ -507,8 +515,7 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
   pr_long_geometry<<<(N + 255) / 256, 256, 0, s>>>(p.geo, N, geo);
   const long long total = (long long)M * N;
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
-  const long long warps = (long long)M * T;
-  const unsigned tile_grid = (unsigned)((warps + 3) / 4);
+  const dim3 tile_grid((unsigned)T, (unsigned)((M + 3) / 4));
   const size_t tile_smem = sizeof(double) * 4 * (kLongM - 1) * 9 * 32;   // elimination records, 4 warps per CTA
   pr_long_tile<LONG_INIT, CMP><<<tile_grid, 128, tile_smem, s>>>(q);
   launches.fetch_add(3);

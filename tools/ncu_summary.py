@@ -35,8 +35,11 @@ for r in rows[2:]:
     o = m.group(2).split(".")[0]
     if o == "MUFU":
         o = m.group(2)
-    n = int(r[ix["Instructions Executed"]] or 0)
-    s = int(r[ix["# Samples"]] or 0)
+    try:
+        n = int(r[ix["Instructions Executed"]] or 0)
+        s = int(r[ix["# Samples"]] or 0)
+    except ValueError:        # a repeated header: the report holds several kernels (the totals below cover all of them)
+        continue
     op[o] += n; samp[o] += s; ti += n; ts += s
     thr[o] += int(r[ix["Thread Instructions Executed"]] or 0)
     for c in stall_cols:
