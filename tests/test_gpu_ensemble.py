@@ -290,3 +290,38 @@ def test_gate_controlled_curve_on_the_long_reach_path():
     for m in range(3):
         util.assert_parity(out["depth"][m], out["flow"][m], ref["depth"], ref["flow"], "gated, tiled path")
         assert np.array_equal(out["iters"][m], ref["iters"])
+
+
+def test_unsupported_combinations_are_refused_with_a_message_not_emulated():
+    """Every configuration the kernels do not implement comes back as PR_ERR_UNSUPPORTED / PR_ERR_ARG with a reason in
+    pr_last_error - never a silent CPU path or a wrong answer."""
+    from flow_sim_b200.abi import PreissmannLibraryError
+
+    def refused(flat, M, pattern, **kw):
+        with pytest.raises(PreissmannLibraryError, match=pattern):
+            run_flat(flat, n_members=M, **kw)
+
+    # general lumped storage together with a per-member floodplain roughness
+    flat = util.golden_inputs("storage_general")
+    flat.member_n_fp = np.array([0.05, 0.06])
+    refused(flat, 2, "floodplain roughness")
+    # gate-controlled curve: not upstream
+    flat = util.golden_inputs("gerd_gated")
+    flat.up, flat.down = copy.copy(flat.down), copy.copy(flat.up)
+    refused(flat, 1, "upstream")
+    # long-reach path: no per-member roughness, no curvature
+    flat = util.golden_inputs("gerd_calib_m0")
+    flat.member_n_main = np.array([0.02, 0.03])
+    refused(flat, 2, "per-member roughness", lanes=-1)
+    flat = util.golden_inputs("gerd_full")
+    refused(flat, 1, "curvature", lanes=-1)
+    # malformed inputs
+    flat = util.golden_inputs("example")
+    flat.down.storage_area = 0.0
+    refused(flat, 1, "surface area")
+    flat = util.golden_inputs("gerd_calib_m0")
+    flat.down.rating = dict(flat.down.rating, buffer=0.0)
+    refused(flat, 1, "buffer")
+    flat = util.golden_inputs("gerd_calib_m0")
+    flat.down.member_ratings = [flat.down.rating, dict(flat.down.rating, n_gates=99)]
+    refused(flat, 2, "n_gates")
