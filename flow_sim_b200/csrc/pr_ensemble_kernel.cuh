@@ -157,7 +157,9 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   // EXACT: (N-1) % M == 0, i.e. every lane owns either M cells or none.  Lanes without cells then run the
   // cell pass on padding (finite copies of the last node, zeroed scratch) instead of branching around it,
   // which leaves the node/cell/merge loop as straight-line code.
-  static_assert(G == 32, "the level-constant refresh assumes one member per warp");
+  static_assert(G == 8 || G == 16 || G == 32, "a member occupies 8, 16 or 32 lanes");
+  // G < 32: 32/G members share a warp and run in lockstep; each keeps its own level / iteration / status, and
+  // everything that is decided per member (convergence, failure, the level-constant refresh) is per lane group.
 
   // ---- state: initial conditions (Solver.initialize_t0, solver.py:61-63) ----
   double h[M], q[M];
@@ -235,6 +237,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   // Node pass at the current state that only (re)builds the level constants: once for the initial state and once
   // per accepted level.  Cheaper than producing candidates in every Newton iteration (one extra node pass per
   // level against 4 stores + 9 flops per cell per iteration), and it halves the constants' shared memory.
+  bool commit = true;      // G < 32: which lanes take the refreshed constants
   auto refresh_level_constants = [&]() {
     NodeVals left, right;
     node_eval<CURV, RM>(sg, NP, gl, h[0], q[0], rg, k, left);
@@ -252,7 +255,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       }
       double nC, nM, nA, nS;
       level_constants(left, right, k, nC, nM, nA, nS);
-      PC(0, j) = nC; PC(1, j) = nM; PC(2, j) = nA; PC(3, j) = nS;
+      if (G == 32 || commit) { PC(0, j) = nC; PC(1, j) = nM; PC(2, j) = nA; PC(3, j) = nS; }
       left = right;
     }
     __syncwarp();
@@ -427,7 +430,9 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
     // ------------------------------ accept / update (preissmann.py:146-156) ------------------------------
     // a boundary evaluation the reference would abort on (brentq without a sign change) fails the member at once
-    const bool bc_failed = __any_sync(kFull, (is_first && U.fail) || (owns_last && D.fail));
+    bool bc_failed;
+    if (G == 32) bc_failed = __any_sync(kFull, (is_first && U.fail) || (owns_last && D.fail));
+    else bc_failed = (__ballot_sync(kFull, (is_first && U.fail) || (owns_last && D.fail)) & ((((1u << (G & 31)) - 1u) << (lane - gl)))) != 0u;
     const bool converged = !bc_failed && err < p.tol;
     if (active) {
       if (converged) {
@@ -448,7 +453,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       }
     }
     // the accepted iterate becomes the stored level: rebuild its constants before the update is applied
-    // (warp-uniform: one member per warp)
+    // (every lane runs the pass as soon as one member of the warp needs it; only that member's lanes commit)
+    if (G < 32) commit = active && converged;
     if (__any_sync(kFull, active && converged)) refresh_level_constants();
     if (active) {
 #pragma unroll
@@ -484,52 +490,53 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   }
 }
 
-// Launch of one nodes-per-lane family (all CURV x RM variants); defined in pr_ensemble_m<M>.cu so that the
-// instantiations compile in parallel.  Returns a cudaError_t as int.
-template <int M, int W>
+// Launch of one (lanes per member, nodes per lane) family (all CURV x RM variants); defined in pr_ensemble_*.cu so
+// that the instantiations compile in parallel.  Returns a cudaError_t as int.
+template <int G, int M, int W>
 int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
 
-#define PR_DEFINE_ENSEMBLE_FAMILY(M_, W_)                                                                    \
+#define PR_DEFINE_ENSEMBLE_FAMILY(G_, M_, W_)                                                                \
   namespace pr {                                                                                             \
   template <bool CURV, int RM, bool EXACT, bool GST>                                                         \
-  static int launch_y_##M_(const DevParams& p, cudaStream_t s) {                                             \
-    constexpr size_t smem = ensemble_smem_bytes<32, M_, W_>();                                               \
+  static int launch_y_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                      \
+    constexpr size_t smem = ensemble_smem_bytes<G_, M_, W_>();                                               \
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");                                      \
-    auto kern = pr_ensemble_kernel<32, M_, W_, CURV, RM, EXACT, GST>;                                        \
+    auto kern = pr_ensemble_kernel<G_, M_, W_, CURV, RM, EXACT, GST>;                                        \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                     \
-    const unsigned grid = (unsigned)((p.M + W_ - 1) / W_);                                                   \
+    constexpr int per_cta = W_ * (32 / G_);                                                                  \
+    const unsigned grid = (unsigned)((p.M + per_cta - 1) / per_cta);                                         \
     kern<<<grid, W_ * 32, smem, s>>>(p);                                                                     \
     return (int)cudaGetLastError();                                                                          \
   }                                                                                                          \
   template <bool CURV, int RM, bool EXACT>                                                                   \
-  static int launch_x_##M_(const DevParams& p, cudaStream_t s) {                                             \
+  static int launch_x_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                      \
     /* general lumped storage (Brent solve / losses) and gate-controlled rating curves: built without the  */ \
     /* floodplain-roughness override and the straight-line variant (-4 = unsupported)                      */ \
     const bool gst = (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && (p.dn.st_general || p.dn.st_losses)) ||      \
                      (p.dn.type == PR_BC_RATING_CURVE && p.dn.gated);                                        \
-    if (!gst) return launch_y_##M_<CURV, RM, EXACT, false>(p, s);                                            \
+    if (!gst) return launch_y_##G_##_##M_<CURV, RM, EXACT, false>(p, s);                                     \
     if (RM > 1) return -4;                                                                                   \
-    return launch_y_##M_<CURV, (RM & 1), false, true>(p, s);                                                 \
+    return launch_y_##G_##_##M_<CURV, (RM & 1), false, true>(p, s);                                          \
   }                                                                                                          \
   template <bool CURV, int RM>                                                                               \
-  static int launch_one_##M_(const DevParams& p, cudaStream_t s) {                                           \
+  static int launch_one_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                    \
     /* the straight-line variant is built for the curvature-free kernels (the ensemble workloads) */         \
-    if (!CURV && (p.N - 1) % M_ == 0) return launch_x_##M_<CURV, RM, !CURV>(p, s);                            \
-    return launch_x_##M_<CURV, RM, false>(p, s);                                                             \
+    if (!CURV && (p.N - 1) % M_ == 0) return launch_x_##G_##_##M_<CURV, RM, !CURV>(p, s);                     \
+    return launch_x_##G_##_##M_<CURV, RM, false>(p, s);                                                      \
   }                                                                                                          \
   template <bool CURV>                                                                                       \
-  static int launch_rm_##M_(const DevParams& p, cudaStream_t s) {                                            \
+  static int launch_rm_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                     \
     switch (rough_mode(p.geo)) {                                                                             \
-      case 0: return launch_one_##M_<CURV, 0>(p, s);                                                         \
-      case 1: return launch_one_##M_<CURV, 1>(p, s);                                                         \
-      case 2: return launch_one_##M_<CURV, 2>(p, s);                                                         \
-      default: return launch_one_##M_<CURV, 3>(p, s);                                                        \
+      case 0: return launch_one_##G_##_##M_<CURV, 0>(p, s);                                                  \
+      case 1: return launch_one_##G_##_##M_<CURV, 1>(p, s);                                                  \
+      case 2: return launch_one_##G_##_##M_<CURV, 2>(p, s);                                                  \
+      default: return launch_one_##G_##_##M_<CURV, 3>(p, s);                                                 \
     }                                                                                                        \
   }                                                                                                          \
   template <>                                                                                                \
-  int launch_ensemble_family<M_, W_>(const DevParams& p, bool curv, cudaStream_t s) {                        \
-    return curv ? launch_rm_##M_<true>(p, s) : launch_rm_##M_<false>(p, s);                                  \
+  int launch_ensemble_family<G_, M_, W_>(const DevParams& p, bool curv, cudaStream_t s) {                    \
+    return curv ? launch_rm_##G_##_##M_<true>(p, s) : launch_rm_##G_##_##M_<false>(p, s);                    \
   }                                                                                                          \
   }
 

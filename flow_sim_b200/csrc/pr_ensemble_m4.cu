@@ -4,4 +4,4 @@
 #ifndef PR_W4
 #define PR_W4 16
 #endif
-PR_DEFINE_ENSEMBLE_FAMILY(4, PR_W4)
+PR_DEFINE_ENSEMBLE_FAMILY(32, 4, PR_W4)

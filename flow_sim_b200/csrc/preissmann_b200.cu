@@ -373,17 +373,26 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   p.final_error = st.out(out->final_error, M * (L > 1 ? L - 1 : 1));
   if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
 
-  // nodes per lane: smallest M with ceil((N-1)/M) + 1 <= 32 chain rows
-  const int need = (int)((N - 1 + 30) / 31);      // ceil((N-1)/31)
+  // Lanes per member G and nodes per lane M: the chain has ceil(cells / M) + 1 <= G block rows.  Short reaches pack
+  // 4 or 2 members into a warp (G = 8, 16) so that neither lanes nor parallel-cyclic-reduction steps are wasted.
+  const int cells = (int)N - 1;
+  const int lpm = cfg->lanes_per_member;
+  if (lpm != 0 && lpm != -1 && lpm != 8 && lpm != 16 && lpm != 32)
+    return fail(PR_ERR_ARG, "lanes_per_member=%d: must be 0 (auto), 8, 16, 32 or -1 (long-reach path)", lpm);
+  auto fits = [&](int G, int M) { return (lpm == 0 || lpm == G) && cells <= (G - 1) * M; };
   int rc;
-  if (cfg->lanes_per_member != 0 && cfg->lanes_per_member != 32 && cfg->lanes_per_member != -1)
-    return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: this build has the 32-lane instantiations", cfg->lanes_per_member);
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
-  if (cfg->lanes_per_member == -1) rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);   // forced long-reach path
-  else if (need <= 1) rc = launch_family(pr::launch_ensemble_family<1, 16>(p, has_curv, s));
-  else if (need <= 2) rc = launch_family(pr::launch_ensemble_family<2, 16>(p, has_curv, s));
-  else if (need <= 4) rc = launch_family(pr::launch_ensemble_family<4, PR_W4>(p, has_curv, s));
-  else if (need <= 8) rc = launch_family(pr::launch_ensemble_family<8, 7>(p, has_curv, s));
+  if (lpm == -1) rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);   // forced long-reach path
+  else if (fits(8, 1)) rc = launch_family(pr::launch_ensemble_family<8, 1, 16>(p, has_curv, s));
+  else if (fits(8, 2)) rc = launch_family(pr::launch_ensemble_family<8, 2, 16>(p, has_curv, s));
+  else if (fits(8, 4)) rc = launch_family(pr::launch_ensemble_family<8, 4, 16>(p, has_curv, s));
+  else if (fits(16, 2)) rc = launch_family(pr::launch_ensemble_family<16, 2, 16>(p, has_curv, s));
+  else if (fits(32, 1)) rc = launch_family(pr::launch_ensemble_family<32, 1, 16>(p, has_curv, s));
+  else if (fits(16, 4)) rc = launch_family(pr::launch_ensemble_family<16, 4, 16>(p, has_curv, s));
+  else if (fits(32, 2)) rc = launch_family(pr::launch_ensemble_family<32, 2, 16>(p, has_curv, s));
+  else if (fits(32, 4)) rc = launch_family(pr::launch_ensemble_family<32, 4, PR_W4>(p, has_curv, s));
+  else if (fits(32, 8)) rc = launch_family(pr::launch_ensemble_family<32, 8, 7>(p, has_curv, s));
+  else if (lpm != 0) return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: no instantiation holds %d nodes", lpm, (int)N);
   else rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);
   if (rc) return rc;
   cudaError_t e = st.finish();

@@ -325,3 +325,68 @@ def test_unsupported_combinations_are_refused_with_a_message_not_emulated():
     flat = util.golden_inputs("gerd_calib_m0")
     flat.down.member_ratings = [flat.down.rating, dict(flat.down.rating, n_gates=99)]
     refused(flat, 2, "n_gates")
+
+
+# ---- short reaches: 2 or 4 members per warp (8 / 16 lanes per member) --------------------------------------------
+
+@pytest.mark.parametrize("n_nodes,lanes", [(2, 0), (8, 0), (9, 0), (15, 0), (16, 0), (21, 0), (29, 0), (30, 0), (31, 0),
+                                           (32, 0), (45, 0), (61, 0), (62, 0), (21, 16), (21, 32), (8, 16), (61, 32)])
+def test_packed_warp_families_vs_oracle(n_nodes, lanes):
+    """Members that share a warp run in lockstep but converge on their own: 11 members with different roughness and
+    inflow (so different iteration counts and convergence moments inside one warp), every size class of the
+    8- and 16-lane kernels, and the same sizes forced onto wider groups."""
+    import oracle_py
+
+    M = 11                                                    # not a multiple of the members per warp
+    flat = _prismatic(kind="compound", n_nodes=n_nodes, levels=5)
+    flat.member_n_main = 0.022 + 0.004 * np.arange(M)
+    base = np.array(flat.up.series)
+    flat.up.series = np.stack([base[0] + (base - base[0]) * (0.3 + 0.25 * m) for m in range(M)])
+    ora = oracle_py.run(flat, n_members=M)
+    out = run_flat(flat, n_members=M, lanes=lanes)
+    assert np.array_equal(out["status"], ora["status"]) and not out["status"].any()
+    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], f"N={n_nodes} lanes={lanes}")
+    assert np.array_equal(out["iters"], ora["iters"])
+    assert len({tuple(r) for r in out["iters"]}) > 1 or n_nodes <= 3     # the members really differ
+
+
+def test_packed_warp_one_member_failing_leaves_its_warp_mates_alone():
+    """max_iter cut short for everybody, but only the members with the big flood need that many iterations: the
+    failing members of a warp stop (NaN-filled), the others finish, exactly as the oracle says."""
+    import oracle_py
+
+    M = 8
+    flat = _prismatic(kind="compound", n_nodes=21, levels=6)
+    base = np.array(flat.up.series)
+    flat.up.series = np.stack([base[0] + (base - base[0]) * (0.05 if m % 2 else 3.0) for m in range(M)])
+    flat.max_iter = 24
+    ora = oracle_py.run(flat, n_members=M)
+    assert 0 < (ora["status"] != 0).sum() < M                 # a mix of failing and surviving members in each warp
+    out = run_flat(flat, n_members=M)
+    assert np.array_equal(out["status"], ora["status"]) and np.array_equal(out["fail_level"], ora["fail_level"])
+    assert np.array_equal(np.isnan(out["depth"]), np.isnan(ora["depth"]))
+    fin = ~np.isnan(ora["depth"])
+    util.assert_parity(out["depth"][fin], out["flow"][fin], ora["depth"][fin], ora["flow"][fin], "mixed failure")
+    assert np.array_equal(out["iters"], ora["iters"])
+
+
+@pytest.mark.parametrize("case", ["example", "akbari", "storage_general"])
+def test_shipped_short_cases_as_packed_ensembles(case):
+    """Configs 1 and 2 (N = 21 / 30: lumped storage, normal depth) as 9-member inflow ensembles on the packed
+    kernels, member 0 being the reference's own run."""
+    import oracle_py
+
+    flat = util.golden_inputs(case)
+    ref = util.golden_outputs(case)
+    M = 9
+    base = np.array(flat.up.series)
+    flat.up.series = np.stack([base[0] + (base - base[0]) * (1.0 + 0.1 * m) for m in range(M)])
+    ora = oracle_py.run(flat, n_members=M)
+    out = run_flat(flat, n_members=M)
+    assert np.array_equal(out["status"], ora["status"])
+    fin = ~np.isnan(ora["depth"])
+    util.assert_parity(out["depth"][fin], out["flow"][fin], ora["depth"][fin], ora["flow"][fin], case)
+    assert np.array_equal(out["iters"], ora["iters"])
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], f"{case} member 0 vs reference")
+    if "storage_stage" in ref.files:
+        assert util.max_rel(out["storage_stage"][0], ref["storage_stage"]) <= util.RTOL
