@@ -390,3 +390,29 @@ def test_shipped_short_cases_as_packed_ensembles(case):
     util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], f"{case} member 0 vs reference")
     if "storage_stage" in ref.files:
         assert util.max_rel(out["storage_stage"][0], ref["storage_stage"]) <= util.RTOL
+
+
+def test_solver_run_ensemble_entry_point():
+    """PreissmannSolver.run_ensemble (the additive API of SURVEY.md 8b) on the mirror objects: roughness members of the
+    gerd calibration case must equal single runs of the reference (goldens), release scenarios its gerd_release run."""
+    from flow_sim_b200.cases import build_gerd
+    from flow_sim_b200.cases import gerd_roseires as gr
+
+    solver, kw = build_gerd(n_main=0.03, calibration=True)
+    ms = [0, 36408, 65535]
+    res = solver.run_ensemble({"n_main": [util.calib_n(m) for m in ms]}, tolerance=kw["tolerance"], full_output=True,
+                              q_query=Q_QUERY, h_target=H_TARGET)
+    for i, m in enumerate(ms):
+        ref = util.golden_outputs(f"gerd_calib_m{m}")
+        util.assert_parity(res["depth"][i], res["flow"][i], ref["depth"], ref["flow"], f"run_ensemble member {m}")
+        assert np.array_equal(res["iterations"][i], ref["iters"])
+        assert abs(res["rmse"][i] - float(ref["calib_rmse"])) <= util.RTOL * float(ref["calib_rmse"])
+    q0 = float(solver.channel.initial_flow_rate)
+    curves = [gr.RoseiresRatingCurve(initial_stage=486.2, initial_flow=q0, jammed_spillways=2, jammed_sluice_gates=1, buffer=0.3),
+              gr.RoseiresRatingCurve(initial_stage=487.0, initial_flow=q0)]
+    res = solver.run_ensemble({"rating_curves": curves, "n_main": [0.03, 0.03]}, tolerance=kw["tolerance"], full_output=True)
+    ref = util.golden_outputs("gerd_release")
+    util.assert_parity(res["depth"][0], res["flow"][0], ref["depth"], ref["flow"], "run_ensemble release scenario")
+    assert np.array_equal(res["iterations"][0], ref["iters"]) and not res["status"].any()
+    with pytest.raises(ValueError, match="unknown member overrides"):
+        solver.run_ensemble({"n_bank": [0.1]})
