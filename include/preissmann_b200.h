@@ -77,8 +77,9 @@ typedef struct pr_config {
   int32_t out_mode;     /* enum pr_out_mode */
   int32_t mem;          /* enum pr_mem: where EVERY array of this call lives */
   int32_t device;       /* CUDA device ordinal, -1 = current device */
-  int32_t lanes_per_member; /* 0 = auto (fused warp-per-member kernel up to 249 nodes, tiled long-reach path
-                               above); 32 = same; -1 = force the long-reach path (testing / comparison) */
+  int32_t lanes_per_member; /* 0 = auto: fused kernel with 8 / 16 / 32 lanes per member (4 / 2 / 1 members per warp)
+                               for reaches of up to 29 / 61 / 249 nodes, tiled long-reach path above;
+                               8, 16, 32 = force that group width; -1 = force the long-reach path (testing) */
   int32_t reserved0;
   double theta;         /* Preissmann weighting factor */
   double dt;            /* time_step [s] */
