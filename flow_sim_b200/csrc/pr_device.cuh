@@ -154,18 +154,27 @@ __device__ inline void stage_geometry(const DevGeom& g, int N, int NP, double* s
 }
 
 // Roughness mode (template parameter RM of the kernels): bit 0 = per-member n_main override,
-// bit 1 = per-member n_fp override (model.run(n_main=, n_fp=)); 0 = the node's own values.
+// bit 1 = per-member n_fp override (model.run(n_main=, n_fp=)); 0 = the node's own values;
+// 4 = decided at run time from the two flags below (the long-reach kernels, which are not built per mode).
 struct Rough {
   double nm, inm, cnm, cnfp;    // n_main, 1/n_main, n_main^-1.5, n_fp^-1.5
+  bool om, ofp;                 // RM = 4: which overrides are present
 };
+
+template <int RM>
+__device__ __forceinline__ bool rough_main(const Rough& r) { return RM == 4 ? r.om : (RM & 1) != 0; }
+template <int RM>
+__device__ __forceinline__ bool rough_fp(const Rough& r) { return RM == 4 ? r.ofp : (RM & 2) != 0; }
 
 template <int RM>
 __device__ __forceinline__ Rough load_rough(const DevGeom& g, long long member) {
   Rough rg;
-  rg.nm = (RM & 1) ? g.member_nm[member] : 1.0;
+  rg.om = RM == 4 ? g.member_nm != nullptr : (RM & 1) != 0;
+  rg.ofp = RM == 4 ? g.member_nfp != nullptr : (RM & 2) != 0;
+  rg.nm = rg.om ? g.member_nm[member] : 1.0;
   rg.inm = 1.0 / rg.nm;
   rg.cnm = inv_n15(rg.nm);
-  rg.cnfp = (RM & 2) ? inv_n15(g.member_nfp[member]) : 1.0;
+  rg.cnfp = rg.ofp ? inv_n15(g.member_nfp[member]) : 1.0;
   return rg;
 }
 
@@ -236,9 +245,9 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       const double To = GEO(F_WB) + 2.0 * mfp * dfp;
       // K_j^1.5 = A_j*sqrt(A_j) * (A_j/P_j) * n_j^-1.5   (cross_section.py:681-754, hydraulics.py:15-26)
       const double Am = Amf + GEO(F_TB) * dfp;               // conveyance area includes the column (:694)
-      const double cnm = (RM & 1) ? rg.cnm : GEO(F_CNM);
-      const double cnl = (RM & 2) ? rg.cnfp : GEO(F_CNL);
-      const double cnr = (RM & 2) ? rg.cnfp : GEO(F_CNR);
+      const double cnm = rough_main<RM>(rg) ? rg.cnm : GEO(F_CNM);
+      const double cnl = rough_fp<RM>(rg) ? rg.cnfp : GEO(F_CNL);
+      const double cnr = rough_fp<RM>(rg) ? rg.cnfp : GEO(F_CNR);
       const double w = fast_rcp(Pl * Pr);
       double Xo = (Am * Am) * fast_sqrt(Am) * (GEO(F_INVPM) * cnm);
       Xo = fma((Al * Al) * fast_sqrt(Al), (Pr * w) * cnl, Xo);
@@ -255,7 +264,7 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
   const double PT = P * T;
   const double u = fast_rcp(A * PT);
   const double invA = u * PT, invTP = u * A;
-  const double nm = (RM & 1) ? rg.nm : GEO(F_NM);
+  const double nm = rough_main<RM>(rg) ? rg.nm : GEO(F_NM);
   if (!over) X = A * (invTP * T);                          // R = A/P
   const double r = fast_rcbrt(X);
   const double r2 = r * r, r4 = r2 * r2;
@@ -274,7 +283,7 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
   double dSeQ = 2.0 * absQ * invK2;                         // hydraulics.py:77-92
   double K = 0.0;
   if (WANT_K || CURV) {
-    const double inm = (RM & 1) ? rg.inm : GEO(F_INVNM);
+    const double inm = rough_main<RM>(rg) ? rg.inm : GEO(F_INVNM);
     K = over ? X * r : A * (X * r) * inm;
   }
   if (CURV) {

@@ -133,19 +133,19 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
     for (int f = 0; f < 4; ++f) pcv[j][f] = (MODE != LONG_INIT) ? pc[(size_t)f * N + c] : 0.0;
   }
   if (!act) return;
-  const Rough rg = load_rough<0>(p.geo, 0);
+  const Rough rg = load_rough<4>(p.geo, m);
   // elimination records of the UPDATE pass live in shared memory ([record][field][lane] per warp)
   extern __shared__ double long_smem[];
   double* elw = long_smem + (size_t)(threadIdx.x >> 5) * ((kLongM - 1) * 9 * 32);
 #define LEL(j, c) elw[((j)*9 + (c)) * 32 + lane]
   NodeVals nv[2];
-  node_eval<false, 0, false, DevParams, CMP>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
+  node_eval<false, 4, false, DevParams, CMP>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
   double ss = 0.0;
   Cell S;
 #pragma unroll
   for (int j = 0; j < kLongM; ++j) {
     const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
-    node_eval<false, 0, false, DevParams, CMP>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
+    node_eval<false, 4, false, DevParams, CMP>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
     if (j < nc) {
       const int c = c0 + j;
       Cell e;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   const int it = q.it[m] + 1;
   const double* xh = q.xh + (size_t)m * N;
   const double* xq = q.xq + (size_t)m * N;
-  const Rough rg = load_rough<0>(p.geo, 0);
+  const Rough rg = load_rough<4>(p.geo, m);
 #define REC(j, c) rec[((j)*10 + (c)) * 32 + lane]
   // ---- per-lane serial condensation of Kc tile cells ----
   const int t0 = lane * Kc;
@@ -303,12 +303,12 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   const double hyd_dn = p.dn.series ? p.dn.series[(size_t)m * p.dn.series_stride + level] : 0.0;
   if (lane == 0) {
     NodeVals nvb; NodeConv kc;
-    node_eval<false, 0, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
+    node_eval<false, 4, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
     U = bc_eval<false>(p.up, m, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, p.g, kc, nvb.T);
   }
   if (lane == Lc) {
     NodeVals nvb; NodeConv kc;
-    node_eval<false, 0, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
+    node_eval<false, 4, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
     D = bc_eval<true>(p.dn, m, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T, &q.gate[m]);
   }
   const double Ures = __shfl_sync(kFull, U.res, 0), Dres = __shfl_sync(kFull, D.res, Lc);
@@ -471,8 +471,6 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
                             std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
   if (has_curv) return fail(PR_ERR_UNSUPPORTED, "long-reach path: centre-line curvature is not supported");
-  if (p.geo.member_nm || p.geo.member_nfp)
-    return fail(PR_ERR_UNSUPPORTED, "long-reach path: per-member roughness overrides are not supported");
   if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses)
     return fail(PR_ERR_UNSUPPORTED, "long-reach path: lumped-storage head losses are not supported");
   const int N = p.N, M = p.M;

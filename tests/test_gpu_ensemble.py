@@ -309,10 +309,7 @@ def test_unsupported_combinations_are_refused_with_a_message_not_emulated():
     flat = util.golden_inputs("gerd_gated")
     flat.up, flat.down = copy.copy(flat.down), copy.copy(flat.up)
     refused(flat, 1, "upstream")
-    # long-reach path: no per-member roughness, no curvature
-    flat = util.golden_inputs("gerd_calib_m0")
-    flat.member_n_main = np.array([0.02, 0.03])
-    refused(flat, 2, "per-member roughness", lanes=-1)
+    # long-reach path: no curvature
     flat = util.golden_inputs("gerd_full")
     refused(flat, 1, "curvature", lanes=-1)
     # malformed inputs

@@ -21,7 +21,7 @@ def _case(seed):
     up = str(rng.choice(["flow_hydrograph", "flow_hydrograph", "stage_hydrograph"]))
     flat = _prismatic(kind=kind, down=down, up=up, n_nodes=n_nodes, levels=int(rng.integers(2, 6)))
     M = int(rng.integers(1, 14))
-    if n_nodes < 250 and rng.random() < 0.7:                       # the tiled path takes no per-member roughness
+    if rng.random() < 0.7:
         flat.member_n_main = rng.uniform(0.02, 0.045, M)
         if kind == "compound" and rng.random() < 0.5:
             flat.member_n_fp = rng.uniform(0.04, 0.08, M)
@@ -36,7 +36,6 @@ def _case(seed):
         lanes = int(rng.choice([16, 32]))
     elif n_nodes < 250 and rng.random() < 0.2:
         lanes = -1
-        flat.member_n_main = flat.member_n_fp = None
     return flat, M, lanes, f"seed {seed}: N={n_nodes} {kind} {up}->{down} M={M} lanes={lanes}"
 
 

@@ -111,3 +111,24 @@ def test_config5_size_two_steps():
     ora = oracle_py.run(one, n_members=1)
     util.assert_parity(out["depth"][1], out["flow"][1], ora["depth"][0], ora["flow"][0], "config 5")
     assert np.array_equal(out["iters"][1], ora["iters"][0])
+
+
+def test_roughness_members_on_the_tiled_path():
+    """Per-member n_main / n_fp on the long-reach kernels: the config-4 members forced onto the tiled path equal the
+    reference goldens, and a 600-node compound reach with both overrides equals the oracle."""
+    from test_gpu_ensemble import _prismatic
+
+    flat = util.golden_inputs("gerd_calib_m0")
+    ms = [0, 36408, 65535]
+    flat.member_n_main = np.array([util.calib_n(m) for m in ms])
+    flat.ic_depth = np.stack([util.golden_inputs(f"gerd_calib_m{m}").ic_depth for m in ms])
+    flat.ic_flow = np.stack([util.golden_inputs(f"gerd_calib_m{m}").ic_flow for m in ms])
+    out = run_flat(flat, n_members=3, lanes=-1)
+    for i, m in enumerate(ms):
+        ref = util.golden_outputs(f"gerd_calib_m{m}")
+        util.assert_parity(out["depth"][i], out["flow"][i], ref["depth"], ref["flow"], f"tiled path, member {m}")
+        assert np.array_equal(out["iters"][i], ref["iters"])
+    flat = _prismatic(kind="compound", n_nodes=600, levels=3)
+    flat.member_n_main = np.array([0.025, 0.03, 0.035, 0.04, 0.045])
+    flat.member_n_fp = np.array([0.05, 0.06, 0.07, 0.08, 0.09])
+    _vs_oracle(flat, 5, "N=600 with per-member n_main and n_fp")
