@@ -18,6 +18,7 @@ struct GvfParams {
   long long q0_stride;
   double *ic_h, *ic_q;
   int* status;
+  const double* table;         // [F_COUNT][N] derived geometry in global memory for reaches too long to stage, else NULL
 };
 
 // dh/dx of the gradually-varied-flow equation at one node (get_dh_dx, channel.py:316-347)
@@ -38,10 +39,13 @@ __device__ __forceinline__ double gvf_slope(const double* sg, int NP, int node, 
 
 template <bool CURV, int RM>
 __global__ void __launch_bounds__(128) pr_gvf_kernel(const __grid_constant__ GvfParams p) {
-  extern __shared__ double smem[];
+  extern __shared__ double gvf_smem[];
   const int NP = p.N;
-  stage_geometry(p.geo, p.N, NP, smem, threadIdx.x, blockDim.x, [](int idx) { return idx; });
-  __syncthreads();
+  const double* smem = p.table ? p.table : gvf_smem;
+  if (!p.table) {
+    stage_geometry(p.geo, p.N, NP, gvf_smem, threadIdx.x, blockDim.x, [](int idx) { return idx; });
+    __syncthreads();
+  }
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= p.M) return;
   const Rough rg = load_rough<RM>(p.geo, m);

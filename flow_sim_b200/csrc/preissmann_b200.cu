@@ -426,9 +426,17 @@ int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const d
   p.status = st.out(status, M);
   if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
   const size_t smem = sizeof(double) * pr::F_COUNT * N;
-  if (smem > 200 * 1024) return fail(PR_ERR_UNSUPPORTED, "GVF initial conditions: n_nodes=%zu exceeds the shared-memory geometry stage", N);
+  if (smem > 200 * 1024) {          // a reach too long to stage per CTA: derived geometry table in global memory
+    double* table = nullptr;
+    CUDA_TRY(cudaMalloc(&table, smem));
+    st.allocs.push_back(table);
+    pr::pr_long_geometry<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(p.geo, (int)N, table);
+    g_launches.fetch_add(1);
+    p.table = table;
+  }
   const unsigned grid = (unsigned)((M + 127) / 128);
-  if (int rc = has_curv ? launch_gvf_rm<true>(p, grid, smem, s) : launch_gvf_rm<false>(p, grid, smem, s)) return rc;
+  const size_t gvf_smem = p.table ? 0 : smem;
+  if (int rc = has_curv ? launch_gvf_rm<true>(p, grid, gvf_smem, s) : launch_gvf_rm<false>(p, grid, gvf_smem, s)) return rc;
   cudaError_t e = st.finish();
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_gvf_initial_conditions: %s", cudaGetErrorString(e));
   return PR_OK;

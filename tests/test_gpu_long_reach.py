@@ -132,3 +132,21 @@ def test_roughness_members_on_the_tiled_path():
     flat.member_n_main = np.array([0.025, 0.03, 0.035, 0.04, 0.045])
     flat.member_n_fp = np.array([0.05, 0.06, 0.07, 0.08, 0.09])
     _vs_oracle(flat, 5, "N=600 with per-member n_main and n_fp")
+
+
+def test_gvf_profile_on_a_reach_too_long_for_the_shared_memory_stage():
+    """N = 3000 (> 1219 nodes): the GVF kernel reads the derived geometry from a global table; per-member roughness,
+    flow and downstream depth; against the oracle's restatement of Channel._gvh_conditions."""
+    import oracle_py
+    from flow_sim_b200.runner import gvf_initial_conditions
+    from test_gpu_ensemble import _prismatic
+
+    flat = _prismatic(kind="compound", n_nodes=3000, levels=2)
+    M = 5
+    flat.member_n_main = np.array([0.025, 0.03, 0.035, 0.04, 0.045])
+    q0 = np.array([40.0, 60.0, 80.0, 100.0, 120.0])
+    hd = np.array([1.5, 2.0, 2.5, 3.0, 3.5])
+    h, q, st = gvf_initial_conditions(flat, M, q0, hd)
+    ho, qo, sto = oracle_py.gvf(flat, q0, hd, n_members=M)
+    assert np.array_equal(st, sto)
+    assert util.max_rel(h, ho) <= 1e-12 and np.array_equal(q, qo)
