@@ -97,7 +97,7 @@ __device__ __forceinline__ Cell shfl_cell(const Cell& c, int src) {
   return o;
 }
 
-template <int MODE, bool CMP>
+template <int MODE, bool CMP, bool CURV>
 __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const int lane = threadIdx.x & 31;
@@ -139,13 +139,13 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
   double* elw = long_smem + (size_t)(threadIdx.x >> 5) * ((kLongM - 1) * 9 * 32);
 #define LEL(j, c) elw[((j)*9 + (c)) * 32 + lane]
   NodeVals nv[2];
-  node_eval<false, 4, false, DevParams, CMP>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
+  node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
   double ss = 0.0;
   Cell S;
 #pragma unroll
   for (int j = 0; j < kLongM; ++j) {
     const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
-    node_eval<false, 4, false, DevParams, CMP>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
+    node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
     if (j < nc) {
       const int c = c0 + j;
       Cell e;
@@ -466,11 +466,10 @@ struct LongWorkspace {
 };
 inline LongWorkspace& long_workspace() { static LongWorkspace w; return w; }
 
-template <bool CMP>
-inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, std::atomic<long long>& launches,
+template <bool CMP, bool CURV>
+inline int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches,
                             std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
-  if (has_curv) return fail(PR_ERR_UNSUPPORTED, "long-reach path: centre-line curvature is not supported");
   if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses)
     return fail(PR_ERR_UNSUPPORTED, "long-reach path: lumped-storage head losses are not supported");
   const int N = p.N, M = p.M;
@@ -515,16 +514,16 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
   const dim3 tile_grid((unsigned)T, (unsigned)((M + 3) / 4));
   const size_t tile_smem = sizeof(double) * 4 * (kLongM - 1) * 9 * 32;   // elimination records, 4 warps per CTA
-  pr_long_tile<LONG_INIT, CMP><<<tile_grid, 128, tile_smem, s>>>(q);
+  pr_long_tile<LONG_INIT, CMP, CURV><<<tile_grid, 128, tile_smem, s>>>(q);
   launches.fetch_add(3);
   const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
   e = cudaFuncSetAttribute(pr_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
   int done = (p.L > 1) ? 0 : M;
   const long long max_trips = (long long)(p.L - 1) * (p.max_iter > 0 ? p.max_iter : 1) + 1;
   for (long long trip = 0; trip < max_trips && done < M && e == cudaSuccess; ++trip) {
-    pr_long_tile<LONG_CONDENSE, CMP><<<tile_grid, 128, tile_smem, s>>>(q);
+    pr_long_tile<LONG_CONDENSE, CMP, CURV><<<tile_grid, 128, tile_smem, s>>>(q);
     pr_long_chain<<<M, 32, chain_smem, s>>>(q);
-    pr_long_tile<LONG_UPDATE, CMP><<<tile_grid, 128, tile_smem, s>>>(q);
+    pr_long_tile<LONG_UPDATE, CMP, CURV><<<tile_grid, 128, tile_smem, s>>>(q);
     pr_long_retire<<<(M + 127) / 128, 128, 0, s>>>(q);
     launches.fetch_add(4);
     std::swap(q.xh, q.xh_out);
@@ -549,8 +548,11 @@ inline int long_reach_run_t(const DevParams& p, bool has_curv, cudaStream_t s, s
 
 inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, cudaStream_t s,
                           std::atomic<long long>& launches, std::string& err) {
-  return has_compound ? long_reach_run_t<true>(p, has_curv, s, launches, err)
-                      : long_reach_run_t<false>(p, has_curv, s, launches, err);
+  // centre-line curvature: compiled with the compound-section node pass only (a curved reach with floodplains is the
+  // shipped gerd case; a curved prismatic reach takes the same kernels, the floodplain terms select to nothing)
+  if (has_curv) return long_reach_run_t<true, true>(p, s, launches, err);
+  return has_compound ? long_reach_run_t<true, false>(p, s, launches, err)
+                      : long_reach_run_t<false, false>(p, s, launches, err);
 }
 
 }  // namespace pr

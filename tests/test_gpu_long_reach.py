@@ -33,10 +33,11 @@ def test_akbari_long_clone_matches_reference_golden():
     assert np.array_equal(out["iters"][0], ref["iters"])
 
 
-@pytest.mark.parametrize("case", ["example", "akbari", "gerd_calib_m0", "gerd_calib_m65535"])
+@pytest.mark.parametrize("case", ["example", "akbari", "gerd_calib_m0", "gerd_calib_m65535", "gerd_full", "gerd_gated_full"])
 def test_long_path_equals_fused_kernel_on_short_reaches(case):
     """Forcing the tiled path on the shipped cases (storage, normal-depth and Roseires boundaries, compound
-    sections): same results as the fused kernel and as the reference."""
+    sections, centre-line curvature over 384 levels, gate control): same results as the fused kernel and as the
+    reference."""
     flat = util.golden_inputs(case)
     ref = util.golden_outputs(case)
     out = run_flat(flat, lanes=-1)
