@@ -406,7 +406,15 @@ __global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
   }
   if (nd == p.N - 1) {
     q.qprev_last[m] = qv;
-    const double st = q.geo[F_Z * p.N + nd] + h;
+    double st = q.geo[F_Z * p.N + nd] + h;
+    if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses) {      // initial stage = Y - energy_loss (solver.py:101-108)
+      const Rough rg = load_rough<4>(p.geo, m);
+      NodeVals t;
+      NodeConv kc;
+      node_eval<false, 4, true>(q.geo, p.N, nd, h, qv, rg, p, t, &kc);
+      const double V = qv / kc.A;
+      st -= kc.Sf * p.dn.st_length + p.dn.st_kq * (V * V) / (2.0 * p.g);
+    }
     q.stage_prev[m] = st;
     gate_init(q.gate[m], p.dn.member_rc ? p.dn.member_rc[m] : p.dn.rc);
     if (p.storage_stage) p.storage_stage[(size_t)m * p.L] = st;
@@ -470,8 +478,6 @@ template <bool CMP, bool CURV>
 inline int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches,
                             std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
-  if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses)
-    return fail(PR_ERR_UNSUPPORTED, "long-reach path: lumped-storage head losses are not supported");
   const int N = p.N, M = p.M;
   const int T = (N - 1 + kTileCells - 1) / kTileCells;
   const int Kc = (T + 30) / 31;           // tile cells per lane so that the chain has <= 32 rows

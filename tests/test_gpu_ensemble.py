@@ -309,9 +309,6 @@ def test_unsupported_combinations_are_refused_with_a_message_not_emulated():
     flat = util.golden_inputs("gerd_gated")
     flat.up, flat.down = copy.copy(flat.down), copy.copy(flat.up)
     refused(flat, 1, "upstream")
-    # long-reach path: no storage head losses
-    flat = util.golden_inputs("storage_general")
-    refused(flat, 1, "head losses", lanes=-1)
     # malformed inputs
     flat = util.golden_inputs("example")
     flat.down.storage_area = 0.0

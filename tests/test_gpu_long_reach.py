@@ -71,14 +71,12 @@ def test_inflow_scenarios_on_a_long_reach():
 
 
 def test_general_storage_on_the_long_path():
-    """Area curve + outflow curve through the tiled path; head losses are rejected there, not emulated."""
-    import copy
-
-    from flow_sim_b200.abi import PreissmannLibraryError
-
+    """Area curve + outflow curve + head losses through the tiled path: the reference's own run of that case."""
     full = util.golden_inputs("storage_general")
-    with pytest.raises(PreissmannLibraryError, match="head losses"):
-        run_flat(full, lanes=-1)
+    ref = util.golden_outputs("storage_general")
+    out, _ = _vs_oracle(full, 1, "general storage with losses, long path", lanes=-1)
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], "storage_general, long path")
+    assert util.max_rel(out["storage_stage"][0], ref["storage_stage"]) <= util.RTOL
     a = copy.copy(full); a.down = copy.copy(full.down); a.down.storage_losses = False
     _vs_oracle(a, 1, "general storage, long path", lanes=-1)
 
