@@ -511,13 +511,12 @@ int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
   }                                                                                                          \
   template <bool CURV, int RM, bool EXACT>                                                                   \
   static int launch_x_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                      \
-    /* general lumped storage (Brent solve / losses) and gate-controlled rating curves: built without the  */ \
-    /* floodplain-roughness override and the straight-line variant (-4 = unsupported)                      */ \
+    /* general lumped storage (Brent solve / losses) and gate-controlled rating curves: one build per       */ \
+    /* curvature setting, roughness overrides decided at run time (RM = 4), no straight-line variant        */ \
     const bool gst = (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && (p.dn.st_general || p.dn.st_losses)) ||      \
                      (p.dn.type == PR_BC_RATING_CURVE && p.dn.gated);                                        \
     if (!gst) return launch_y_##G_##_##M_<CURV, RM, EXACT, false>(p, s);                                     \
-    if (RM > 1) return -4;                                                                                   \
-    return launch_y_##G_##_##M_<CURV, (RM & 1), false, true>(p, s);                                          \
+    return launch_y_##G_##_##M_<CURV, 4, false, true>(p, s);                                                 \
   }                                                                                                          \
   template <bool CURV, int RM>                                                                               \
   static int launch_one_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                    \

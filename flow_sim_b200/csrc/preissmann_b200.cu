@@ -268,9 +268,6 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
 }
 
 int launch_family(int rc_cuda) {
-  if (rc_cuda == -4)
-    return fail(PR_ERR_UNSUPPORTED, "general lumped storage (area curve / outflow curve / head losses) or a gate-controlled "
-                                    "rating curve together with per-member floodplain roughness overrides");
   if (rc_cuda != 0) return fail(PR_ERR_CUDA, "ensemble kernel launch: %s", cudaGetErrorString((cudaError_t)rc_cuda));
   g_launches.fetch_add(1);
   return PR_OK;

@@ -201,6 +201,19 @@ def test_general_lumped_storage_variants_vs_oracle():
         assert util.max_rel(out["storage_stage"], ora["storage_stage"]) <= util.RTOL
 
 
+def test_general_storage_and_gate_control_with_both_roughness_overrides():
+    """The rare-boundary kernels decide the roughness overrides at run time: per-member n_main AND n_fp."""
+    from test_gpu_ensemble import _prismatic as prism
+
+    flat = util.golden_inputs("gerd_gated")
+    flat.member_n_main = np.array([0.028, 0.030, 0.034])
+    flat.member_n_fp = np.array([0.04, 0.05, 0.06])
+    _check(flat, 3, "gate control + n_main + n_fp")
+    flat = util.golden_inputs("storage_general")
+    flat.member_n_main = np.array([0.03, 0.035])
+    _check(flat, 2, "general storage + n_main")
+
+
 def test_storage_root_outside_solution_boundaries_fails_the_member():
     """scipy's brentq raises when the mass balance has no sign change on solution_boundaries; the member stops at that
     iteration with status NaN (the oracle does the same), for the closed-form and for the Brent variant."""
@@ -268,7 +281,7 @@ def test_gate_controlled_rating_curve_state_per_member():
     when its gates slam shut - all against the oracle, which reproduces the reference's gated run (gerd_gated)."""
     flat = util.golden_inputs("gerd_gated")
     base = np.array(flat.up.series)
-    variants = [(1.0, 7200.0, 1, 0.030), (1.0, 18000.0, 0, 0.030), (4.0, 7200.0, 1, 0.025), (3.0, 3600.0, 0, 0.040),
+    variants = [(1.0, 7200.0, 1, 0.030), (1.0, 18000.0, 0, 0.030), (4.0, 7200.0, 1, 0.030), (3.0, 3600.0, 0, 0.040),
                 (6.0, 3600.0, 1, 0.030), (2.0, 0.0, 1, 0.035)]
     M = len(variants)
     flat.up.series = np.stack([base[0] + (base - base[0]) * v[0] for v in variants])
@@ -301,10 +314,6 @@ def test_unsupported_combinations_are_refused_with_a_message_not_emulated():
         with pytest.raises(PreissmannLibraryError, match=pattern):
             run_flat(flat, n_members=M, **kw)
 
-    # general lumped storage together with a per-member floodplain roughness
-    flat = util.golden_inputs("storage_general")
-    flat.member_n_fp = np.array([0.05, 0.06])
-    refused(flat, 2, "floodplain roughness")
     # gate-controlled curve: not upstream
     flat = util.golden_inputs("gerd_gated")
     flat.up, flat.down = copy.copy(flat.down), copy.copy(flat.up)
