@@ -12,14 +12,14 @@ import threading
 
 import numpy as np
 
-PR_ABI_VERSION = 5
+PR_ABI_VERSION = 6
 PR_MAX_POLY = 12
 PR_MAX_GATES = 8
 
 PR_OK, PR_ERR_ARG, PR_ERR_UNSUPPORTED, PR_ERR_CUDA = 0, 1, 2, 3
 PR_STATUS_OK, PR_STATUS_MAX_ITER, PR_STATUS_NAN, PR_STATUS_SUPERCRITICAL = 0, 1, 2, 3
 
-PR_XS_RECT, PR_XS_TRAPEZOID, PR_XS_COMPOUND = 0, 1, 2
+PR_XS_RECT, PR_XS_TRAPEZOID, PR_XS_COMPOUND, PR_XS_IRREGULAR = 0, 1, 2, 3
 (PR_BC_FLOW_HYDROGRAPH, PR_BC_FIXED_DEPTH, PR_BC_NORMAL_DEPTH, PR_BC_RATING_CURVE,
  PR_BC_STAGE_HYDROGRAPH, PR_BC_FIXED_DEPTH_STORAGE) = range(6)
 PR_RC_NONE, PR_RC_POLY2, PR_RC_POWER, PR_RC_POLYNOMIAL, PR_RC_ROSEIRES = range(5)
@@ -53,7 +53,9 @@ GEOM_FIELDS = ["kind", "z_bed", "b_main", "m_main", "h_bank", "T_bank", "W_bank"
 
 class pr_geom(C.Structure):
     _fields_ = ([("kind", c_int32_p)] + [(f, c_double_p) for f in GEOM_FIELDS[1:]] +
-                [("member_n_main", c_double_p), ("member_n_fp", c_double_p)])
+                [("member_n_main", c_double_p), ("member_n_fp", c_double_p),
+                 ("irr_offset", c_int32_p), ("irr_x", c_double_p), ("irr_z", c_double_p),
+                 ("irr_left", c_double_p), ("irr_right", c_double_p)])
 
 
 class pr_rating(C.Structure):

@@ -83,10 +83,16 @@ class FlatCase:
 # ------------------------------------------------------------------------------------------
 
 def _section_row(xs) -> dict:
+    if hasattr(xs, "x") and hasattr(xs, "z") and hasattr(xs, "left_fp_limit") and not hasattr(xs, "b_main"):
+        # IrregularSection (cross_section.py:207-543): polyline + composite roughness; the trapezoid columns are unused
+        return dict(kind=abi.PR_XS_IRREGULAR, z_bed=float(xs.z_min), b_main=0.0, m_main=0.0, h_bank=0.0, T_bank=0.0,
+                    W_bank=0.0, b_fp_l=0.0, b_fp_r=0.0, m_fp=0.0, n_l=float(xs.n_left), n_m=float(xs.n_main),
+                    n_r=float(xs.n_right), curvature=float(xs.curvature),
+                    _poly=(np.asarray(xs.x, dtype=np.float64), np.asarray(xs.z, dtype=np.float64),
+                           float(xs.left_fp_limit), float(xs.right_fp_limit)))
     if not hasattr(xs, "_is_compound") or not hasattr(xs, "b_main"):
         raise NotImplementedError(
-            f"{type(xs).__name__}: only TrapezoidalSection (rect / simple / compound) runs on the device; "
-            "IrregularSection is listed as next in SURVEY.md 8f-4")
+            f"{type(xs).__name__}: only TrapezoidalSection (rect / simple / compound) and IrregularSection run on the device")
     compound = bool(xs._is_compound)
     rect = bool(getattr(xs, "_is_rect", (not compound) and xs.m_main == 0.0))
     kind = abi.PR_XS_COMPOUND if compound else (abi.PR_XS_RECT if rect else abi.PR_XS_TRAPEZOID)
@@ -130,9 +136,20 @@ def interpolation_weights(ch_at_node, xs_chainages):
 
 def flatten_geometry(channel) -> dict:
     rows = [_section_row(xs) for xs in channel.xs_at_node]
-    geom = {k: np.array([r[k] for r in rows], dtype=np.int32 if k == "kind" else np.float64) for k in rows[0]}
+    geom = {k: np.array([r[k] for r in rows], dtype=np.int32 if k == "kind" else np.float64)
+            for k in rows[0] if not k.startswith("_")}
     w1, w2 = interpolation_weights(channel.ch_at_node, channel.xs_chainages)
     geom["w1"], geom["w2"] = w1, w2
+    if any("_poly" in r for r in rows):
+        empty = (np.empty(0), np.empty(0), 0.0, 0.0)
+        polys = [r.get("_poly", empty) for r in rows]
+        geom["irr_offset"] = np.concatenate([[0], np.cumsum([len(p[0]) for p in polys])]).astype(np.int32)
+        geom["irr_x"] = np.concatenate([p[0] for p in polys])
+        geom["irr_z"] = np.concatenate([p[1] for p in polys])
+        geom["irr_left"] = np.array([p[2] for p in polys], dtype=np.float64)
+        geom["irr_right"] = np.array([p[3] for p in polys], dtype=np.float64)
+        if np.any((geom["kind"] == abi.PR_XS_IRREGULAR) & (geom["curvature"] != 0.0)):
+            raise NotImplementedError("centre-line curvature at an IrregularSection node")
     return geom
 
 
@@ -346,6 +363,8 @@ def load_flat(path: str) -> FlatCase:
     s = z["scalars"]
     geom = {k[5:]: np.array(z[k]) for k in z.files if k.startswith("geom_")}
     geom["kind"] = geom["kind"].astype(np.int32)
+    if "irr_offset" in geom:
+        geom["irr_offset"] = geom["irr_offset"].astype(np.int32)
     flat = FlatCase(n_nodes=int(s[0]), n_levels=int(s[1]), theta=float(s[2]), dt=float(s[3]), dx=float(s[4]),
                     tol=float(s[5]), max_iter=int(s[6]), g=float(s[7]), geom=geom,
                     up=_bc_from_npz("up", z), down=_bc_from_npz("down", z),

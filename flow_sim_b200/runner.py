@@ -33,16 +33,7 @@ class PreparedCall:
                                  lanes_per_member=lanes, theta=flat.theta, dt=flat.dt, dx=flat.dx,
                                  tol=flat.tol, g=flat.g)
 
-        g = abi.pr_geom()
-        for name in abi.GEOM_FIELDS:
-            ptr, _ = ar.put(flat.geom[name], np.int32 if name == "kind" else np.float64)
-            setattr(g, name, ptr)
-        for name in ("member_n_main", "member_n_fp"):
-            v = getattr(flat, name)
-            if v is not None and len(v) != M:
-                raise ValueError(f"{name} has {len(v)} entries for {M} members")
-            setattr(g, name, ar.put(v)[0])
-        self.geom = g
+        self.geom = _geom_struct(flat, ar, M)
 
         self.up = self._bc(flat.up)
         self.down = self._bc(flat.down)
@@ -144,6 +135,10 @@ def _geom_struct(flat: FlatCase, arena: abi.Arena, M: int) -> abi.pr_geom:
         if v is not None and len(v) != M:
             raise ValueError(f"{name} has {len(v)} entries for {M} members")
         setattr(g, name, arena.put(v)[0])
+    if "irr_offset" in flat.geom:          # IrregularSection nodes: CSR polylines + composite-roughness limits
+        g.irr_offset = arena.put(flat.geom["irr_offset"], np.int32)[0]
+        for name in ("irr_x", "irr_z", "irr_left", "irr_right"):
+            setattr(g, name, arena.put(flat.geom[name], np.float64)[0])
     return g
 
 

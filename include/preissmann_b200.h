@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PR_ABI_VERSION 5
+#define PR_ABI_VERSION 6
 #define PR_MAX_POLY 12   /* max coefficients of a fitted numpy Polynomial rating curve */
 #define PR_MAX_GATES 8   /* Roseires: 7 spillway gates (roseires_rating_curve.py:11) */
 
@@ -38,7 +38,7 @@ extern "C" {
 #define PR_STATUS_SUPERCRITICAL 3 /* GVF initial condition: flow became supercritical (channel.py:328-332) */
 
 /* cross_section.py:636-674 - which branch of TrapezoidalSection.properties applies */
-enum pr_section_kind { PR_XS_RECT = 0, PR_XS_TRAPEZOID = 1, PR_XS_COMPOUND = 2 };
+enum pr_section_kind { PR_XS_RECT = 0, PR_XS_TRAPEZOID = 1, PR_XS_COMPOUND = 2, PR_XS_IRREGULAR = 3 };
 
 /* boundary.py:32 - condition names; FIXED_DEPTH_STORAGE = 'fixed_depth' + set_lumped_storage() */
 enum pr_bc_type {
@@ -113,6 +113,15 @@ typedef struct pr_geom {
   const double* w2;
   const double* member_n_main; /* [M] or NULL */
   const double* member_n_fp;   /* [M] or NULL */
+  /* IrregularSection nodes (kind = PR_XS_IRREGULAR, cross_section.py:207-543): the polyline of node i is
+   * irr_x/irr_z[irr_offset[i] .. irr_offset[i+1]) sorted by x (empty for the other kinds); z_bed[i] = min z;
+   * irr_left/irr_right[i] = left_fp_limit / right_fp_limit of the composite roughness (n_l, n_m, n_r as above).
+   * All NULL when the reach has no irregular section. */
+  const int32_t* irr_offset;   /* [N+1] */
+  const double* irr_x;
+  const double* irr_z;
+  const double* irr_left;      /* [N] */
+  const double* irr_right;     /* [N] */
 } pr_geom;
 
 typedef struct pr_rating {

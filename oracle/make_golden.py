@@ -36,7 +36,7 @@ def calib_n(m: int) -> float:
 # one release scenario (a member of a gate-state ensemble): lower pool, jammed gates, narrower blend buffer
 RELEASE_SCENARIO = dict(initial_roseires_level=486.2, rating_kwargs=dict(jammed_spillways=2, jammed_sluice_gates=1, buffer=0.3))
 
-CASES = ["example", "akbari", "gerd_full", "akbari_long", "storage_general", "gerd_release", "gerd_gated", "gerd_gated_full"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
+CASES = ["example", "akbari", "gerd_full", "akbari_long", "storage_general", "gerd_release", "gerd_gated", "gerd_gated_full", "irregular"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
 
 
 def build(case: str):
@@ -57,6 +57,8 @@ def build(case: str):
         # open and a 2 h cool-down makes them close (level 5) and re-open (level 25) in the middle of Newton loops
         return rh.build_gerd(n_main=0.03, calibration=True,
                              rating_kwargs=dict(smooth=False, initially_open=True, max_cooldown=7200))
+    if case == "irregular":          # IrregularSection polylines with composite roughness
+        return rh.build_irregular()
     if case == "gerd_gated_full":   # config 3 (curvature, 16 days) with gate control: dozens of open/close cycles
         return rh.build_gerd(calibration=False, rating_kwargs=dict(smooth=False))
     if case == "gerd_full":

@@ -30,6 +30,10 @@
 typedef struct {
   int kind;
   double z, b, m, hb, Tb, Wb, bl, br, mfp, nl, nm, nr, curv;
+  /* IrregularSection (cross_section.py:207-543): polyline sorted by x, composite-roughness limits */
+  const double *px, *pz;
+  int np;
+  double lim_l, lim_r;
 } xs_t;
 
 static xs_t xs_load(const pr_geom* g, int i, int member) {
@@ -40,6 +44,12 @@ static xs_t xs_load(const pr_geom* g, int i, int member) {
   s.bl = g->b_fp_l[i]; s.br = g->b_fp_r[i]; s.mfp = g->m_fp[i];
   s.nl = g->n_l[i]; s.nm = g->n_m[i]; s.nr = g->n_r[i];
   s.curv = g->curvature[i];
+  s.px = s.pz = NULL; s.np = 0; s.lim_l = s.lim_r = 0.0;
+  if (s.kind == PR_XS_IRREGULAR) {
+    s.px = g->irr_x + g->irr_offset[i]; s.pz = g->irr_z + g->irr_offset[i];
+    s.np = g->irr_offset[i + 1] - g->irr_offset[i];
+    s.lim_l = g->irr_left[i]; s.lim_r = g->irr_right[i];
+  }
   if (g->member_n_main) {            /* cross_section.py:892 with xs1.n_main == xs2.n_main == v */
     double v = g->member_n_main[member];
     s.nm = v * g->w1[i] + v * g->w2[i];
@@ -52,8 +62,158 @@ static xs_t xs_load(const pr_geom* g, int i, int member) {
   return s;
 }
 
+
+static double hy_conveyance(double A, double n, double R);
+
+/* ---------------- IrregularSection (cross_section.py:207-543) ---------------- */
+
+/* numpy's pairwise summation of a contiguous double array (np.sum, loops_utils.h.src pairwise_sum) */
+static double np_sum(const double* a, int n) {
+  if (n < 8) {
+    double res = 0.;
+    for (int i = 0; i < n; ++i) res += a[i];
+    return res;
+  }
+  if (n <= 128) {
+    double r[8];
+    int i;
+    for (i = 0; i < 8; ++i) r[i] = a[i];
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_sum(a, n2) + np_sum(a + n2, n - n2);
+}
+
+/* IrregularSection.properties (:247-327) on the sub-polyline [lo, hi] taken as a section of its own (what
+ * get_equivalent_n's subsection_props builds with IrregularSection(x[mask], z[mask]), :448-470). */
+static void irr_properties(const double* x, const double* z, int lo, int hi, double hw, double* A_out, double* P_out,
+                           double* T_out) {
+  *A_out = *P_out = *T_out = 0.0;
+  int n = hi - lo + 1;
+  if (n <= 0) return;
+  x += lo; z += lo;
+  double z_min = z[0];
+  for (int i = 1; i < n; ++i) if (z[i] < z_min) z_min = z[i];
+  if (hw <= z_min) return;
+  double A_total = 0.0, P_total = 0.0, T_total = 0.0;
+  double* xs = (double*)malloc(sizeof(double) * (n + 2) * 4);
+  double *zs = xs + (n + 2), *ta = zs + (n + 2), *tp = ta + (n + 2);
+  int i = 0;
+  while (i < n) {
+    if (hw - z[i] > 0.0) {
+      int i0 = i;
+      while (i + 1 < n && hw - z[i + 1] > 0.0) i += 1;
+      int iN = i, m = 0;
+      if (i0 > 0 && z[i0 - 1] > hw) {                          /* intersection with the water surface on the left */
+        double z0 = z[i0 - 1], z1 = z[i0], x0 = x[i0 - 1], x1 = x[i0];
+        double t = (hw - z0) / (z1 - z0);
+        xs[m] = x0 + t * (x1 - x0); zs[m] = hw; ++m;
+      }
+      for (int k = i0; k <= iN; ++k) { xs[m] = x[k]; zs[m] = z[k]; ++m; }
+      if (iN < n - 1 && z[iN + 1] > hw) {
+        double z0 = z[iN], z1 = z[iN + 1], x0 = x[iN], x1 = x[iN + 1];
+        double t = (hw - z0) / (z1 - z0);
+        xs[m] = x0 + t * (x1 - x0); zs[m] = hw; ++m;
+      }
+      for (int k = 0; k + 1 < m; ++k) {
+        double d0 = fmax(hw - zs[k], 0.0), d1 = fmax(hw - zs[k + 1], 0.0);
+        double dx = xs[k + 1] - xs[k], dz = zs[k + 1] - zs[k];
+        ta[k] = 0.5 * (d0 + d1) * dx;
+        tp[k] = sqrt(dx * dx + dz * dz);
+      }
+      A_total += np_sum(ta, m - 1);
+      P_total += np_sum(tp, m - 1);
+      T_total += xs[m - 1] - xs[0];
+    }
+    i += 1;
+  }
+  free(xs);
+  *A_out = A_total; *P_out = P_total; *T_out = T_total;
+}
+
+static void irr_props_full(const xs_t* s, double hw, double* A, double* P, double* R, double* T) {
+  irr_properties(s->px, s->pz, 0, s->np - 1, hw, A, P, T);
+  *R = (*P > 0.0) ? *A / *P : 0.0;
+}
+
+/* number of wetted sub-channels with at least two submerged points (get_subchannels, :329-372) */
+static int irr_subchannels(const xs_t* s, double hw) {
+  int count = 0, i = 0, n = s->np;
+  while (i < n) {
+    if (!(s->pz[i] < hw)) { i += 1; continue; }
+    int start = i;
+    while (i < n && s->pz[i] < hw) i += 1;
+    if (i - start >= 2) count += 1;
+  }
+  return count;
+}
+
+/* get_equivalent_n.subsection_props (:448-470): conveyance of the points with x_min <= x <= x_max */
+static double irr_sub_K(const xs_t* s, double hw, double x_min, double x_max, double n_value) {
+  int lo = 0, hi = s->np - 1;
+  while (lo < s->np && !(s->px[lo] >= x_min)) ++lo;
+  while (hi >= 0 && !(s->px[hi] <= x_max)) --hi;
+  if (hi - lo + 1 < 2) return 0.0;
+  double A, P, T;
+  irr_properties(s->px, s->pz, lo, hi, hw, &A, &P, &T);
+  if (A <= 0) return 0.0;
+  if (P <= 0) return 0.0;
+  return hy_conveyance(A, n_value, A / P);
+}
+
+/* IrregularSection.get_equivalent_n (:441-500) */
+static double irr_equivalent_n(const xs_t* s, double hw) {
+  double left_K = irr_sub_K(s, hw, s->px[0], s->lim_l, s->nl);
+  double main_K = irr_sub_K(s, hw, s->lim_l, s->lim_r, s->nm);
+  double right_K = irr_sub_K(s, hw, s->lim_r, s->px[s->np - 1], s->nr);
+  double A, P, R, T;
+  irr_props_full(s, hw, &A, &P, &R, &T);
+  if (A <= 0 || P <= 0) return s->nm;
+  double R_total = A / P;
+  double K_total = pow(pow(left_K, 1.5) + pow(main_K, 1.5) + pow(right_K, 1.5), 2.0 / 3.0);
+  if (K_total <= 0.0) return s->nm;
+  return (A * pow(R_total, 2.0 / 3.0)) / K_total;
+}
+
+/* IrregularSection.conveyance (:502-510), dR_dA (:524-532), dA_dh (:534-539), dK_dA (:512-522) */
+static double irr_conveyance(const xs_t* s, double hw) {
+  double A, P, R, T;
+  irr_props_full(s, hw, &A, &P, &R, &T);
+  if (A <= 0.0) return 0.0;
+  return hy_conveyance(A, irr_equivalent_n(s, hw), R);
+}
+static double irr_dR_dA(const xs_t* s, double hw) {
+  const double dh = 1e-6;
+  double A1, A2, P1, P2, R1, R2, T;
+  irr_props_full(s, hw - dh, &A1, &P1, &R1, &T);
+  irr_props_full(s, hw + dh, &A2, &P2, &R2, &T);
+  if ((A2 - A1) == 0.0) return 0.0;
+  return (R2 - R1) / (A2 - A1);
+}
+static double irr_dA_dh(const xs_t* s, double hw) {
+  const double dh = 1e-6;
+  double A1, A2, P, R, T;
+  irr_props_full(s, hw - dh, &A1, &P, &R, &T);
+  irr_props_full(s, hw + dh, &A2, &P, &R, &T);
+  return (A2 - A1) / (2 * dh);
+}
+static double irr_dK_dA(const xs_t* s, double hw) {
+  double A, P, R, T;
+  irr_props_full(s, hw, &A, &P, &R, &T);
+  if (A <= 0.0) return 0.0;
+  double n = irr_equivalent_n(s, hw);
+  double dR_dA = irr_dR_dA(s, hw);
+  return (pow(R, TWO_THIRDS) + A * 2. / 3. * pow(R, M_ONE_THIRD) * dR_dA) / n;
+}
+
 /* TrapezoidalSection.properties, cross_section.py:623-679 */
 static void xs_properties(const xs_t* s, double hw, double* A, double* P, double* R, double* T) {
+  if (s->kind == PR_XS_IRREGULAR) { irr_props_full(s, hw, A, P, R, T); return; }
   double depth = fmax(0.0, hw - s->z);
   if (depth <= 0.0) { *A = *P = *R = *T = 0.0; return; }
   if (s->kind == PR_XS_RECT) {
@@ -107,6 +267,7 @@ static void xs_subsections(const xs_t* s, double hw, double sub[3][3]) {
 
 /* TrapezoidalSection.conveyance, cross_section.py:741-754 */
 static double xs_conveyance(const xs_t* s, double hw) {
+  if (s->kind == PR_XS_IRREGULAR) return irr_conveyance(s, hw);
   if (s->kind != PR_XS_COMPOUND) {
     double A, P, R, T;
     xs_properties(s, hw, &A, &P, &R, &T);
@@ -122,6 +283,7 @@ static double xs_conveyance(const xs_t* s, double hw) {
 
 /* TrapezoidalSection.get_equivalent_n, cross_section.py:710-739 */
 static double xs_equivalent_n(const xs_t* s, double hw) {
+  if (s->kind == PR_XS_IRREGULAR) return irr_equivalent_n(s, hw);
   if (s->kind != PR_XS_COMPOUND) return s->nm;
   double K = xs_conveyance(s, hw);
   double A, P, R, T;
@@ -133,6 +295,7 @@ static double xs_equivalent_n(const xs_t* s, double hw) {
 
 /* TrapezoidalSection.dR_dA, cross_section.py:766-790 */
 static double xs_dR_dA(const xs_t* s, double hw) {
+  if (s->kind == PR_XS_IRREGULAR) return irr_dR_dA(s, hw);
   double A, P, R, T;
   xs_properties(s, hw, &A, &P, &R, &T);
   if (P <= 0.0 || T <= 0.0) return 0.0;
@@ -149,6 +312,7 @@ static double xs_dR_dA(const xs_t* s, double hw) {
 
 /* TrapezoidalSection.dK_dA + hydraulics.dK_dA_, cross_section.py:756-764, hydraulics.py:28-40 */
 static double xs_dK_dA(const xs_t* s, double hw) {
+  if (s->kind == PR_XS_IRREGULAR) return irr_dK_dA(s, hw);
   double A, P, R, T;
   xs_properties(s, hw, &A, &P, &R, &T);
   if (A <= 0.0) return 0.0;
@@ -161,7 +325,20 @@ static double xs_dK_dA(const xs_t* s, double hw) {
 static double hy_Sf(double Q, double K) { return Q * fabs(Q) / (K * K); }
 
 /* CrossSection.friction_slope / dSf_dA / dSf_dQ, cross_section.py:114-141 */
+/* IrregularSection overrides (:374-439): one wetted sub-channel -> the base-class formulas; two or more (a levee
+ * splitting the flow) are NOT restated - the evaluation returns NaN and the member stops with PR_STATUS_NAN. */
+static int xs_split(const xs_t* s, double hw) { return s->kind == PR_XS_IRREGULAR && irr_subchannels(s, hw) > 1; }
+
+/* CrossSection.dA_dh: top width for the trapezoids (:792-793), central difference for polylines (:534-539) */
+static double xs_dA_dh(const xs_t* s, double hw) {
+  if (s->kind == PR_XS_IRREGULAR) return irr_dA_dh(s, hw);
+  double A, P, R, T;
+  xs_properties(s, hw, &A, &P, &R, &T);
+  return T;
+}
+
 static double xs_friction_slope(const xs_t* s, double h, double Q) {
+  if (xs_split(s, h + s->z)) return NAN;
   return hy_Sf(Q, xs_conveyance(s, h + s->z));
 }
 static double xs_dSf_dA(const xs_t* s, double h, double Q) {
@@ -545,7 +722,7 @@ static double bc_df_dh(const bc_ctx* c, double depth, double flow) {
   double hw = depth + b->bed_level;
   double A, P, R, T;
   xs_properties(c->xs, hw, &A, &P, &R, &T);
-  double dA_dh = T;
+  double dA_dh = xs_dA_dh(c->xs, hw);
   switch (b->type) {
     case PR_BC_FIXED_DEPTH: return 1 - 0 * dA_dh;
     case PR_BC_FIXED_DEPTH_STORAGE: {                        /* boundary.py:168-177 */
@@ -665,10 +842,8 @@ static double area_at(const sch_t* s, int lvl, int i) {
   xs_properties(&s->xs[i], s->xs[i].z + h, &A, &P, &R, &T);
   return A;
 }
-static double topw_at(const sch_t* s, int i) {
-  double A, P, R, T;
-  xs_properties(&s->xs[i], s->xs[i].z + s->h1[i], &A, &P, &R, &T);
-  return T;
+static double topw_at(const sch_t* s, int i) {      /* Solver.dA_dh (solver.py:295-296) */
+  return xs_dA_dh(&s->xs[i], s->xs[i].z + s->h1[i]);
 }
 static double wl_at(const sch_t* s, int lvl, int i) { return s->xs[i].z + (lvl ? s->h1[i] : s->h0[i]); }
 static double flow_at(const sch_t* s, int lvl, int i) { return lvl ? s->q1[i] : s->q0[i]; }

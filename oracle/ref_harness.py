@@ -285,3 +285,38 @@ if __name__ == "__main__":
     s, kw = build_example()
     r = run_and_record(s, kw)
     print("example iters", r["iters"].tolist(), r["depth"].sum(), r["flow"].sum(), r["seconds"])
+
+
+def build_irregular(levee: bool = False):
+    """Synthetic companion case for IrregularSection (no shipped case instantiates it): a 12 km
+    reach between two surveyed-style polylines with composite roughness, interpolated node by node
+    (cross_section.py:933-969), flow hydrograph upstream, fixed depth downstream."""
+    setup_reference()
+    from math import pi, sin
+
+    from src.hydromodel.boundary import Boundary
+    from src.hydromodel.channel import Channel
+    from src.hydromodel.cross_section import IrregularSection
+    from src.hydromodel.hydrograph import Hydrograph
+    from src.hydromodel.preissmann import PreissmannSolver
+
+    L, S0, dt = 12000.0, 0.0005, 1800
+    wave = lambda t: 60 + 40 * sin(pi * min(t, 6 * dt) / (6 * dt)) ** 2
+    us = Boundary("flow_hydrograph", chainage=0, bed_level=S0 * L, initial_depth=2.0, hydrograph=Hydrograph(function=wave))
+    ds = Boundary("fixed_depth", chainage=L, bed_level=0.0, initial_depth=2.0)
+    ch = Channel(upstream_boundary=us, downstream_boundary=ds, initial_flow=60.0, roughness=0.03, width=30.0,
+                 interpolation_method="linear")
+
+    def sec(z0, shift):
+        x = np.array([0, 10, 14, 20, 30, 36, 40, 50.0]) + shift
+        z = np.array([6, 3.0, 1.2, 0.0, 0.1, 1.5, 3.2, 6.0]) + z0
+        if levee:       # a mid-channel bar that splits low flows into two wetted sub-channels
+            x = np.array([0, 10, 14, 20, 24, 26, 30, 36, 40, 50.0]) + shift
+            z = np.array([6, 3.0, 1.2, 0.0, 2.6, 2.6, 0.1, 1.5, 3.2, 6.0]) + z0
+        s = IrregularSection(x=x, z=z, n=0.03, bed_slope=S0)
+        s.set_roughness_para((0.05, 0.03, 0.06, 14.0 + shift, 36.0 + shift))
+        return s
+
+    ch.set_cross_sections([0.0, L], [sec(S0 * L, 0.0), sec(0.0, 1.0)])
+    solver = PreissmannSolver(channel=ch, theta=0.6, time_step=dt, spatial_step=1000.0, simulation_time=8 * dt)
+    return solver, dict(tolerance=1e-6, max_iter=60)
