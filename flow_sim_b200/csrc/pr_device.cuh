@@ -57,6 +57,9 @@ struct DevGeom {
   const int* kind;
   const double *z, *b, *m, *hb, *Tb, *Wb, *bl, *br, *mfp, *nl, *nm, *nr, *curv;
   const double *member_nm, *member_nfp;
+  // IrregularSection nodes (pr_irregular.cuh): CSR polylines and composite-roughness limits, or nullptr
+  const int* irr_offset;
+  const double *irr_x, *irr_z, *irr_left, *irr_right;
 };
 
 struct DevParams {
@@ -158,6 +161,7 @@ __device__ inline void stage_geometry(const DevGeom& g, int N, int NP, double* s
 // 4 = decided at run time from the two flags below (the long-reach kernels, which are not built per mode).
 struct Rough {
   double nm, inm, cnm, cnfp;    // n_main, 1/n_main, n_main^-1.5, n_fp^-1.5
+  double nfp;                   // n_fp itself (irregular sections)
   bool om, ofp;                 // RM = 4: which overrides are present
 };
 
@@ -174,7 +178,8 @@ __device__ __forceinline__ Rough load_rough(const DevGeom& g, long long member) 
   rg.nm = rg.om ? g.member_nm[member] : 1.0;
   rg.inm = 1.0 / rg.nm;
   rg.cnm = inv_n15(rg.nm);
-  rg.cnfp = rg.ofp ? inv_n15(g.member_nfp[member]) : 1.0;
+  rg.nfp = rg.ofp ? g.member_nfp[member] : 1.0;
+  rg.cnfp = inv_n15(rg.nfp);
   return rg;
 }
 

@@ -1,0 +1,137 @@
+// pr_irregular.cuh - node pass for IrregularSection nodes (cross_section.py:207-543): polyline sections with
+// composite roughness and finite-difference derivatives.  Used by the long-reach kernels only (a reach with an
+// irregular section is routed there whatever its length): the work per node is a handful of scans over the
+// section's points in global memory, not register arithmetic.
+//
+// One wetted sub-channel (get_subchannels, :329-372) takes the base-class formulas the reference falls back to
+// (:374-439 -> :114-141).  Two or more (a bar or levee splitting the flow) are NOT evaluated: the slope comes back
+// NaN and the member stops with PR_STATUS_NAN.
+#pragma once
+#include "pr_device.cuh"
+
+namespace pr {
+
+// IrregularSection.properties (:247-327) of the sub-polyline [lo, hi] taken as a section of its own (what
+// get_equivalent_n's subsection_props builds, :448-470).  The two np.sum reductions are reproduced in numpy's
+// pairwise order (8 interleaved accumulators up to 128 terms): the reference differentiates A and R by central
+// differences with dh = 1e-6, which amplifies a last-bit difference in A a million times.
+__device__ inline void irr_properties(const double* __restrict__ x, const double* __restrict__ z, int lo, int hi,
+                                      double hw, double& A_out, double& P_out, double& T_out) {
+  A_out = 0.0; P_out = 0.0; T_out = 0.0;
+  const int n = hi - lo + 1;
+  if (n <= 0) return;
+  x += lo; z += lo;
+  double z_min = z[0];
+  for (int i = 1; i < n; ++i) z_min = z[i] < z_min ? z[i] : z_min;
+  if (hw <= z_min) return;
+  double A_total = 0.0, P_total = 0.0, T_total = 0.0;
+  int i = 0;
+  while (i < n) {
+    if (hw - z[i] > 0.0) {
+      const int i0 = i;
+      while (i + 1 < n && hw - z[i + 1] > 0.0) i += 1;
+      const int iN = i;
+      const bool has_l = i0 > 0 && z[i0 - 1] > hw, has_r = iN < n - 1 && z[iN + 1] > hw;
+      double xl = 0.0, xr = 0.0;
+      if (has_l) { const double z0 = z[i0 - 1], z1 = z[i0], x0 = x[i0 - 1], x1 = x[i0]; xl = x0 + (hw - z0) / (z1 - z0) * (x1 - x0); }
+      if (has_r) { const double z0 = z[iN], z1 = z[iN + 1], x0 = x[iN], x1 = x[iN + 1]; xr = x0 + (hw - z0) / (z1 - z0) * (x1 - x0); }
+      const int m = (iN - i0 + 1) + (has_l ? 1 : 0) + (has_r ? 1 : 0), nt = m - 1;
+      // point k of the wetted polyline (intersection points carry z = hw)
+      auto px = [&](int k) { const int j = k - (has_l ? 1 : 0); return j < 0 ? xl : (j > iN - i0 ? xr : x[i0 + j]); };
+      auto pz = [&](int k) { const int j = k - (has_l ? 1 : 0); return (j < 0 || j > iN - i0) ? hw : z[i0 + j]; };
+      auto term = [&](int k, double& ta, double& tp) {
+        const double xa = px(k), xb = px(k + 1), za = pz(k), zb = pz(k + 1);
+        const double d0 = fmax(hw - za, 0.0), d1 = fmax(hw - zb, 0.0), dx = xb - xa, dz = zb - za;
+        ta = 0.5 * (d0 + d1) * dx;
+        tp = sqrt(dx * dx + dz * dz);
+      };
+      double sa = 0.0, sp = 0.0;
+      if (nt < 8) {
+        for (int k = 0; k < nt; ++k) { double ta, tp; term(k, ta, tp); sa += ta; sp += tp; }
+      } else {                                   // numpy pairwise sum, block of <= 128 terms
+        double ra[8], rp[8];
+        for (int k = 0; k < 8; ++k) term(k, ra[k], rp[k]);
+        const int nb = nt - (nt % 8);
+        for (int k = 8; k < nb; ++k) { double ta, tp; term(k, ta, tp); ra[k & 7] += ta; rp[k & 7] += tp; }
+        sa = ((ra[0] + ra[1]) + (ra[2] + ra[3])) + ((ra[4] + ra[5]) + (ra[6] + ra[7]));
+        sp = ((rp[0] + rp[1]) + (rp[2] + rp[3])) + ((rp[4] + rp[5]) + (rp[6] + rp[7]));
+        for (int k = nb; k < nt; ++k) { double ta, tp; term(k, ta, tp); sa += ta; sp += tp; }
+      }
+      A_total += sa; P_total += sp; T_total += px(m - 1) - px(0);
+    }
+    i += 1;
+  }
+  A_out = A_total; P_out = P_total; T_out = T_total;
+}
+
+// conveyance of the points with x_min <= x <= x_max (subsection_props, :448-470)
+__device__ inline double irr_sub_K(const double* x, const double* z, int n, double hw, double x_min, double x_max, double n_value) {
+  int lo = 0, hi = n - 1;
+  while (lo < n && !(x[lo] >= x_min)) ++lo;
+  while (hi >= 0 && !(x[hi] <= x_max)) --hi;
+  if (hi - lo + 1 < 2) return 0.0;
+  double A, P, T;
+  irr_properties(x, z, lo, hi, hw, A, P, T);
+  if (A <= 0.0 || P <= 0.0) return 0.0;
+  return A * pow(A / P, 2.0 / 3.0) / n_value;                 // hydraulics.conveyance (hydraulics.py:15-26)
+}
+
+// Everything the scheme needs from an irregular node: the counterpart of node_eval.
+//   T is Solver.dA_dh = the central difference of the area (:534-539), which is what the Jacobian uses.
+template <class KP>
+__device__ inline void node_eval_irregular(const DevGeom& g, int node, double h, double Q, const Rough& rg, const KP& k,
+                                           NodeVals& o, NodeConv* kc) {
+  const int off = g.irr_offset[node], n = g.irr_offset[node + 1] - off;
+  const double* x = g.irr_x + off;
+  const double* z = g.irr_z + off;
+  const double z_min = g.z[node];
+  const double hw = h + z_min;
+  const double nm = rg.om ? rg.nm : g.nm[node];
+  const double nl = rg.ofp ? rg.nfp : g.nl[node], nr = rg.ofp ? rg.nfp : g.nr[node];
+  const double dh = 1e-6;
+  double A, P, T, A1, P1, T1, A2, P2, T2;
+  irr_properties(x, z, 0, n - 1, hw, A, P, T);
+  irr_properties(x, z, 0, n - 1, hw - dh, A1, P1, T1);
+  irr_properties(x, z, 0, n - 1, hw + dh, A2, P2, T2);
+  const double R = P > 0.0 ? A / P : 0.0;
+  const double R1 = P1 > 0.0 ? A1 / P1 : 0.0, R2 = P2 > 0.0 ? A2 / P2 : 0.0;
+  // get_equivalent_n (:441-500)
+  double n_eq = nm;
+  if (A > 0.0 && P > 0.0) {
+    const double lim_l = g.irr_left[node], lim_r = g.irr_right[node];
+    const double Kl = irr_sub_K(x, z, n, hw, x[0], lim_l, nl);
+    const double Km = irr_sub_K(x, z, n, hw, lim_l, lim_r, nm);
+    const double Kr = irr_sub_K(x, z, n, hw, lim_r, x[n - 1], nr);
+    const double K_total = pow(pow(Kl, 1.5) + pow(Km, 1.5) + pow(Kr, 1.5), 2.0 / 3.0);
+    if (K_total > 0.0) n_eq = (A * pow(R, 2.0 / 3.0)) / K_total;
+  }
+  // conveyance (:502-510), dR_dA (:524-532), dK_dA (:512-522 with hydraulics.dK_dA_, hydraulics.py:28-40)
+  double K = 0.0, dKA = 0.0;
+  if (A > 0.0) {
+    K = A * pow(R, 2.0 / 3.0) / n_eq;
+    const double dRA = (A2 - A1) == 0.0 ? 0.0 : (R2 - R1) / (A2 - A1);
+    dKA = (pow(R, 2.0 / 3.0) + A * 2. / 3. * pow(R, 2.0 / 3.0 - 1.0) * dRA) / n_eq;
+  }
+  // more than one wetted sub-channel (z < hw runs of >= 2 points): not evaluated
+  int runs = 0;
+  for (int i = 0; i < n;) {
+    if (!(z[i] < hw)) { ++i; continue; }
+    const int s = i;
+    while (i < n && z[i] < hw) ++i;
+    runs += (i - s >= 2) ? 1 : 0;
+  }
+  const double absQ = fabs(Q);
+  double Sf = Q * absQ / (K * K);                              // hydraulics.Sf (hydraulics.py:42-57)
+  if (runs > 1) Sf = nan("");
+  const double dSfA = -2 * Sf * (dKA / K), dSfQ = 2 * absQ / (K * K);
+  const double dAdh = (A2 - A1) / (2 * dh);
+  const double QA = Q / A;
+  o.Q = Q; o.A = A; o.T = dAdh; o.Y = hw; o.Se = Sf; o.F = Q * QA; o.QA = QA;
+  o.w1 = (k.th_dx * QA) * (QA * dAdh);
+  o.w2 = (k.hth * dSfA) * dAdh;
+  o.w3 = k.hth * dSfQ;
+  o.w4 = k.th_dx2 * QA;
+  if (kc) { kc->K = K; kc->dKA = dKA; kc->A = A; kc->Sf = Sf; kc->dSfA = dSfA; kc->dSfQ = dSfQ; }
+}
+
+}  // namespace pr

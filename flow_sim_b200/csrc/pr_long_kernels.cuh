@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "pr_ensemble_kernel.cuh"
+#include "pr_irregular.cuh"
 
 namespace pr {
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ Cell shfl_cell(const Cell& c, int src) {
   return o;
 }
 
-template <int MODE, bool CMP, bool CURV>
+template <int MODE, bool CMP, bool CURV, bool IRR>
 __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const int lane = threadIdx.x & 31;
@@ -139,13 +140,18 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
   double* elw = long_smem + (size_t)(threadIdx.x >> 5) * ((kLongM - 1) * 9 * 32);
 #define LEL(j, c) elw[((j)*9 + (c)) * 32 + lane]
   NodeVals nv[2];
-  node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, c0 < N ? c0 : N - 1, h[0], qq[0], rg, p, nv[0]);
+  // node pass of one node: arithmetic on the derived table, or polyline scans for an IrregularSection node
+  auto eval_node = [&](int nd, double hh, double qv, NodeVals& out) {
+    if (IRR && q.geo[F_KIND * N + nd] == (double)PR_XS_IRREGULAR) node_eval_irregular(p.geo, nd, hh, qv, rg, p, out, nullptr);
+    else node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, nd, hh, qv, rg, p, out);
+  };
+  eval_node(c0 < N ? c0 : N - 1, h[0], qq[0], nv[0]);
   double ss = 0.0;
   Cell S;
 #pragma unroll
   for (int j = 0; j < kLongM; ++j) {
     const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
-    node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, nd, h[j + 1], qq[j + 1], rg, p, nv[(j + 1) & 1]);
+    eval_node(nd, h[j + 1], qq[j + 1], nv[(j + 1) & 1]);
     if (j < nc) {
       const int c = c0 + j;
       Cell e;
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
 
 // One warp per member: chain of tile cells + boundary rows, convergence and bookkeeping.
 // Shared memory per warp: Kc-1 elimination records x 10 doubles x 32 lanes.
+template <bool IRR>
 __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ LongParams q) {
   extern __shared__ double rec[];
   const DevParams& p = q.p;
@@ -303,12 +310,14 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   const double hyd_dn = p.dn.series ? p.dn.series[(size_t)m * p.dn.series_stride + level] : 0.0;
   if (lane == 0) {
     NodeVals nvb; NodeConv kc;
-    node_eval<false, 4, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
+    if (IRR && q.geo[F_KIND * N] == (double)PR_XS_IRREGULAR) node_eval_irregular(p.geo, 0, xh[0], xq[0], rg, p, nvb, &kc);
+    else node_eval<false, 4, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
     U = bc_eval<false>(p.up, m, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, p.g, kc, nvb.T);
   }
   if (lane == Lc) {
     NodeVals nvb; NodeConv kc;
-    node_eval<false, 4, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
+    if (IRR && q.geo[F_KIND * N + N - 1] == (double)PR_XS_IRREGULAR) node_eval_irregular(p.geo, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
+    else node_eval<false, 4, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
     D = bc_eval<true>(p.dn, m, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T, &q.gate[m]);
   }
   const double Ures = __shfl_sync(kFull, U.res, 0), Dres = __shfl_sync(kFull, D.res, Lc);
@@ -474,7 +483,7 @@ struct LongWorkspace {
 };
 inline LongWorkspace& long_workspace() { static LongWorkspace w; return w; }
 
-template <bool CMP, bool CURV>
+template <bool CMP, bool CURV, bool IRR>
 inline int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches,
                             std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
@@ -520,16 +529,16 @@ inline int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
   const dim3 tile_grid((unsigned)T, (unsigned)((M + 3) / 4));
   const size_t tile_smem = sizeof(double) * 4 * (kLongM - 1) * 9 * 32;   // elimination records, 4 warps per CTA
-  pr_long_tile<LONG_INIT, CMP, CURV><<<tile_grid, 128, tile_smem, s>>>(q);
+  pr_long_tile<LONG_INIT, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);
   launches.fetch_add(3);
   const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
-  e = cudaFuncSetAttribute(pr_long_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
+  e = cudaFuncSetAttribute(pr_long_chain<IRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
   int done = (p.L > 1) ? 0 : M;
   const long long max_trips = (long long)(p.L - 1) * (p.max_iter > 0 ? p.max_iter : 1) + 1;
   for (long long trip = 0; trip < max_trips && done < M && e == cudaSuccess; ++trip) {
-    pr_long_tile<LONG_CONDENSE, CMP, CURV><<<tile_grid, 128, tile_smem, s>>>(q);
-    pr_long_chain<<<M, 32, chain_smem, s>>>(q);
-    pr_long_tile<LONG_UPDATE, CMP, CURV><<<tile_grid, 128, tile_smem, s>>>(q);
+    pr_long_tile<LONG_CONDENSE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);
+    pr_long_chain<IRR><<<M, 32, chain_smem, s>>>(q);
+    pr_long_tile<LONG_UPDATE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);
     pr_long_retire<<<(M + 127) / 128, 128, 0, s>>>(q);
     launches.fetch_add(4);
     std::swap(q.xh, q.xh_out);
@@ -552,13 +561,21 @@ inline int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long
   return PR_OK;
 }
 
-inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, cudaStream_t s,
+inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, bool has_irregular, cudaStream_t s,
                           std::atomic<long long>& launches, std::string& err) {
+  // IrregularSection nodes: one more set of kernels (compound arithmetic for the trapezoid nodes of a mixed reach).
+  if (has_irregular) {
+    if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses) {
+      err = "lumped-storage head losses together with irregular sections";
+      return PR_ERR_UNSUPPORTED;
+    }
+    return long_reach_run_t<true, false, true>(p, s, launches, err);
+  }
   // centre-line curvature: compiled with the compound-section node pass only (a curved reach with floodplains is the
   // shipped gerd case; a curved prismatic reach takes the same kernels, the floodplain terms select to nothing)
-  if (has_curv) return long_reach_run_t<true, true>(p, s, launches, err);
-  return has_compound ? long_reach_run_t<true, false>(p, s, launches, err)
-                      : long_reach_run_t<false, false>(p, s, launches, err);
+  if (has_curv) return long_reach_run_t<true, true, false>(p, s, launches, err);
+  return has_compound ? long_reach_run_t<true, false, false>(p, s, launches, err)
+                      : long_reach_run_t<false, false, false>(p, s, launches, err);
 }
 
 }  // namespace pr

@@ -264,6 +264,28 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
   d.curv = st.in(g->curvature, N);
   d.member_nm = st.in(g->member_n_main, M);
   d.member_nfp = st.in(g->member_n_fp, M);
+  d.irr_offset = nullptr; d.irr_x = d.irr_z = d.irr_left = d.irr_right = nullptr;
+  if (g->irr_offset) {                 // IrregularSection polylines (CSR)
+    if (!g->irr_x || !g->irr_z || !g->irr_left || !g->irr_right) return fail(PR_ERR_ARG, "geom: irregular-section arrays are incomplete");
+    int32_t total = 0;
+    if (cfg.mem == PR_MEM_HOST) total = g->irr_offset[N];
+    else CUDA_TRY(cudaMemcpy(&total, g->irr_offset + N, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (total < 0) return fail(PR_ERR_ARG, "geom: irr_offset is not a prefix sum");
+    d.irr_offset = st.in(g->irr_offset, N + 1);
+    d.irr_x = st.in(g->irr_x, (size_t)total); d.irr_z = st.in(g->irr_z, (size_t)total);
+    d.irr_left = st.in(g->irr_left, N); d.irr_right = st.in(g->irr_right, N);
+  }
+  return PR_OK;
+}
+
+// true when some node is an IrregularSection (the setup kernels below take the trapezoid kinds only)
+int any_irregular(const pr_config& cfg, const pr_geom* g, bool& found) {
+  found = false;
+  if (!g || !g->kind) return fail(PR_ERR_ARG, "geom is incomplete");
+  std::vector<int32_t> kinds((size_t)cfg.n_nodes);
+  if (cfg.mem == PR_MEM_HOST) std::memcpy(kinds.data(), g->kind, kinds.size() * sizeof(int32_t));
+  else CUDA_TRY(cudaMemcpy(kinds.data(), g->kind, kinds.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int32_t kd : kinds) found |= (kd == PR_XS_IRREGULAR);
   return PR_OK;
 }
 
@@ -341,15 +363,18 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   if (int rc = fetch(geom->z_bed, N, cfg->mem, zb)) return rc;
   bool has_curv = false;
   for (double c : curv) has_curv |= (c != 0.0);
-  bool has_compound = false;
+  bool has_compound = false, has_irregular = false;
   {
     std::vector<int32_t> kinds(N);
     if (cfg->mem == PR_MEM_HOST) std::memcpy(kinds.data(), geom->kind, N * sizeof(int32_t));
     else CUDA_TRY(cudaMemcpy(kinds.data(), geom->kind, N * sizeof(int32_t), cudaMemcpyDeviceToHost));
     for (int32_t kd : kinds) {
-      if (kd < PR_XS_RECT || kd > PR_XS_COMPOUND) return fail(PR_ERR_ARG, "geom.kind holds an unknown section kind %d", kd);
+      if (kd < PR_XS_RECT || kd > PR_XS_IRREGULAR) return fail(PR_ERR_ARG, "geom.kind holds an unknown section kind %d", kd);
       has_compound |= (kd == PR_XS_COMPOUND);
+      has_irregular |= (kd == PR_XS_IRREGULAR);
     }
+    if (has_irregular && !geom->irr_offset) return fail(PR_ERR_ARG, "geom: irregular sections without their polylines");
+    if (has_irregular && has_curv) return fail(PR_ERR_UNSUPPORTED, "centre-line curvature together with irregular sections");
   }
 
   if (int rc = stage_geom(*cfg, geom, st, p.geo)) return rc;
@@ -379,7 +404,8 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   auto fits = [&](int G, int M) { return (lpm == 0 || lpm == G) && cells <= (G - 1) * M; };
   int rc;
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
-  if (lpm == -1) rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);   // forced long-reach path
+  if (has_irregular) rc = pr::long_reach_run(p, false, true, true, s, g_launches, g_err);       // polyline node pass
+  else if (lpm == -1) rc = pr::long_reach_run(p, has_curv, has_compound, false, s, g_launches, g_err);   // forced long-reach path
   else if (fits(8, 1)) rc = launch_family(pr::launch_ensemble_family<8, 1, 16>(p, has_curv, s));
   else if (fits(8, 2)) rc = launch_family(pr::launch_ensemble_family<8, 2, 16>(p, has_curv, s));
   else if (fits(8, 4)) rc = launch_family(pr::launch_ensemble_family<8, 4, 16>(p, has_curv, s));
@@ -390,7 +416,7 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   else if (fits(32, 4)) rc = launch_family(pr::launch_ensemble_family<32, 4, PR_W4>(p, has_curv, s));
   else if (fits(32, 8)) rc = launch_family(pr::launch_ensemble_family<32, 8, 7>(p, has_curv, s));
   else if (lpm != 0) return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: no instantiation holds %d nodes", lpm, (int)N);
-  else rc = pr::long_reach_run(p, has_curv, has_compound, s, g_launches, g_err);
+  else rc = pr::long_reach_run(p, has_curv, has_compound, false, s, g_launches, g_err);
   if (rc) return rc;
   cudaError_t e = st.finish();
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, "pr_ensemble_run: %s", cudaGetErrorString(e));
@@ -402,6 +428,11 @@ int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const d
                               double* ic_depth, double* ic_flow, int32_t* status, void* cuda_stream) {
   if (int rc = check_config(cfg)) return rc;
   if (!q0 || !downstream_depth || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "q0 / downstream_depth / ic buffers are NULL");
+  {
+    bool irr = false;
+    if (int rc = any_irregular(*cfg, geom, irr)) return rc;
+    if (irr) return fail(PR_ERR_UNSUPPORTED, "GVF initial conditions on the device: irregular sections are not covered (use the host profile)");
+  }
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t N = cfg->n_nodes, M = cfg->n_members;
   Stage st(cfg->mem == PR_MEM_HOST, s);
@@ -468,6 +499,11 @@ int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* 
                        double* level, double* area, double* top_width, double* froude, double* velocity,
                        double* celerity, void* cuda_stream) {
   if (int rc = check_config(cfg)) return rc;
+  {
+    bool irr = false;
+    if (int rc = any_irregular(*cfg, geom, irr)) return rc;
+    if (irr) return fail(PR_ERR_UNSUPPORTED, "derived result arrays on the device: irregular sections are not covered");
+  }
   if (!depth || !flow) return fail(PR_ERR_ARG, "derived results: depth / flow are NULL");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t N = cfg->n_nodes, total = (size_t)cfg->n_members * cfg->n_levels * N;
@@ -505,6 +541,11 @@ int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom
                                        const double* q0, int64_t q0_member_stride, double* ic_depth,
                                        double* ic_flow, void* cuda_stream) {
   if (int rc = check_config(cfg)) return rc;
+  {
+    bool irr = false;
+    if (int rc = any_irregular(*cfg, geom, irr)) return rc;
+    if (irr) return fail(PR_ERR_UNSUPPORTED, "normal-depth initial conditions on the device: irregular sections are not covered");
+  }
   if (!bed_slope || !q0 || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "normal depth: NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t N = cfg->n_nodes, M = cfg->n_members;

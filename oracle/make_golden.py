@@ -59,6 +59,8 @@ def build(case: str):
                              rating_kwargs=dict(smooth=False, initially_open=True, max_cooldown=7200))
     if case == "irregular":          # IrregularSection polylines with composite roughness
         return rh.build_irregular()
+    if case == "irregular_levee":    # inputs only: a bar splits low flows into two sub-channels (refused at run time)
+        return rh.build_irregular(levee=True)
     if case == "gerd_gated_full":   # config 3 (curvature, 16 days) with gate control: dozens of open/close cycles
         return rh.build_gerd(calibration=False, rating_kwargs=dict(smooth=False))
     if case == "gerd_full":

@@ -1,0 +1,94 @@
+"""IrregularSection nodes through the C ABI: polyline sections with composite roughness and the
+reference's finite-difference derivatives, against the live reference's run of the synthetic companion case
+(tests/golden/irregular.*, oracle/ref_harness.build_irregular) and against the oracle."""
+import copy
+
+import numpy as np
+import pytest
+
+import util
+from flow_sim_b200 import abi
+from flow_sim_b200.runner import run_flat
+
+pytestmark = pytest.mark.gpu
+
+
+def test_irregular_reach_matches_the_reference_run():
+    flat = util.golden_inputs("irregular")
+    ref = util.golden_outputs("irregular")
+    assert (flat.geom["kind"] == abi.PR_XS_IRREGULAR).all() and flat.geom["irr_offset"][-1] == 192
+    out = run_flat(flat)
+    assert out["status"][0] == abi.PR_STATUS_OK
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], "irregular")
+    assert np.array_equal(out["iters"][0], ref["iters"])
+
+
+def test_irregular_ensemble_roughness_and_inflow_members():
+    import oracle_py
+
+    flat = util.golden_inputs("irregular")
+    M = 7
+    flat.member_n_main = np.linspace(0.025, 0.04, M)
+    flat.member_n_fp = np.linspace(0.045, 0.07, M)
+    base = np.array(flat.up.series)
+    flat.up.series = np.stack([base[0] + (base - base[0]) * (0.5 + 0.25 * m) for m in range(M)])
+    ora = oracle_py.run(flat, n_members=M)
+    out = run_flat(flat, n_members=M)
+    assert np.array_equal(out["status"], ora["status"]) and not out["status"].any()
+    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "irregular ensemble")
+    assert np.array_equal(out["iters"], ora["iters"])
+
+
+def test_mixed_reach_and_other_boundaries():
+    """Trapezoid nodes next to polyline nodes (what interpolating a surveyed section with a design section gives at the
+    input stations), with a normal-depth downstream boundary evaluated on a polyline node."""
+    import oracle_py
+
+    flat = util.golden_inputs("irregular")
+    N = flat.n_nodes
+    g = {k: np.array(v) for k, v in flat.geom.items()}
+    # node 0 becomes a compound trapezoid with the same invert
+    off = g["irr_offset"]
+    n0 = off[1] - off[0]
+    g["irr_x"], g["irr_z"] = g["irr_x"][n0:], g["irr_z"][n0:]
+    g["irr_offset"] = np.concatenate([[0], off[1:] - n0]).astype(np.int32)
+    g["kind"][0] = abi.PR_XS_COMPOUND
+    g["b_main"][0], g["m_main"][0], g["h_bank"][0] = 12.0, 1.5, 1.6
+    g["T_bank"][0] = 12.0 + 2 * 1.5 * 1.6
+    g["b_fp_l"][0], g["b_fp_r"][0], g["m_fp"][0] = 8.0, 6.0, 3.0
+    g["W_bank"][0] = g["T_bank"][0] + 14.0
+    flat.geom = g
+    flat.down = copy.copy(flat.down)
+    flat.down.type = abi.PR_BC_NORMAL_DEPTH
+    flat.down.bed_slope = 0.0005
+    ora = oracle_py.run(flat)
+    out = run_flat(flat)
+    assert np.array_equal(out["status"], ora["status"]) and out["status"][0] == 0
+    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "mixed reach, normal depth")
+    assert np.array_equal(out["iters"], ora["iters"])
+
+
+def test_split_flow_is_refused_per_member_not_emulated():
+    """A mid-channel bar that splits low flows into two wetted sub-channels: the reference switches to its
+    multi-sub-channel conveyance there, which is not built; oracle and device both stop the member with
+    PR_STATUS_NAN instead of returning single-channel numbers."""
+    import oracle_py
+
+    flat = util.golden_inputs("irregular_levee")        # oracle/ref_harness.build_irregular(levee=True)
+    ora = oracle_py.run(flat)
+    out = run_flat(flat)
+    assert ora["status"][0] == abi.PR_STATUS_NAN and out["status"][0] == abi.PR_STATUS_NAN
+    assert out["fail_level"][0] == ora["fail_level"][0]
+
+
+def test_refused_combinations():
+    from flow_sim_b200.abi import PreissmannLibraryError
+    from flow_sim_b200.runner import gvf_initial_conditions
+
+    flat = util.golden_inputs("irregular")
+    flat.geom = dict(flat.geom); flat.geom["curvature"] = np.full(flat.n_nodes, 1e-4)
+    with pytest.raises(PreissmannLibraryError, match="curvature"):
+        run_flat(flat)
+    flat = util.golden_inputs("irregular")
+    with pytest.raises(PreissmannLibraryError, match="irregular"):
+        gvf_initial_conditions(flat, 2, 60.0, 2.0)
