@@ -1,0 +1,35 @@
+"""A synthetic reach with surveyed-style polyline sections (``IrregularSection``), the companion of
+``oracle/ref_harness.build_irregular`` on the mirror API.  The reference ships no case of its own with irregular
+sections; this one pins the device path to a run of the live reference (tests/golden/irregular.*)."""
+from math import pi, sin
+
+import numpy as np
+
+from ..hydromodel import Boundary, Channel, Hydrograph, IrregularSection, PreissmannSolver
+
+LENGTH, BED_SLOPE, TIME_STEP = 12000.0, 0.0005, 1800
+
+
+def inflow(t):
+    return 60 + 40 * sin(pi * min(t, 6 * TIME_STEP) / (6 * TIME_STEP)) ** 2
+
+
+def section(invert, shift, bar=False):
+    """Main channel between stations 14 and 36, rougher overbanks; ``bar`` adds a mid-channel bar that splits low flows."""
+    x = [0, 10, 14, 20, 24, 26, 30, 36, 40, 50.0] if bar else [0, 10, 14, 20, 30, 36, 40, 50.0]
+    z = [6, 3.0, 1.2, 0.0, 2.6, 2.6, 0.1, 1.5, 3.2, 6.0] if bar else [6, 3.0, 1.2, 0.0, 0.1, 1.5, 3.2, 6.0]
+    s = IrregularSection(x=np.array(x) + shift, z=np.array(z) + invert, n=0.03, bed_slope=BED_SLOPE)
+    s.set_roughness_para((0.05, 0.03, 0.06, 14.0 + shift, 36.0 + shift))
+    return s
+
+
+def build(bar=False, levels=8):
+    up = Boundary("flow_hydrograph", chainage=0, bed_level=BED_SLOPE * LENGTH, initial_depth=2.0,
+                  hydrograph=Hydrograph(function=inflow))
+    down = Boundary("fixed_depth", chainage=LENGTH, bed_level=0.0, initial_depth=2.0)
+    ch = Channel(upstream_boundary=up, downstream_boundary=down, initial_flow=60.0, roughness=0.03, width=30.0,
+                 interpolation_method="linear")
+    ch.set_cross_sections([0.0, LENGTH], [section(BED_SLOPE * LENGTH, 0.0, bar), section(0.0, 1.0, bar)])
+    solver = PreissmannSolver(channel=ch, theta=0.6, time_step=TIME_STEP, spatial_step=1000.0,
+                              simulation_time=levels * TIME_STEP)
+    return solver, dict(tolerance=1e-6, max_iter=60)

@@ -9,7 +9,7 @@ import sys
 from . import boundary, channel, cross_section, hydraulics, hydrograph, lumped_storage, preissmann, rating_curve, solver, utility
 from .boundary import Boundary
 from .channel import Channel
-from .cross_section import TrapezoidalSection, interpolate_cross_section
+from .cross_section import IrregularSection, TrapezoidalSection, interpolate_cross_section
 from .hydrograph import Hydrograph
 from .lumped_storage import LumpedStorage
 from .preissmann import PreissmannSolver

@@ -1,6 +1,6 @@
-"""``TrapezoidalSection`` and ``interpolate_cross_section`` with the reference's constructor, attributes
-and method names (cross_section.py:549-846, 857-930).  Rectangular, simple and compound trapezoids -
-the only section family the shipped cases instantiate; ``IrregularSection`` is not provided.
+"""``TrapezoidalSection``, ``IrregularSection`` and ``interpolate_cross_section`` with the reference's constructors,
+attributes and method names (cross_section.py:207-543, 549-846, 857-969).  Rectangular, simple and compound
+trapezoids are what the shipped cases instantiate; polyline sections are the SURVEY.md 8f-4 widening.
 
 Host-side SETUP code (geometry interpolation, initial conditions, derived results).  The per-iteration
 evaluation of these quantities happens in the CUDA node pass, never here.
@@ -8,6 +8,8 @@ evaluation of these quantities happens in the CUDA node pass, never here.
 from __future__ import annotations
 
 import math
+
+import numpy as np
 
 from . import hydraulics
 
@@ -218,6 +220,152 @@ class TrapezoidalSection(CrossSection):
             return 0.0
 
 
+class IrregularSection(CrossSection):
+    """Surveyed section given as a polyline (x, z), with composite roughness between ``left_fp_limit`` and
+    ``right_fp_limit`` (cross_section.py:207-543).  Area and hydraulic radius are differentiated by central
+    differences with dh = 1e-6, as the reference does."""
+
+    def __init__(self, x, z, **kwargs):
+        super().__init__(**kwargs)
+        x = np.ascontiguousarray(x, dtype=float)
+        z = np.ascontiguousarray(z, dtype=float)
+        if x.shape != z.shape:
+            raise ValueError("x and z must have the same shape")
+        if x.ndim != 1:
+            raise ValueError("x and z must be 1-D arrays")
+        order = np.argsort(x)
+        self.x, self.z = x[order], z[order]
+        self.left_fp_limit, self.right_fp_limit = self.x[0], self.x[-1]
+
+    @property
+    def z_min(self):
+        return float(self.z.min())
+
+    @property
+    def width(self):
+        return float(self.x.max() - self.x.min())
+
+    def _runs(self, wet):
+        """[first, last] index pairs of the maximal runs of True."""
+        edges = np.flatnonzero(np.diff(np.concatenate(([0], wet.astype(np.int8), [0]))))
+        return [(int(a), int(b) - 1) for a, b in zip(edges[0::2], edges[1::2])]
+
+    def properties(self, hw):
+        hw = float(hw)
+        x, z = self.x, self.z
+        if hw <= self.z_min:
+            return 0.0, 0.0, 0.0, 0.0
+        area = perimeter = top = 0.0
+        for first, last in self._runs(hw - z > 0.0):
+            px, pz = x[first:last + 1], z[first:last + 1]
+            if first > 0 and z[first - 1] > hw:             # the bank cuts the water surface
+                frac = (hw - z[first - 1]) / (z[first] - z[first - 1])
+                px = np.insert(px, 0, x[first - 1] + frac * (x[first] - x[first - 1]))
+                pz = np.insert(pz, 0, hw)
+            if last < x.size - 1 and z[last + 1] > hw:
+                frac = (hw - z[last]) / (z[last + 1] - z[last])
+                px = np.append(px, x[last] + frac * (x[last + 1] - x[last]))
+                pz = np.append(pz, hw)
+            depth = np.maximum(hw - pz, 0.0)
+            span, rise = np.diff(px), np.diff(pz)
+            area += np.sum(0.5 * (depth[:-1] + depth[1:]) * span)
+            perimeter += np.sum(np.sqrt(span ** 2 + rise ** 2))
+            top += px[-1] - px[0]
+        radius = area / perimeter if perimeter > 0.0 else 0.0
+        return float(area), float(perimeter), float(radius), float(top)
+
+    def area(self, hw):
+        return self.properties(hw)[0]
+
+    def wetted_perimeter(self, hw):
+        return self.properties(hw)[1]
+
+    def hydraulic_radius(self, hw):
+        return self.properties(hw)[2]
+
+    def top_width(self, hw):
+        return self.properties(hw)[3]
+
+    def z_at(self, x):
+        return np.interp(x, self.x, self.z, left=self.z[0], right=self.z[-1])
+
+    def sub_channels(self, hw):
+        """Number of separately wetted sub-channels with at least two submerged points."""
+        return sum(1 for a, b in self._runs(self.z < hw) if b - a + 1 >= 2)
+
+    def _part_conveyance(self, hw, x_from, x_to, n_value):
+        inside = (self.x >= x_from) & (self.x <= x_to)
+        if inside.sum() < 2:
+            return 0.0
+        part = IrregularSection(x=self.x[inside], z=self.z[inside])
+        A, P, _, _ = part.properties(hw)
+        if A <= 0 or P <= 0:
+            return 0.0
+        return hydraulics.conveyance(A=A, n=n_value, R=A / P)
+
+    def get_equivalent_n(self, hw):
+        parts = (self._part_conveyance(hw, self.x[0], self.left_fp_limit, self.n_left),
+                 self._part_conveyance(hw, self.left_fp_limit, self.right_fp_limit, self.n_main),
+                 self._part_conveyance(hw, self.right_fp_limit, self.x[-1], self.n_right))
+        A, P, _, _ = self.properties(hw)
+        if A <= 0 or P <= 0:
+            return self.n_main
+        K = (parts[0] ** 1.5 + parts[1] ** 1.5 + parts[2] ** 1.5) ** (2.0 / 3.0)
+        if K <= 0.0:
+            return self.n_main
+        return (A * (A / P) ** (2.0 / 3.0)) / K
+
+    def conveyance(self, hw):
+        A = self.area(hw)
+        if A <= 0.0:
+            return 0.0
+        return hydraulics.conveyance(A=A, n=self.get_equivalent_n(hw), R=self.hydraulic_radius(hw))
+
+    def dR_dA(self, hw, dh=1e-6):
+        lo, hi = self.properties(hw - dh), self.properties(hw + dh)
+        if hi[0] - lo[0] == 0.0:
+            return 0.0
+        return (hi[2] - lo[2]) / (hi[0] - lo[0])
+
+    def dA_dh(self, hw, dh=1e-6):
+        return (self.area(hw + dh) - self.area(hw - dh)) / (2 * dh)
+
+    def dK_dA(self, hw):
+        A = self.area(hw)
+        if A <= 0.0:
+            return 0.0
+        return hydraulics.dK_dA_(A=A, n=self.get_equivalent_n(hw), R=self.hydraulic_radius(hw), dR_dA=self.dR_dA(hw))
+
+    def _single_channel(self, hw):
+        if self.sub_channels(hw) > 1:
+            raise NotImplementedError("IrregularSection split into several wetted sub-channels")
+
+    def friction_slope(self, h, Q):
+        hw = h + self.z_min
+        self._single_channel(hw)
+        return hydraulics.Sf(Q=Q, K=self.conveyance(hw))
+
+    def dSf_dA(self, h, Q):
+        hw = h + self.z_min
+        self._single_channel(hw)
+        return hydraulics.dSf_dA(Q=Q, K=self.conveyance(hw), dK_dA=self.dK_dA(hw))
+
+    def dSf_dQ(self, h, Q):
+        hw = h + self.z_min
+        self._single_channel(hw)
+        return hydraulics.dSf_dQ(Q=Q, K=self.conveyance(hw))
+
+    def curvature_slope(self, h, Q):
+        if self.curvature == 0:
+            return 0.0
+        raise NotImplementedError("centre-line curvature at an IrregularSection node")
+
+    dSc_dA = dSc_dQ = lambda self, h, Q: 0.0 if abs(self.curvature) <= 1e-12 else self.curvature_slope(h, Q)
+
+    normal_flow = TrapezoidalSection.normal_flow
+    normal_depth = TrapezoidalSection.normal_depth
+
+
 def interpolate_cross_section(xs1, xs2, dist1, dist2):
     """Distance-weighted blend of two trapezoidal sections (cross_section.py:857-930).  Returns xs1 / xs2
     themselves when the location coincides with one of them."""
@@ -226,11 +374,21 @@ def interpolate_cross_section(xs1, xs2, dist1, dist2):
         return xs1
     if dist2 < 1e-9:
         return xs2
-    if not (isinstance(xs1, TrapezoidalSection) and isinstance(xs2, TrapezoidalSection)):
-        raise NotImplementedError("only TrapezoidalSection pairs can be interpolated (IrregularSection: SURVEY.md 8f-4)")
     w1, w2 = dist2 / total, dist1 / total
     mix = lambda a, b: a * w1 + b * w2
     slope = None if (xs1.bed_slope is None or xs2.bed_slope is None) else mix(xs1.bed_slope, xs2.bed_slope)
+    if not (isinstance(xs1, TrapezoidalSection) and isinstance(xs2, TrapezoidalSection)):
+        # a polyline on either side: blend bed elevations on the union of the lateral stations (cross_section.py:933-969)
+        if not all(hasattr(s, "z_at") for s in (xs1, xs2)):
+            raise NotImplementedError("interpolation between a TrapezoidalSection and an IrregularSection")
+        stations = [s.x for s in (xs1, xs2) if isinstance(s, IrregularSection)]
+        grid = np.union1d(stations[0], stations[1]) if len(stations) == 2 else stations[0]
+        bed = lambda s: np.array([s.z_at(v) for v in grid], dtype=float)
+        out = IrregularSection(x=grid, z=bed(xs1) * w1 + bed(xs2) * w2, n=mix(xs1.n_main, xs2.n_main), bed_slope=slope,
+                               curvature=mix(xs1.curvature, xs2.curvature))
+        out.set_roughness_para((mix(xs1.n_left, xs2.n_left), mix(xs1.n_main, xs2.n_main), mix(xs1.n_right, xs2.n_right),
+                                mix(xs1.left_fp_limit, xs2.left_fp_limit), mix(xs1.right_fp_limit, xs2.right_fp_limit)))
+        return out
     z_bed = mix(xs1.z_bed, xs2.z_bed)
     y1 = (xs1.z_bank - xs1.z_bed) if xs1._is_compound else 0.0
     y2 = (xs2.z_bank - xs2.z_bed) if xs2._is_compound else 0.0

@@ -92,3 +92,18 @@ def test_refused_combinations():
     flat = util.golden_inputs("irregular")
     with pytest.raises(PreissmannLibraryError, match="irregular"):
         gvf_initial_conditions(flat, 2, 60.0, 2.0)
+
+
+def test_mirror_solver_run_with_polyline_sections():
+    """The drop-in surface: IrregularSection objects on the mirror API, solver.run() on the device, the reference's
+    result arrays (derived arrays come from the host-side section objects, as in the reference)."""
+    from flow_sim_b200.cases import build_irregular
+
+    solver, kw = build_irregular()
+    solver.run(verbose=0, **kw)
+    ref = util.golden_outputs("irregular")
+    util.assert_parity(solver.depth, solver.flow, ref["depth"], ref["flow"], "mirror run, irregular")
+    assert np.array_equal(solver.iterations, ref["iters"])
+    assert solver.area.shape == solver.depth.shape and np.all(solver.top_width > 0) and np.all(solver.froude_number < 1)
+    with pytest.raises(ValueError, match="Convergence|NaN"):
+        build_irregular(bar=True)[0].run(verbose=0, **kw)

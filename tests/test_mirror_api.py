@@ -8,7 +8,7 @@ import pytest
 
 import util
 from flow_sim_b200 import abi, hydromodel
-from flow_sim_b200.cases import build_akbari, build_example, build_gerd
+from flow_sim_b200.cases import build_akbari, build_example, build_gerd, build_irregular
 from flow_sim_b200.cases import akbari_firoozi, gerd_roseires
 from flow_sim_b200.flatten import flatten_solver, load_flat, save_flat
 
@@ -40,6 +40,8 @@ def _same_flat(a, b):
     ("gerd_calib_m0", lambda: build_gerd(n_main=util.calib_n(0), calibration=True)),
     ("gerd_calib_m36408", lambda: build_gerd(n_main=util.calib_n(36408), calibration=True)),
     ("gerd_full", lambda: build_gerd()),
+    ("irregular", lambda: build_irregular()),
+    ("irregular_levee", lambda: build_irregular(bar=True)),
 ])
 def test_case_builders_reproduce_reference_inputs(case, builder):
     solver, kw = builder()
@@ -73,6 +75,32 @@ def test_general_storage_flattens_like_the_reference(tmp_path):
     assert np.array_equal(load_flat(p).down.storage_curve, flat.down.storage_curve)
 
 
+def test_irregular_section_mirror_equals_the_oracle_restatement():
+    """IrregularSection on the mirror API (host-side set-up code) against the oracle's restatement, which is
+    bit-identical with the live reference (oracle/ref_harness, checked when the goldens were made)."""
+    import oracle_py
+
+    solver, kw = build_irregular()
+    flat = flatten_solver(solver, **kw)
+    assert (flat.geom["kind"] == abi.PR_XS_IRREGULAR).all()
+    rng = np.random.default_rng(2)
+    for node in (0, 5, 12):
+        xs = solver.channel.xs_at_node[node]
+        for _ in range(25):
+            h, Q = rng.uniform(0.3, 5.5), rng.uniform(20, 200)
+            hw = h + xs.z_min
+            got = oracle_py.section_probe(flat, node, h, Q)
+            mine = dict(A=xs.area(hw), P=xs.wetted_perimeter(hw), T=xs.top_width(hw), K=xs.conveyance(hw),
+                        n_eq=xs.get_equivalent_n(hw), dR_dA=xs.dR_dA(hw), dK_dA=xs.dK_dA(hw), Sf=xs.friction_slope(h, Q),
+                        dSf_dA=xs.dSf_dA(h, Q), dSf_dQ=xs.dSf_dQ(h, Q))
+            for k, v in mine.items():
+                assert abs(got[k] - v) <= 1e-13 * abs(v), k
+    bar = build_irregular(bar=True)[0].channel.xs_at_node[4]
+    assert bar.sub_channels(bar.z_min + 1.0) == 2 and bar.sub_channels(bar.z_min + 4.0) == 1
+    with pytest.raises(NotImplementedError, match="sub-channels"):
+        bar.friction_slope(1.0, 60.0)
+
+
 def test_flat_roundtrip(tmp_path):
     solver, kw = build_gerd(n_main=0.03, calibration=True)
     flat = flatten_solver(solver, tolerance=kw["tolerance"])
@@ -80,6 +108,12 @@ def test_flat_roundtrip(tmp_path):
     save_flat(p, flat)
     _same_flat(flat, load_flat(p))
     assert load_flat(p).meta["downstream_depth"] == flat.meta["downstream_depth"]
+    solver, kw = build_irregular()
+    flat = flatten_solver(solver, **kw)
+    save_flat(p, flat)
+    back = load_flat(p)
+    _same_flat(flat, back)
+    assert back.geom["irr_offset"].dtype == np.int32 and np.array_equal(back.geom["irr_x"], flat.geom["irr_x"])
 
 
 def test_grid_sizing_matches_reference_rules():
