@@ -4,6 +4,7 @@
 //   * DFMA peak probe (roofline denominator)
 #pragma once
 #include "pr_device.cuh"
+#include "pr_irregular.cuh"
 
 namespace pr {
 
@@ -27,7 +28,13 @@ __device__ __forceinline__ double gvf_slope(const double* sg, int NP, int node, 
                                             const Rough& rg, const GvfParams& p, int& status) {
   const double g = p.g;
   NodeVals nv;
-  node_eval<CURV, RM, false, GvfParams>(sg, NP, node, h_in, Q, rg, p, nv);
+  if (p.geo.irr_offset && sg[F_KIND * NP + node] == (double)PR_XS_IRREGULAR) {
+    double top;
+    node_eval_irregular(p.geo, node, h_in, Q, rg, p, nv, nullptr, &top);
+    nv.T = top;                                   // the profile uses the geometric top width, not dA/dh
+  } else {
+    node_eval<CURV, RM, false, GvfParams>(sg, NP, node, h_in, Q, rg, p, nv);
+  }
   if (nv.T < 1e-6 || nv.A < 1e-6 || !(h_in > 0.0)) return 0.0;
   const double V = Q / fmax(nv.A, 1e-6), D = nv.A / fmax(nv.T, 1e-6);    // hydraulics.froude_num (:155-168)
   const double Fr = V / sqrt(g * fmax(D, 1e-6));

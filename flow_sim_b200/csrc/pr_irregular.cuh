@@ -78,9 +78,10 @@ __device__ inline double irr_sub_K(const double* x, const double* z, int n, doub
 
 // Everything the scheme needs from an irregular node: the counterpart of node_eval.
 //   T is Solver.dA_dh = the central difference of the area (:534-539), which is what the Jacobian uses.
+//   top_width (optional): the geometric top width of `properties`, which the GVF initial profile uses (channel.py:320).
 template <class KP>
 __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h, double Q, const Rough& rg, const KP& k,
-                                           NodeVals& o, NodeConv* kc) {
+                                           NodeVals& o, NodeConv* kc, double* top_width = nullptr) {
   const int off = g.irr_offset[node], n = g.irr_offset[node + 1] - off;
   const double* x = g.irr_x + off;
   const double* z = g.irr_z + off;
@@ -132,6 +133,7 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   o.w3 = k.hth * dSfQ;
   o.w4 = k.th_dx2 * QA;
   if (kc) { kc->K = K; kc->dKA = dKA; kc->A = A; kc->Sf = Sf; kc->dSfA = dSfA; kc->dSfQ = dSfQ; }
+  if (top_width) *top_width = T;
 }
 
 }  // namespace pr

@@ -428,11 +428,7 @@ int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const d
                               double* ic_depth, double* ic_flow, int32_t* status, void* cuda_stream) {
   if (int rc = check_config(cfg)) return rc;
   if (!q0 || !downstream_depth || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "q0 / downstream_depth / ic buffers are NULL");
-  {
-    bool irr = false;
-    if (int rc = any_irregular(*cfg, geom, irr)) return rc;
-    if (irr) return fail(PR_ERR_UNSUPPORTED, "GVF initial conditions on the device: irregular sections are not covered (use the host profile)");
-  }
+
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t N = cfg->n_nodes, M = cfg->n_members;
   Stage st(cfg->mem == PR_MEM_HOST, s);

@@ -8,7 +8,7 @@ import pytest
 
 import util
 from flow_sim_b200 import abi
-from flow_sim_b200.runner import run_flat
+from flow_sim_b200.runner import gvf_initial_conditions, run_flat
 
 pytestmark = pytest.mark.gpu
 
@@ -89,9 +89,37 @@ def test_refused_combinations():
     flat.geom = dict(flat.geom); flat.geom["curvature"] = np.full(flat.n_nodes, 1e-4)
     with pytest.raises(PreissmannLibraryError, match="curvature"):
         run_flat(flat)
+    from flow_sim_b200.runner import derived_results
     flat = util.golden_inputs("irregular")
     with pytest.raises(PreissmannLibraryError, match="irregular"):
-        gvf_initial_conditions(flat, 2, 60.0, 2.0)
+        derived_results(flat, np.full((1, flat.n_levels, flat.n_nodes), 2.0), np.full((1, flat.n_levels, flat.n_nodes), 60.0))
+
+
+def test_backwater_profile_and_roughness_sweep_on_polyline_sections():
+    """The calibration workflow on surveyed sections: device GVF profile per member (geometric top width, composite
+    roughness), then the ensemble solve from those profiles - against the oracle."""
+    import oracle_py
+    from flow_sim_b200.ensemble import EnsembleRunner, to_host
+
+    flat = util.golden_inputs("irregular")
+    M = 6
+    n_main = np.linspace(0.025, 0.04, M)
+    n_fp = np.linspace(0.05, 0.08, M)
+    flat.member_n_main, flat.member_n_fp = n_main, n_fp
+    q0, hd = np.linspace(50.0, 70.0, M), np.linspace(1.8, 2.4, M)
+    h, q, st = gvf_initial_conditions(flat, M, q0, hd)
+    ho, qo, sto = oracle_py.gvf(flat, q0, hd, n_members=M)
+    assert np.array_equal(st, sto) and not st.any()
+    assert util.max_rel(h, ho) <= 1e-12 and np.array_equal(q, qo)
+    flat.member_n_main = flat.member_n_fp = None
+    res = to_host(EnsembleRunner(flat, "cuda:0").roughness_sweep(n_main, n_fp=n_fp, downstream_depth=2.0, q0=60.0,
+                                                                  out_mode=abi.PR_OUT_FULL))
+    flat.member_n_main, flat.member_n_fp = n_main, n_fp
+    ho, qo, _ = oracle_py.gvf(flat, 60.0, 2.0, n_members=M)
+    flat.ic_depth, flat.ic_flow = ho, qo
+    ora = oracle_py.run(flat, n_members=M)
+    assert not res["status"].any() and np.array_equal(res["iters"], ora["iters"])
+    util.assert_parity(res["depth"], res["flow"], ora["depth"], ora["flow"], "roughness sweep on polyline sections")
 
 
 def test_mirror_solver_run_with_polyline_sections():
