@@ -23,13 +23,19 @@ def section(invert, shift, bar=False):
     return s
 
 
-def build(bar=False, levels=8):
+def build(bar=False, levels=8, curved=False):
     up = Boundary("flow_hydrograph", chainage=0, bed_level=BED_SLOPE * LENGTH, initial_depth=2.0,
                   hydrograph=Hydrograph(function=inflow))
     down = Boundary("fixed_depth", chainage=LENGTH, bed_level=0.0, initial_depth=2.0)
     ch = Channel(upstream_boundary=up, downstream_boundary=down, initial_flow=60.0, roughness=0.03, width=30.0,
                  interpolation_method="linear")
-    ch.set_cross_sections([0.0, LENGTH], [section(BED_SLOPE * LENGTH, 0.0, bar), section(0.0, 1.0, bar)])
+    if curved:      # an S-bend; curvature is computed at the interior input sections (channel.py:243-277)
+        sx = np.linspace(0.0, LENGTH, 25)
+        ch.set_coords(coords=np.column_stack([sx, 600.0 * np.sin(2 * np.pi * sx / LENGTH)]), chainages=sx * 1.0)
+        stations = [0.0, 4000.0, 8000.0, LENGTH]
+        ch.set_cross_sections(stations, [section(BED_SLOPE * (LENGTH - c), c / LENGTH, bar) for c in stations])
+    else:
+        ch.set_cross_sections([0.0, LENGTH], [section(BED_SLOPE * LENGTH, 0.0, bar), section(0.0, 1.0, bar)])
     solver = PreissmannSolver(channel=ch, theta=0.6, time_step=TIME_STEP, spatial_step=1000.0,
                               simulation_time=levels * TIME_STEP)
     return solver, dict(tolerance=1e-6, max_iter=60)

@@ -79,7 +79,7 @@ __device__ inline double irr_sub_K(const double* x, const double* z, int n, doub
 // Everything the scheme needs from an irregular node: the counterpart of node_eval.
 //   T is Solver.dA_dh = the central difference of the area (:534-539), which is what the Jacobian uses.
 //   top_width (optional): the geometric top width of `properties`, which the GVF initial profile uses (channel.py:320).
-template <class KP>
+template <class KP, bool CURV = false>
 __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h, double Q, const Rough& rg, const KP& k,
                                            NodeVals& o, NodeConv* kc, double* top_width = nullptr) {
   const int off = g.irr_offset[node], n = g.irr_offset[node + 1] - off;
@@ -108,9 +108,9 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   }
   // conveyance (:502-510), dR_dA (:524-532), dK_dA (:512-522 with hydraulics.dK_dA_, hydraulics.py:28-40)
   double K = 0.0, dKA = 0.0;
+  const double dRA = (A2 - A1) == 0.0 ? 0.0 : (R2 - R1) / (A2 - A1);
   if (A > 0.0) {
     K = A * pow(R, 2.0 / 3.0) / n_eq;
-    const double dRA = (A2 - A1) == 0.0 ? 0.0 : (R2 - R1) / (A2 - A1);
     dKA = (pow(R, 2.0 / 3.0) + A * 2. / 3. * pow(R, 2.0 / 3.0 - 1.0) * dRA) / n_eq;
   }
   // more than one wetted sub-channel (z < hw runs of >= 2 points): not evaluated
@@ -126,11 +126,39 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   if (runs > 1) Sf = nan("");
   const double dSfA = -2 * Sf * (dKA / K), dSfQ = 2 * absQ / (K * K);
   const double dAdh = (A2 - A1) / (2 * dh);
+  double Se = Sf, dSeA = dSfA, dSeQ = dSfQ;
+  if (CURV) {
+    // CrossSection.curvature_slope / dSc_dA / dSc_dQ (cross_section.py:143-175) with hydraulics.Sc, dSc_dA, dSc_dQ,
+    // froude_num, dFr_dA, dFr_dQ (hydraulics.py:94-204): geometric top width T, composite n, finite-difference dR/dA
+    const double curv = g.curv[node];
+    if (curv != 0.0) {
+      const double rc = 1.0 / curv, gg = k.g;
+      const double V = Q / fmax(A, 1e-6), D = A / fmax(T, 1e-6);
+      const double Fr = V / sqrt(gg * fmax(D, 1e-6));
+      const double C = pow(R, 1.0 / 6.0) / n_eq;
+      const double f = 8 * gg / (C * C), sqf = sqrt(f);
+      const double lead = 2.86 * sqf + 2.07 * f;
+      const double num = lead * (h * h) * (Fr * Fr), den = (0.565 + sqf) * (rc * rc);
+      Se += num / den;
+      if (fabs(curv) > 1e-12) {
+        const double Vu = Q / A, Du = A / T;                       // unclamped in the derivatives (quirk 7)
+        const double dFrA = -0.5 * Vu * pow(gg * Du, -1.5) * gg * (1.0 / T) + (-Q / (A * A)) * pow(gg * Du, -0.5);
+        const double dFrQ = (1.0 / A) * pow(gg * Du, -0.5);
+        const double dfA = -(8.0 / 3.0) * gg * (n_eq * n_eq) * pow(R, -4.0 / 3.0) * dRA;
+        const double dnumA = (2.86 / (2 * sqf) * dfA + 2.07 * dfA) * (h * h) * (Fr * Fr) +
+                             lead * (2 * h * (1. / T) * (Fr * Fr) + (h * h) * 2 * Fr * dFrA);
+        const double ddenA = (1.0 / (2 * sqf) * dfA) * (rc * rc);
+        dSeA += (dnumA * den - num * ddenA) / (den * den) * dAdh;  // already x dA_dh, multiplied again below (quirk 7)
+        const double dnumQ = lead * (h * h) * 2 * Fr * dFrQ;
+        dSeQ += (dnumQ * den - num * 0.0) / (den * den);
+      }
+    }
+  }
   const double QA = Q / A;
-  o.Q = Q; o.A = A; o.T = dAdh; o.Y = hw; o.Se = Sf; o.F = Q * QA; o.QA = QA;
+  o.Q = Q; o.A = A; o.T = dAdh; o.Y = hw; o.Se = Se; o.F = Q * QA; o.QA = QA;
   o.w1 = (k.th_dx * QA) * (QA * dAdh);
-  o.w2 = (k.hth * dSfA) * dAdh;
-  o.w3 = k.hth * dSfQ;
+  o.w2 = (k.hth * dSeA) * dAdh;
+  o.w3 = k.hth * dSeQ;
   o.w4 = k.th_dx2 * QA;
   if (kc) { kc->K = K; kc->dKA = dKA; kc->A = A; kc->Sf = Sf; kc->dSfA = dSfA; kc->dSfQ = dSfQ; }
   if (top_width) *top_width = T;

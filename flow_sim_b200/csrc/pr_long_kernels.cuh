@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
   NodeVals nv[2];
   // node pass of one node: arithmetic on the derived table, or polyline scans for an IrregularSection node
   auto eval_node = [&](int nd, double hh, double qv, NodeVals& out) {
-    if (IRR && q.geo[F_KIND * N + nd] == (double)PR_XS_IRREGULAR) node_eval_irregular(p.geo, nd, hh, qv, rg, p, out, nullptr);
+    if (IRR && q.geo[F_KIND * N + nd] == (double)PR_XS_IRREGULAR) node_eval_irregular<DevParams, CURV>(p.geo, nd, hh, qv, rg, p, out, nullptr);
     else node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, nd, hh, qv, rg, p, out);
   };
   eval_node(c0 < N ? c0 : N - 1, h[0], qq[0], nv[0]);
@@ -569,7 +569,8 @@ inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, 
       err = "lumped-storage head losses together with irregular sections";
       return PR_ERR_UNSUPPORTED;
     }
-    return long_reach_run_t<true, false, true>(p, s, launches, err);
+    return has_curv ? long_reach_run_t<true, true, true>(p, s, launches, err)
+                    : long_reach_run_t<true, false, true>(p, s, launches, err);
   }
   // centre-line curvature: compiled with the compound-section node pass only (a curved reach with floodplains is the
   // shipped gerd case; a curved prismatic reach takes the same kernels, the floodplain terms select to nothing)

@@ -374,7 +374,6 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
       has_irregular |= (kd == PR_XS_IRREGULAR);
     }
     if (has_irregular && !geom->irr_offset) return fail(PR_ERR_ARG, "geom: irregular sections without their polylines");
-    if (has_irregular && has_curv) return fail(PR_ERR_UNSUPPORTED, "centre-line curvature together with irregular sections");
   }
 
   if (int rc = stage_geom(*cfg, geom, st, p.geo)) return rc;
@@ -404,7 +403,7 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   auto fits = [&](int G, int M) { return (lpm == 0 || lpm == G) && cells <= (G - 1) * M; };
   int rc;
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
-  if (has_irregular) rc = pr::long_reach_run(p, false, true, true, s, g_launches, g_err);       // polyline node pass
+  if (has_irregular) rc = pr::long_reach_run(p, has_curv, true, true, s, g_launches, g_err);    // polyline node pass
   else if (lpm == -1) rc = pr::long_reach_run(p, has_curv, has_compound, false, s, g_launches, g_err);   // forced long-reach path
   else if (fits(8, 1)) rc = launch_family(pr::launch_ensemble_family<8, 1, 16>(p, has_curv, s));
   else if (fits(8, 2)) rc = launch_family(pr::launch_ensemble_family<8, 2, 16>(p, has_curv, s));

@@ -148,8 +148,6 @@ def flatten_geometry(channel) -> dict:
         geom["irr_z"] = np.concatenate([p[1] for p in polys])
         geom["irr_left"] = np.array([p[2] for p in polys], dtype=np.float64)
         geom["irr_right"] = np.array([p[3] for p in polys], dtype=np.float64)
-        if np.any((geom["kind"] == abi.PR_XS_IRREGULAR) & (geom["curvature"] != 0.0)):
-            raise NotImplementedError("centre-line curvature at an IrregularSection node")
     return geom
 
 

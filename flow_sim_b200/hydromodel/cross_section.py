@@ -355,13 +355,10 @@ class IrregularSection(CrossSection):
         self._single_channel(hw)
         return hydraulics.dSf_dQ(Q=Q, K=self.conveyance(hw))
 
-    def curvature_slope(self, h, Q):
-        if self.curvature == 0:
-            return 0.0
-        raise NotImplementedError("centre-line curvature at an IrregularSection node")
-
-    dSc_dA = dSc_dQ = lambda self, h, Q: 0.0 if abs(self.curvature) <= 1e-12 else self.curvature_slope(h, Q)
-
+    # the curvature slope only needs properties / n_eq / dR_dA / dA_dh, which both section families provide
+    curvature_slope = TrapezoidalSection.curvature_slope
+    dSc_dA = TrapezoidalSection.dSc_dA
+    dSc_dQ = TrapezoidalSection.dSc_dQ
     normal_flow = TrapezoidalSection.normal_flow
     normal_depth = TrapezoidalSection.normal_depth
 

@@ -64,6 +64,7 @@ static xs_t xs_load(const pr_geom* g, int i, int member) {
 
 
 static double hy_conveyance(double A, double n, double R);
+static double xs_dA_dh(const xs_t* s, double hw);
 
 /* ---------------- IrregularSection (cross_section.py:207-543) ---------------- */
 
@@ -428,7 +429,7 @@ static double xs_dSc_dA(const xs_t* s, double g, double h, double Q) {
   double A, P, R, T;
   xs_properties(s, hw, &A, &P, &R, &T);
   double dR = xs_dR_dA(s, hw);
-  return hy_dSc_dA(g, h, A, Q, n, R, 1.0 / s->curv, dR, T) * T;   /* quirk 7: already x dA_dh */
+  return hy_dSc_dA(g, h, A, Q, n, R, 1.0 / s->curv, dR, T) * xs_dA_dh(s, hw);   /* quirk 7: already x dA_dh (= T for trapezoids) */
 }
 static double xs_dSc_dQ(const xs_t* s, double g, double h, double Q) {
   if (fabs(s->curv) <= 1e-12) return 0.0;

@@ -287,7 +287,7 @@ if __name__ == "__main__":
     print("example iters", r["iters"].tolist(), r["depth"].sum(), r["flow"].sum(), r["seconds"])
 
 
-def build_irregular(levee: bool = False):
+def build_irregular(levee: bool = False, curved: bool = False):
     """Synthetic companion case for IrregularSection (no shipped case instantiates it): a 12 km
     reach between two surveyed-style polylines with composite roughness, interpolated node by node
     (cross_section.py:933-969), flow hydrograph upstream, fixed depth downstream."""
@@ -317,6 +317,13 @@ def build_irregular(levee: bool = False):
         s.set_roughness_para((0.05, 0.03, 0.06, 14.0 + shift, 36.0 + shift))
         return s
 
-    ch.set_cross_sections([0.0, L], [sec(S0 * L, 0.0), sec(0.0, 1.0)])
+    if curved:          # a gentle S-bend: centre-line coordinates -> per-node curvature (channel.py:243-277)
+        sx = np.linspace(0.0, L, 25)
+        ch.set_coords(coords=np.column_stack([sx, 600.0 * np.sin(2 * np.pi * sx / L)]), chainages=sx * 1.0)
+    if curved:          # curvature is computed at the interior input sections only (channel.py:243-277)
+        stations = [0.0, 4000.0, 8000.0, L]
+        ch.set_cross_sections(stations, [sec(S0 * (L - c), c / L) for c in stations])
+    else:
+        ch.set_cross_sections([0.0, L], [sec(S0 * L, 0.0), sec(0.0, 1.0)])
     solver = PreissmannSolver(channel=ch, theta=0.6, time_step=dt, spatial_step=1000.0, simulation_time=8 * dt)
     return solver, dict(tolerance=1e-6, max_iter=60)

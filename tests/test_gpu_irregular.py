@@ -23,6 +23,17 @@ def test_irregular_reach_matches_the_reference_run():
     assert np.array_equal(out["iters"][0], ref["iters"])
 
 
+def test_polyline_sections_on_a_curved_centre_line():
+    """Curvature slope Sc at polyline nodes (geometric top width, composite n, finite-difference dR/dA): the reference's
+    run of the curved companion reach; the curvature moves the stages by 6e-6 m, four orders above the parity bar."""
+    flat = util.golden_inputs("irregular_curved")
+    ref = util.golden_outputs("irregular_curved")
+    assert np.count_nonzero(flat.geom["curvature"]) == 10
+    out = run_flat(flat)
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], "irregular, curved")
+    assert np.array_equal(out["iters"][0], ref["iters"])
+
+
 def test_irregular_ensemble_roughness_and_inflow_members():
     import oracle_py
 
@@ -85,10 +96,6 @@ def test_refused_combinations():
     from flow_sim_b200.abi import PreissmannLibraryError
     from flow_sim_b200.runner import gvf_initial_conditions
 
-    flat = util.golden_inputs("irregular")
-    flat.geom = dict(flat.geom); flat.geom["curvature"] = np.full(flat.n_nodes, 1e-4)
-    with pytest.raises(PreissmannLibraryError, match="curvature"):
-        run_flat(flat)
     from flow_sim_b200.runner import derived_results
     flat = util.golden_inputs("irregular")
     with pytest.raises(PreissmannLibraryError, match="irregular"):

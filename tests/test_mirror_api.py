@@ -42,6 +42,7 @@ def _same_flat(a, b):
     ("gerd_full", lambda: build_gerd()),
     ("irregular", lambda: build_irregular()),
     ("irregular_levee", lambda: build_irregular(bar=True)),
+    ("irregular_curved", lambda: build_irregular(curved=True)),
 ])
 def test_case_builders_reproduce_reference_inputs(case, builder):
     solver, kw = builder()
