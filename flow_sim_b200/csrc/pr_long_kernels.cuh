@@ -420,7 +420,8 @@ __global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
       const Rough rg = load_rough<4>(p.geo, m);
       NodeVals t;
       NodeConv kc;
-      node_eval<false, 4, true>(q.geo, p.N, nd, h, qv, rg, p, t, &kc);
+      if (p.geo.irr_offset && q.geo[F_KIND * p.N + nd] == (double)PR_XS_IRREGULAR) node_eval_irregular(p.geo, nd, h, qv, rg, p, t, &kc);
+      else node_eval<false, 4, true>(q.geo, p.N, nd, h, qv, rg, p, t, &kc);
       const double V = qv / kc.A;
       st -= kc.Sf * p.dn.st_length + p.dn.st_kq * (V * V) / (2.0 * p.g);
     }
@@ -565,10 +566,6 @@ inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, 
                           std::atomic<long long>& launches, std::string& err) {
   // IrregularSection nodes: one more set of kernels (compound arithmetic for the trapezoid nodes of a mixed reach).
   if (has_irregular) {
-    if (p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses) {
-      err = "lumped-storage head losses together with irregular sections";
-      return PR_ERR_UNSUPPORTED;
-    }
     return has_curv ? long_reach_run_t<true, true, true>(p, s, launches, err)
                     : long_reach_run_t<true, false, true>(p, s, launches, err);
   }

@@ -142,3 +142,20 @@ def test_mirror_solver_run_with_polyline_sections():
     assert solver.area.shape == solver.depth.shape and np.all(solver.top_width > 0) and np.all(solver.froude_number < 1)
     with pytest.raises(ValueError, match="Convergence|NaN"):
         build_irregular(bar=True)[0].run(verbose=0, **kw)
+
+
+def test_general_storage_with_head_losses_behind_a_polyline_node():
+    """Area curve + outflow curve + head losses (friction over the reservoir length uses the polyline node's
+    conveyance, composite n and dA/dh) - the downstream boundary of the storage_general case on the polyline reach."""
+    import oracle_py
+
+    flat = util.golden_inputs("irregular")
+    flat.down = copy.copy(util.golden_inputs("storage_general").down)
+    flat.down.fixed_depth = 2.0
+    flat.down.storage_ymax = 200.0
+    ora = oracle_py.run(flat)
+    out = run_flat(flat)
+    assert np.array_equal(out["status"], ora["status"]) and out["status"][0] == 0
+    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "storage with losses, polyline reach")
+    assert np.array_equal(out["iters"], ora["iters"])
+    assert util.max_rel(out["storage_stage"], ora["storage_stage"]) <= util.RTOL
