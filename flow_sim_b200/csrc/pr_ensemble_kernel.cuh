@@ -23,6 +23,7 @@
 // ping-pong so that an iteration that turns out to be the converged one costs no re-evaluation.
 #pragma once
 #include "pr_device.cuh"
+#include "pr_irregular.cuh"
 
 namespace pr {
 
@@ -121,7 +122,7 @@ __host__ __device__ constexpr size_t ensemble_smem_bytes() {
   return sizeof(double) * ((size_t)F_COUNT * G * M + (size_t)W * warp_smem_doubles<M>());
 }
 
-template <int G, int M, int W, bool CURV, int RM, bool EXACT, bool GST>
+template <int G, int M, int W, bool CURV, int RM, bool EXACT, bool GST, bool IRR = false>
 __global__ void __launch_bounds__(W * 32, 1)
 pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ double smem[];
@@ -210,7 +211,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     if (GST && p.dn.type == PR_BC_FIXED_DEPTH_STORAGE && p.dn.st_losses && owns_last) {
       NodeVals t;
       NodeConv kc;
-      node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
+      if (IRR && sg[F_KIND * NP + slot_last * G + gl] == (double)PR_XS_IRREGULAR) node_eval_irregular_call<CURV>(p.geo, N - 1, hl, ql, rg, k, t, &kc);
+      else node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
       const double V = ql / kc.A;
       stage_prev -= kc.Sf * p.dn.st_length + p.dn.st_kq * (V * V) / (2.0 * p.g);     // initial stage = Y - energy_loss
     }
@@ -233,6 +235,14 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 #define PC(c, j) pcw[((c)*M + (j)) * 32 + lane]
 #define EL(j, c) elw[((j)*9 + (c)) * 32 + lane]
 #define XW(c, l) xw[(c)*32 + (l)]
+// Node pass of slot (j, gl) = node gl*M + j.  IRR kernels send IrregularSection nodes to the polyline scans.
+#define PR_NODE(WANTK, j, hh, qq_, out, kcp)                                                                       \
+  do {                                                                                                            \
+    if (IRR && sg[F_KIND * NP + (j)*G + gl] == (double)PR_XS_IRREGULAR)                                            \
+      node_eval_irregular_call<CURV>(p.geo, (gl * M + (j) < N ? gl * M + (j) : N - 1), (hh), (qq_), rg, k, (out), (kcp)); \
+    else                                                                                                          \
+      node_eval<CURV, RM, WANTK>(sg, NP, (j)*G + gl, (hh), (qq_), rg, k, (out), (kcp));                            \
+  } while (0)
 
   // Node pass at the current state that only (re)builds the level constants: once for the initial state and once
   // per accepted level.  Cheaper than producing candidates in every Newton iteration (one extra node pass per
@@ -240,14 +250,14 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   bool commit = true;      // G < 32: which lanes take the refreshed constants
   auto refresh_level_constants = [&]() {
     NodeVals left, right;
-    node_eval<CURV, RM>(sg, NP, gl, h[0], q[0], rg, k, left);
+    PR_NODE(false, 0, h[0], q[0], left, nullptr);
     __syncwarp();
     XW(0, lane) = left.Q;  XW(1, lane) = left.A;  XW(3, lane) = left.Y;  XW(4, lane) = left.Se;  XW(5, lane) = left.QA;
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       if (j + 1 < M) {
-        node_eval<CURV, RM>(sg, NP, (j + 1) * G + gl, h[j + 1], q[j + 1], rg, k, right);
+        PR_NODE(false, j + 1, h[j + 1], q[j + 1], right, nullptr);
       } else {
         const int nl = (lane + 1) & 31;
         right.Q = XW(0, nl);  right.A = XW(1, nl);  right.Y = XW(3, nl);  right.Se = XW(4, nl);
@@ -272,7 +282,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
     // ------------------------------ node + cell pass ------------------------------
     NodeVals left, right;
-    node_eval<CURV, RM>(sg, NP, gl, h[0], q[0], rg, k, left);
+    PR_NODE(false, 0, h[0], q[0], left, nullptr);
     // hand the first node to the lane on the left: it closes that lane's last cell
     __syncwarp();
     XW(0, lane) = left.Q;  XW(1, lane) = left.A;  XW(2, lane) = left.T;  XW(3, lane) = left.Y;  XW(4, lane) = left.Se;
@@ -284,7 +294,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       if (j + 1 < M) {
-        node_eval<CURV, RM>(sg, NP, (j + 1) * G + gl, h[j + 1], q[j + 1], rg, k, right);
+        PR_NODE(false, j + 1, h[j + 1], q[j + 1], right, nullptr);
       } else {
         const int nl = (lane + 1) & 31;
         right.Q = XW(0, nl);  right.A = XW(1, nl);  right.T = XW(2, nl);  right.Y = XW(3, nl);  right.Se = XW(4, nl);
@@ -318,7 +328,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       double T0 = 0.0;
       if (up_normal) {
         NodeVals t;
-        node_eval<CURV, RM, true>(sg, NP, gl, h[0], q[0], rg, k, t, &kc);
+        PR_NODE(true, 0, h[0], q[0], t, &kc);
         T0 = t.T;
       }
       U = bc_eval<false>(p.up, member, level, hyd_up, h[0], q[0], 0.0, 0.0, p.dt, p.g, kc, T0);
@@ -341,7 +351,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       double T0 = 0.0;
       if (dn_normal) {
         NodeVals t;
-        node_eval<CURV, RM, true>(sg, NP, slot_last * G + gl, hl, ql, rg, k, t, &kc);
+        PR_NODE(true, slot_last, hl, ql, t, &kc);
         T0 = t.T;
       }
       D = bc_eval<GST>(p.dn, member, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, p.g, kc, T0, GST ? &gate : nullptr);
@@ -484,6 +494,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 #undef PC
 #undef EL
 #undef XW
+#undef PR_NODE
   if (member_valid && is_first) {
     if (p.status) p.status[member] = status;
     if (p.fail_level) p.fail_level[member] = fail_level;
@@ -536,6 +547,29 @@ int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
   template <>                                                                                                \
   int launch_ensemble_family<G_, M_, W_>(const DevParams& p, bool curv, cudaStream_t s) {                    \
     return curv ? launch_rm_##G_##_##M_<true>(p, s) : launch_rm_##G_##_##M_<false>(p, s);                    \
+  }                                                                                                          \
+  }
+
+// IrregularSection reaches of up to 249 nodes: one build per nodes-per-lane count and curvature setting (run-time
+// roughness mode, every boundary type, 32 lanes per member).
+template <int M>
+int launch_ensemble_irregular(const DevParams& p, bool curv, cudaStream_t s);
+
+#define PR_DEFINE_ENSEMBLE_IRREGULAR(M_, W_)                                                                 \
+  namespace pr {                                                                                             \
+  template <bool CURV>                                                                                       \
+  static int launch_irr_##M_(const DevParams& p, cudaStream_t s) {                                           \
+    constexpr size_t smem = ensemble_smem_bytes<32, M_, W_>();                                               \
+    static_assert(smem <= 227 * 1024, "shared memory budget exceeded");                                      \
+    auto kern = pr_ensemble_kernel<32, M_, W_, CURV, 4, false, true, true>;                                  \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return (int)e;                                                                     \
+    kern<<<(unsigned)((p.M + W_ - 1) / W_), W_ * 32, smem, s>>>(p);                                          \
+    return (int)cudaGetLastError();                                                                          \
+  }                                                                                                          \
+  template <>                                                                                                \
+  int launch_ensemble_irregular<M_>(const DevParams& p, bool curv, cudaStream_t s) {                         \
+    return curv ? launch_irr_##M_<true>(p, s) : launch_irr_##M_<false>(p, s);                                \
   }                                                                                                          \
   }
 

@@ -164,4 +164,11 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   if (top_width) *top_width = T;
 }
 
+// Out-of-line entry for kernels with many node-pass call sites (the fused ensemble kernel): one copy of the scans.
+template <bool CURV>
+__device__ __noinline__ void node_eval_irregular_call(const DevGeom& g, int node, double h, double Q, const Rough& rg,
+                                                      const DevParams& k, NodeVals& o, NodeConv* kc) {
+  node_eval_irregular<DevParams, CURV>(g, node, h, Q, rg, k, o, kc);
+}
+
 }  // namespace pr

@@ -403,7 +403,13 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   auto fits = [&](int G, int M) { return (lpm == 0 || lpm == G) && cells <= (G - 1) * M; };
   int rc;
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
-  if (has_irregular) rc = pr::long_reach_run(p, has_curv, true, true, s, g_launches, g_err);    // polyline node pass
+  if (has_irregular && lpm != -1 && cells <= 31 * 8) {        // polyline node pass inside the fused kernel
+    const int m = (cells + 30) / 31;
+    if (m <= 1) rc = launch_family(pr::launch_ensemble_irregular<1>(p, has_curv, s));
+    else if (m <= 2) rc = launch_family(pr::launch_ensemble_irregular<2>(p, has_curv, s));
+    else if (m <= 4) rc = launch_family(pr::launch_ensemble_irregular<4>(p, has_curv, s));
+    else rc = launch_family(pr::launch_ensemble_irregular<8>(p, has_curv, s));
+  } else if (has_irregular) rc = pr::long_reach_run(p, has_curv, true, true, s, g_launches, g_err);   // ... or the tile kernels
   else if (lpm == -1) rc = pr::long_reach_run(p, has_curv, has_compound, false, s, g_launches, g_err);   // forced long-reach path
   else if (fits(8, 1)) rc = launch_family(pr::launch_ensemble_family<8, 1, 16>(p, has_curv, s));
   else if (fits(8, 2)) rc = launch_family(pr::launch_ensemble_family<8, 2, 16>(p, has_curv, s));

@@ -13,11 +13,12 @@ from flow_sim_b200.runner import gvf_initial_conditions, run_flat
 pytestmark = pytest.mark.gpu
 
 
-def test_irregular_reach_matches_the_reference_run():
+@pytest.mark.parametrize("lanes", [0, -1])       # fused kernel (N <= 249) / tiled long-reach kernels
+def test_irregular_reach_matches_the_reference_run(lanes):
     flat = util.golden_inputs("irregular")
     ref = util.golden_outputs("irregular")
     assert (flat.geom["kind"] == abi.PR_XS_IRREGULAR).all() and flat.geom["irr_offset"][-1] == 192
-    out = run_flat(flat)
+    out = run_flat(flat, lanes=lanes)
     assert out["status"][0] == abi.PR_STATUS_OK
     util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], "irregular")
     assert np.array_equal(out["iters"][0], ref["iters"])
@@ -29,9 +30,10 @@ def test_polyline_sections_on_a_curved_centre_line():
     flat = util.golden_inputs("irregular_curved")
     ref = util.golden_outputs("irregular_curved")
     assert np.count_nonzero(flat.geom["curvature"]) == 10
-    out = run_flat(flat)
-    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], "irregular, curved")
-    assert np.array_equal(out["iters"][0], ref["iters"])
+    for lanes in (0, -1):
+        out = run_flat(flat, lanes=lanes)
+        util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], f"irregular, curved, lanes={lanes}")
+        assert np.array_equal(out["iters"][0], ref["iters"])
 
 
 def test_irregular_ensemble_roughness_and_inflow_members():
@@ -44,10 +46,11 @@ def test_irregular_ensemble_roughness_and_inflow_members():
     base = np.array(flat.up.series)
     flat.up.series = np.stack([base[0] + (base - base[0]) * (0.5 + 0.25 * m) for m in range(M)])
     ora = oracle_py.run(flat, n_members=M)
-    out = run_flat(flat, n_members=M)
-    assert np.array_equal(out["status"], ora["status"]) and not out["status"].any()
-    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "irregular ensemble")
-    assert np.array_equal(out["iters"], ora["iters"])
+    for lanes in (0, -1):
+        out = run_flat(flat, n_members=M, lanes=lanes)
+        assert np.array_equal(out["status"], ora["status"]) and not out["status"].any()
+        util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], f"irregular ensemble, lanes={lanes}")
+        assert np.array_equal(out["iters"], ora["iters"])
 
 
 def test_mixed_reach_and_other_boundaries():
@@ -159,3 +162,34 @@ def test_general_storage_with_head_losses_behind_a_polyline_node():
     util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "storage with losses, polyline reach")
     assert np.array_equal(out["iters"], ora["iters"])
     assert util.max_rel(out["storage_stage"], ora["storage_stage"]) <= util.RTOL
+
+
+def test_long_polyline_reach_on_the_tile_kernels():
+    """N = 301 > 249: the polyline reach stretched to 300 km goes to the tiled path on its own."""
+    import oracle_py
+
+    flat = util.golden_inputs("irregular")
+    N = 301
+    g = flat.geom
+    src = np.minimum(np.arange(N) * flat.n_nodes // N, flat.n_nodes - 1)       # repeat the 13 sections along the reach
+    off = g["irr_offset"]
+    geom = {k: np.array(v)[src] for k, v in g.items() if not k.startswith("irr_") }
+    geom["z_bed"] = g["z_bed"][0] * (1.0 - np.arange(N) / (N - 1))              # uniform slope
+    xs, zs, offs = [], [], [0]
+    for i, s_ in enumerate(src):
+        seg = slice(off[s_], off[s_ + 1])
+        xs.append(g["irr_x"][seg]); zs.append(g["irr_z"][seg] - g["z_bed"][s_] + geom["z_bed"][i])
+        offs.append(offs[-1] + len(xs[-1]))
+    geom["irr_x"], geom["irr_z"] = np.concatenate(xs), np.concatenate(zs)
+    geom["irr_offset"] = np.array(offs, dtype=np.int32)
+    geom["irr_left"], geom["irr_right"] = g["irr_left"][src], g["irr_right"][src]
+    flat.geom, flat.n_nodes = geom, N
+    flat.ic_depth, flat.ic_flow = np.full(N, 2.0), np.full(N, 60.0)
+    flat.up.bed_level = float(geom["z_bed"][0])
+    flat.n_levels = 4
+    flat.up.series = flat.up.series[:4]
+    ora = oracle_py.run(flat)
+    out = run_flat(flat)
+    assert np.array_equal(out["status"], ora["status"]) and out["status"][0] == 0
+    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "N=301 polyline reach")
+    assert np.array_equal(out["iters"], ora["iters"])
