@@ -55,11 +55,41 @@ struct LongParams {
   int T, Kc;
 };
 
-enum LongMode { LONG_INIT = 0, LONG_CONDENSE = 1, LONG_UPDATE = 2 };
-
-__global__ void pr_long_geometry(DevGeom g, int N, double* table) {
+static __global__ void pr_long_geometry(DevGeom g, int N, double* table) {
   stage_geometry(g, N, N, table, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, [](int i) { return i; });
 }
+
+struct LongWorkspace {
+  static constexpr int kSlots = 32;
+  void* ptr[kSlots] = {};
+  size_t bytes[kSlots] = {};
+  int device = -1;
+  void release() {
+    for (int i = 0; i < kSlots; ++i) { if (ptr[i]) cudaFree(ptr[i]); ptr[i] = nullptr; bytes[i] = 0; }
+  }
+  void* get(int slot, size_t n, cudaError_t& e) {
+    if (e != cudaSuccess) return nullptr;
+    if (slot < 0 || slot >= kSlots) { e = cudaErrorInvalidValue; return nullptr; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != device) { release(); device = dev; }
+    if (bytes[slot] < n) {
+      if (ptr[slot]) cudaFree(ptr[slot]);
+      ptr[slot] = nullptr; bytes[slot] = 0;
+      e = cudaMalloc(&ptr[slot], n);
+      if (e == cudaSuccess) bytes[slot] = n;
+    }
+    return ptr[slot];
+  }
+};
+inline LongWorkspace& long_workspace() { static LongWorkspace w; return w; }
+
+template <bool CMP, bool CURV, bool IRR>
+int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches, std::string& err);
+
+#ifndef PR_LONG_DECLARE_ONLY   // the kernels and the driver loop: compiled once per variant in pr_long_v*.cu
+enum LongMode { LONG_INIT = 0, LONG_CONDENSE = 1, LONG_UPDATE = 2 };
+
 
 // PCR over the 32 lanes of a warp for block rows  [l | d | u] y = r  with rank-1 couplings (see the fused kernel).
 __device__ __forceinline__ void pcr32(double& l1, double& l2, double& d11, double& d12, double& d21, double& d22,
@@ -391,14 +421,14 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
 }
 
 // After K3: retire members whose last level was just accepted.
-__global__ void pr_long_retire(const __grid_constant__ LongParams q) {
+static __global__ void pr_long_retire(const __grid_constant__ LongParams q) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= q.p.M) return;
   if (q.active[m] == 1 && q.level[m] >= q.p.L) { q.active[m] = 0; atomicAdd(q.n_done, 1); }
   if (q.active[m] == 2) q.active[m] = 0;
 }
 
-__global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
+static __global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)p.M * p.N;
@@ -436,7 +466,7 @@ __global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
 }
 
 // NaN-fill the levels a failed member never reached.
-__global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
+static __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const int m = blockIdx.y;
   if (!p.status || p.status[m] == PR_STATUS_OK) return;
@@ -459,33 +489,8 @@ __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
 
 // Grow-only device workspace of the long-reach path, kept between calls (allocating and freeing ~7 GB per call
 // costs 50-200 ms); released by pr_release_workspace() or at process exit by the driver.
-struct LongWorkspace {
-  static constexpr int kSlots = 32;
-  void* ptr[kSlots] = {};
-  size_t bytes[kSlots] = {};
-  int device = -1;
-  void release() {
-    for (int i = 0; i < kSlots; ++i) { if (ptr[i]) cudaFree(ptr[i]); ptr[i] = nullptr; bytes[i] = 0; }
-  }
-  void* get(int slot, size_t n, cudaError_t& e) {
-    if (e != cudaSuccess) return nullptr;
-    if (slot < 0 || slot >= kSlots) { e = cudaErrorInvalidValue; return nullptr; }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != device) { release(); device = dev; }
-    if (bytes[slot] < n) {
-      if (ptr[slot]) cudaFree(ptr[slot]);
-      ptr[slot] = nullptr; bytes[slot] = 0;
-      e = cudaMalloc(&ptr[slot], n);
-      if (e == cudaSuccess) bytes[slot] = n;
-    }
-    return ptr[slot];
-  }
-};
-inline LongWorkspace& long_workspace() { static LongWorkspace w; return w; }
-
 template <bool CMP, bool CURV, bool IRR>
-inline int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches,
+int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches,
                             std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
   const int N = p.N, M = p.M;
@@ -561,6 +566,8 @@ inline int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, std::string("long-reach path: ") + cudaGetErrorString(e));
   return PR_OK;
 }
+
+#endif  // PR_LONG_DECLARE_ONLY
 
 inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, bool has_irregular, cudaStream_t s,
                           std::atomic<long long>& launches, std::string& err) {

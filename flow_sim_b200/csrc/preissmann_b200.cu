@@ -16,6 +16,7 @@
 
 #include "pr_aux_kernels.cuh"
 #include "pr_ensemble_kernel.cuh"
+#define PR_LONG_DECLARE_ONLY   // the long-reach kernels are compiled in pr_long_v*.cu
 #include "pr_long_kernels.cuh"
 
 #ifndef PR_W4
