@@ -203,8 +203,6 @@ def test_general_lumped_storage_variants_vs_oracle():
 
 def test_general_storage_and_gate_control_with_both_roughness_overrides():
     """The rare-boundary kernels decide the roughness overrides at run time: per-member n_main AND n_fp."""
-    from test_gpu_ensemble import _prismatic as prism
-
     flat = util.golden_inputs("gerd_gated")
     flat.member_n_main = np.array([0.028, 0.030, 0.034])
     flat.member_n_fp = np.array([0.04, 0.05, 0.06])

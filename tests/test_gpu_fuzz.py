@@ -4,7 +4,6 @@ import numpy as np
 import pytest
 
 import util
-from flow_sim_b200 import abi
 from flow_sim_b200.runner import run_flat
 
 pytestmark = pytest.mark.gpu

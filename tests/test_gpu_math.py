@@ -1,5 +1,4 @@
 """Accuracy of the device's branch-free FP64 primitives (csrc/pr_device.cuh) against IEEE results."""
-import ctypes as C
 
 import numpy as np
 import pytest

@@ -4,7 +4,6 @@ import numpy as np
 import pytest
 
 import util
-from flow_sim_b200 import abi
 from flow_sim_b200.runner import derived_results, normal_depth_initial_conditions, run_flat
 
 pytestmark = pytest.mark.gpu

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """HBM roofline of the derived-results kernel (Solver.prepare_results arrays): 16 B in + 48 B out per (member, level, node)."""
 import json, os, sys
-import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import torch

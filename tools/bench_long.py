@@ -41,7 +41,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from flow_sim_b200 import abi
-    from flow_sim_b200.cases.akbari_firoozi import BASE_FLOW, build_long_reach, flood_wave
+    from flow_sim_b200.cases.akbari_firoozi import build_long_reach, flood_wave
     from flow_sim_b200.ensemble import EnsembleRunner, gather_members, shard_members
     from flow_sim_b200.flatten import flatten_solver
 
