@@ -59,3 +59,29 @@ def test_config5_full_long_reach_members_vs_oracle():
         ora = oracle_py.run(flat, n_members=1, out_mode=abi.PR_OUT_UPSTREAM)
         util.assert_parity(res["depth"][m], res["flow"][m], ora["depth"][0], ora["flow"][0], f"scenario {m}")
         assert np.array_equal(res["iters"][m], ora["iters"][0])
+
+
+@pytest.mark.parametrize("case", ["example", "akbari"])
+def test_packed_warp_kernels_at_scale(case):
+    """Configs 1 and 2 as 4 096-member ensembles (4 / 2 members per warp) with a random flood peak and roughness per
+    member - the initial state is the case's own, so warp-mates converge at different moments and a good share of the
+    members fails outright somewhere in the run: status, failure level and every surviving member against the oracle."""
+    import oracle_py
+    from flow_sim_b200.runner import run_flat
+
+    flat = util.golden_inputs(case)
+    M = 4096
+    base = np.array(flat.up.series)
+    rng = np.random.default_rng(11)
+    scale = 0.5 + 1.5 * rng.random(M)
+    flat.up.series = base[0] + (base - base[0])[None, :] * scale[:, None]
+    flat.member_n_main = rng.uniform(0.018, 0.05, M)
+    ora = oracle_py.run(flat, n_members=M, out_mode=abi.PR_OUT_UPSTREAM)
+    out = run_flat(flat, n_members=M, out_mode=abi.PR_OUT_UPSTREAM)
+    assert np.array_equal(out["status"], ora["status"]) and np.array_equal(out["fail_level"], ora["fail_level"])
+    ok = ora["status"] == 0
+    assert 0.4 * M < ok.sum() < M
+    util.assert_parity(out["depth"][ok], out["flow"][ok], ora["depth"][ok], ora["flow"][ok], f"{case} x {M}")
+    mism = int((out["iters"][ok] != ora["iters"][ok]).sum())
+    assert mism <= 1, f"{mism} iteration-count mismatches in {int(ok.sum()) * out['iters'].shape[1]} level-steps"
+    assert len({tuple(r) for r in ora["iters"][ok]}) > 20
