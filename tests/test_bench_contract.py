@@ -23,3 +23,27 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_one_contract_line():
+    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--members", "512", "--steps", "2", "--warmup", "3",
+                        "--cpu-members-per-core", "1"], capture_output=True, text=True, timeout=900, cwd=REPO)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert "impl" not in d or d["impl"] != "reference"
+    assert d["unit"] == "node-steps/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 0
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["gpu_launches"] == 2 * 3                       # GVF + Newton + objective kernels per step
+    e2e, roof, cb, clk = d["e2e"], d["roofline"], d["cpu_baseline"], d["clocks"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 512 * 8 and e2e["d2h_bytes_per_step"] > 0
+    assert roof["unit"] == "TFLOP/s" and 0 < roof["frac"] < 1 and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
+    assert "sm_mhz" in clk and "reasons" in clk
+    par = d["parity"]
+    assert par["iterations_equal"] is True and par["max_rel_depth"] < 1e-9 and par["max_rel_flow"] < 1e-9
