@@ -22,6 +22,7 @@
 // 112 B (iterate read twice + 4 level constants per cell read twice + iterate written).
 #pragma once
 #include <atomic>
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -61,6 +62,7 @@ static __global__ void pr_long_geometry(DevGeom g, int N, double* table) {
 
 struct LongWorkspace {
   static constexpr int kSlots = 32;
+  std::mutex mu;            // one long-reach run at a time per process: the cached buffers are shared
   void* ptr[kSlots] = {};
   size_t bytes[kSlots] = {};
   int device = -1;
@@ -493,6 +495,7 @@ template <bool CMP, bool CURV, bool IRR>
 int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches,
                             std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
+  std::lock_guard<std::mutex> workspace_lock(long_workspace().mu);
   const int N = p.N, M = p.M;
   const int T = (N - 1 + kTileCells - 1) / kTileCells;
   const int Kc = (T + 30) / 31;           // tile cells per lane so that the chain has <= 32 rows

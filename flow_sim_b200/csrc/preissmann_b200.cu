@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -583,6 +584,7 @@ int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom
 }
 
 int pr_release_workspace(void) {
+  std::lock_guard<std::mutex> lock(pr::long_workspace().mu);
   pr::long_workspace().release();
   return PR_OK;
 }

@@ -251,7 +251,8 @@ int pr_rating_objective(const pr_config* cfg, const double* up_flow, const doubl
 int pr_fp64_peak(double millis, double* tflops_out);
 
 /* The long-reach path (n_nodes > 249) keeps its device workspace (iterate, level constants, tile cells) between
- * calls; this frees it. */
+ * calls; this frees it.  Every entry point may be called from several host threads (pr_last_error is per thread);
+ * long-reach runs share that workspace and therefore run one at a time per process. */
 int pr_release_workspace(void);
 
 /* Diagnostics: evaluates the device's branch-free FP64 primitives (reciprocal, square root, reciprocal square
