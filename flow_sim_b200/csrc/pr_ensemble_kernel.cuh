@@ -227,6 +227,13 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
   const bool roseires3 = !GST && G == 32 && p.dn.type == PR_BC_RATING_CURVE && !p.dn.member_rc && p.dn.rc.type == PR_RC_ROSEIRES;
 
+  // Short reaches: a normal-depth (or head-loss) boundary needs the conveyance of node N-1.  Evaluating that node a
+  // second time on its owner lane costs a whole node pass at one active thread - a third of the iteration with one
+  // node per lane - so these builds take K and dK/dA from the regular pass instead (WANT_K there, a few flops).
+  constexpr bool DNK = (G < 32 || M <= 2) && !IRR;
+  NodeConv kc_last = {0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
+  double T_last = 0.0;
+
   int level = 1, it = 0;
   bool active = member_valid && L > 1;
   int status = PR_STATUS_OK, fail_level = 0;
@@ -282,7 +289,13 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
     // ------------------------------ node + cell pass ------------------------------
     NodeVals left, right;
-    PR_NODE(false, 0, h[0], q[0], left, nullptr);
+    if (DNK && dn_normal) {
+      NodeConv kct;
+      PR_NODE(true, 0, h[0], q[0], left, &kct);
+      if (slot_last == 0) { kc_last = kct; T_last = left.T; }
+    } else {
+      PR_NODE(false, 0, h[0], q[0], left, nullptr);
+    }
     // hand the first node to the lane on the left: it closes that lane's last cell
     __syncwarp();
     XW(0, lane) = left.Q;  XW(1, lane) = left.A;  XW(2, lane) = left.T;  XW(3, lane) = left.Y;  XW(4, lane) = left.Se;
@@ -294,7 +307,13 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       if (j + 1 < M) {
-        PR_NODE(false, j + 1, h[j + 1], q[j + 1], right, nullptr);
+        if (DNK && dn_normal) {
+          NodeConv kct;
+          PR_NODE(true, j + 1, h[j + 1], q[j + 1], right, &kct);
+          if (slot_last == j + 1) { kc_last = kct; T_last = right.T; }
+        } else {
+          PR_NODE(false, j + 1, h[j + 1], q[j + 1], right, nullptr);
+        }
       } else {
         const int nl = (lane + 1) & 31;
         right.Q = XW(0, nl);  right.A = XW(1, nl);  right.T = XW(2, nl);  right.Y = XW(3, nl);  right.Se = XW(4, nl);
@@ -350,9 +369,13 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       NodeConv kc = {0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
       double T0 = 0.0;
       if (dn_normal) {
-        NodeVals t;
-        PR_NODE(true, slot_last, hl, ql, t, &kc);
-        T0 = t.T;
+        if (DNK) {
+          kc = kc_last; T0 = T_last;
+        } else {
+          NodeVals t;
+          PR_NODE(true, slot_last, hl, ql, t, &kc);
+          T0 = t.T;
+        }
       }
       D = bc_eval<GST>(p.dn, member, level, hyd_dn, hl, ql, q_prev_last, stage_prev, p.dt, p.g, kc, T0, GST ? &gate : nullptr);
     }
