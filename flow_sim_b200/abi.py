@@ -12,7 +12,7 @@ import threading
 
 import numpy as np
 
-PR_ABI_VERSION = 6
+PR_ABI_VERSION = 7
 PR_MAX_POLY = 12
 PR_MAX_GATES = 8
 
@@ -44,6 +44,7 @@ class pr_config(C.Structure):
         ("max_iter", C.c_int32), ("out_mode", C.c_int32), ("mem", C.c_int32), ("device", C.c_int32),
         ("lanes_per_member", C.c_int32), ("reserved0", C.c_int32),
         ("theta", C.c_double), ("dt", C.c_double), ("dx", C.c_double), ("tol", C.c_double), ("g", C.c_double),
+        ("member_order", c_int32_p),
     ]
 
 

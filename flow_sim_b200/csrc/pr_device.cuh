@@ -64,7 +64,7 @@ struct DevGeom {
 
 struct DevParams {
   int N, L, M, max_iter, out_mode;
-  double theta, dt, dx, tol, g;
+  double theta, dt, dx, tol, tol2, g;       // tol2 = tol^2
   double i2dt, th_dx, hth, omt_dx, homt;   // 1/(2dt), theta/dx, theta/2, (1-theta)/dx, (1-theta)/2
   double ghth, th_dx2;                     // g*theta/2, 2*theta/dx
   DevGeom geo;
@@ -74,6 +74,11 @@ struct DevParams {
   double *out_h, *out_q;
   int *iters, *status, *fail_level;
   double *storage_stage, *final_error;
+  // persistent scheduling of the fused kernel (pr_ensemble_kernel.cuh): zeroed ticket counter of this launch, number
+  // of tickets, optional processing order of the members (a permutation of 0..M-1), SM count of the device
+  unsigned int* ticket;
+  int n_tickets, sm_count;
+  const int* member_order;
 };
 
 // ---- FP64 primitives without slow-path branches ----------------------------------------------------

@@ -25,6 +25,11 @@
 #include "pr_device.cuh"
 #include "pr_irregular.cuh"
 
+// tuning switches (A/B builds: -DPR_...=0/1)
+#ifndef PR_PCR_V2
+#define PR_PCR_V2 1     // parallel cyclic reduction with two short exchanges per step (14 values) instead of one of 20
+#endif
+
 namespace pr {
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -139,9 +144,6 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
   const int gl = lane % G;            // lane within the member's group
   const int N = p.N, L = p.L;
-  long long member = ((long long)blockIdx.x * W + warp) * MPW + lane / G;
-  const bool member_valid = member < p.M;
-  if (!member_valid) member = p.M - 1;
 
   // chain topology (uniform): lanes 0..Lc hold one block row each
   const int ncells_total = N - 1;
@@ -149,9 +151,26 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   const int my_first = gl * M;                         // first node owned by this lane
   int nc = ncells_total - my_first;                    // cells owned by this lane
   nc = nc < 0 ? 0 : (nc > M ? M : nc);
-  const int owner_last = (N - 1) / M, slot_last = (N - 1) % M;   // where node N-1 lives
+  // where node N-1 lives (EXACT: (N-1) % M == 0, so it is slot 0 of lane Lc - known at compile time)
+  const int slot_last = EXACT ? 0 : (N - 1) % M;
+  const int owner_last = EXACT ? Lc : (N - 1) / M;
   const bool is_first = (gl == 0);
   const bool owns_last = (gl == owner_last);
+
+  // Persistent warps: the grid holds one CTA per SM, and every warp draws its next member (group of 32/G members)
+  // from a ticket counter until the ensemble is used up.  Members differ in their Newton iteration totals (409 ... 676
+  // across the gerd roughness grid), so static member -> CTA assignment leaves SMs idle behind the slowest warp of a
+  // CTA and in the last partial wave; p.member_order (optional) lets the caller hand out expensive members first.
+  for (;;) {
+  // PHASE: prologue
+  unsigned ticket = 0;
+  if (lane == 0) ticket = atomicAdd(p.ticket, 1u);
+  ticket = __shfl_sync(kFull, ticket, 0);
+  if (ticket >= (unsigned)p.n_tickets) break;
+  int member = (int)ticket * MPW + lane / G;
+  const bool member_valid = member < p.M;
+  if (!member_valid) member = p.M - 1;
+  if (p.member_order) member = p.member_order[member];
 
   const DevParams& k = p;
   const Rough rg = load_rough<RM>(p.geo, member);
@@ -165,8 +184,8 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   // ---- state: initial conditions (Solver.initialize_t0, solver.py:61-63) ----
   double h[M], q[M];
   {
-    const double* ih = p.ic_h + member * p.ic_stride;
-    const double* iq = p.ic_q + member * p.ic_stride;
+    const double* ih = p.ic_h + (long long)member * p.ic_stride;
+    const double* iq = p.ic_q + (long long)member * p.ic_stride;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       const int nd = my_first + j < N ? my_first + j : N - 1;
@@ -236,7 +255,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
 
   int level = 1, it = 0;
   bool active = member_valid && L > 1;
-  int status = PR_STATUS_OK, fail_level = 0;
+  bool failed = false;
   double hyd_up = 0.0, hyd_dn = 0.0;
 
 #define PC(c, j) pcw[((c)*M + (j)) * 32 + lane]
@@ -255,6 +274,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
   // per accepted level.  Cheaper than producing candidates in every Newton iteration (one extra node pass per
   // level against 4 stores + 9 flops per cell per iteration), and it halves the constants' shared memory.
   bool commit = true;      // G < 32: which lanes take the refreshed constants
+  // PHASE: level refresh
   auto refresh_level_constants = [&]() {
     NodeVals left, right;
     PR_NODE(false, 0, h[0], q[0], left, nullptr);
@@ -277,17 +297,18 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
     __syncwarp();
   };
+  // PHASE: prologue
   refresh_level_constants();
 
+  // PHASE: loop control
   while (__any_sync(kFull, active)) {
-    if (it == 0) {
-      // hydrograph samples at t = level*dt (preissmann.py:215,313)
-      if (p.up.series) hyd_up = p.up.series[member * p.up.series_stride + (level < L ? level : L - 1)];
-      if (p.dn.series) hyd_dn = p.dn.series[member * p.dn.series_stride + (level < L ? level : L - 1)];
-    }
+    // hydrograph samples at t = level*dt (preissmann.py:215,313)
+#define PR_HYD(bc) ((bc).series ? (bc).series[(long long)member * (bc).series_stride + (level < L ? level : L - 1)] : 0.0)
+    if (it == 0) { hyd_up = PR_HYD(p.up); hyd_dn = PR_HYD(p.dn); }
     if (active) it += 1;
 
     // ------------------------------ node + cell pass ------------------------------
+    // PHASE: node pass
     NodeVals left, right;
     if (DNK && dn_normal) {
       NodeConv kct;
@@ -306,6 +327,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     Cell S;                     // condensed cell of this lane
 #pragma unroll
     for (int j = 0; j < M; ++j) {
+      // PHASE: node pass
       if (j + 1 < M) {
         if (DNK && dn_normal) {
           NodeConv kct;
@@ -322,10 +344,12 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
         right.w1 = (k.th_dx * right.QA) * (right.QA * right.T);
         right.w4 = k.th_dx2 * right.QA;
       }
+      // PHASE: cell pass
       if (EXACT || j < nc) {
         Cell e;
         const double r2 = cell_assemble(left, right, k, PC(0, j), PC(1, j), PC(2, j), PC(3, j), e);
         ss += (!EXACT || nc > 0) ? r2 : 0.0;
+        // PHASE: merge
         if (j == 0) S = e;
         else {
           Elim el;
@@ -339,10 +363,15 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
 
     // ------------------------------ boundary rows ------------------------------
+    // PHASE: boundary rows
     BcRow U, D;
     U.res = 0.0; U.dh = 1.0; U.dq = 0.0; U.stage_rec = 0.0; U.fail = false;
     D = U;
-    if (is_first) {
+    if (p.up.type == PR_BC_FLOW_HYDROGRAPH) {
+      // the usual upstream condition, Q - hyd(t) (boundary.py:81-84): every lane forms it (no divergent one-lane stretch),
+      // lane 0's copy is the row
+      U.res = q[0] - hyd_up; U.dh = 0.0; U.dq = 1.0;
+    } else if (is_first) {
       NodeConv kc = {0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
       double T0 = 0.0;
       if (up_normal) {
@@ -381,9 +410,12 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
     if (is_first) ss = fma(U.res, U.res, ss);
     if (owns_last) ss = fma(D.res, D.res, ss);
-    const double err = sqrt(group_sum<G>(ss));                  // utility.euclidean_norm (utility.py:20-22)
+    // utility.euclidean_norm (utility.py:20-22) < tol, decided on the squared norm; the root is only taken when the
+    // norm itself is asked for (final_error)
+    const double err2 = group_sum<G>(ss);
 
     // ------------------------------ chain rows ------------------------------
+    // PHASE: chain rows
     // row a (top): lane 0 -> U ; lane 1..Lc -> M~ of the previous lane's condensed cell
     // row b (bottom): lane < Lc -> own C~ ; lane Lc -> D ; beyond -> identity
     double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
@@ -403,11 +435,35 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       else { d21 = 0.0; d22 = 1.0; u1 = 0.0; u2 = 0.0; rb = 0.0; }
     }
     // ------------------------------ parallel cyclic reduction ------------------------------
+    // PHASE: PCR
     // Rows whose partner lies outside the chain have a zero coupling (l = 0 / u = 0) by construction, and
     // every lane (rows beyond the chain are identity rows) holds finite data, so no guards are needed.
 #pragma unroll
     for (int s = 1; s < G; s <<= 1) {
       if (s > Lc) break;      // uniform: the chain has Lc+1 rows
+#if PR_PCR_V2
+      // Elimination of the couplings to lanes gl-s (through l) and gl+s (through u).  The work for a neighbour's row
+      // is done HERE, on the lane that owns the pivot block: the neighbours send their coupling vectors (2 + 2 values,
+      // independent of the reciprocal below, so the exchange overlaps it) and get back the five numbers their row
+      // needs - 14 values per lane and step instead of the 20 of shipping whole block rows.
+      const int up_src = (gl - s) & (G - 1), dn_src = (gl + s) & (G - 1);
+      const double Dl1 = __shfl_sync(kFull, l1, dn_src, G), Dl2 = __shfl_sync(kFull, l2, dn_src, G);   // l of lane gl+s
+      const double Uu1 = __shfl_sync(kFull, u1, up_src, G), Uu2 = __shfl_sync(kFull, u2, up_src, G);   // u of lane gl-s
+      const double idet = fast_rcp(d11 * d22 - d12 * d21);
+      const double i11 = d22 * idet, i12 = -d12 * idet, i21 = -d21 * idet, i22 = d11 * idet;
+      // for lane gl+s (this lane is its P): [l1 l2] * Dinv, then its new l, the change of its (d11, d12) and of its ra
+      const double a1 = Dl1 * i11 + Dl2 * i21, a2 = Dl1 * i12 + Dl2 * i22;
+      const double o_l1 = -a1 * l1, o_l2 = -a1 * l2, o_d1 = a2 * u1, o_d2 = a2 * u2, o_r = a1 * ra + a2 * rb;
+      // for lane gl-s (this lane is its N): [u1 u2] * Dinv, then its new u, the change of its (d21, d22) and of its rb
+      const double b1 = Uu1 * i11 + Uu2 * i21, b2 = Uu1 * i12 + Uu2 * i22;
+      const double o_u1 = -b2 * u1, o_u2 = -b2 * u2, o_e1 = b1 * l1, o_e2 = b1 * l2, o_s = b1 * ra + b2 * rb;
+      l1 = __shfl_sync(kFull, o_l1, up_src, G);  l2 = __shfl_sync(kFull, o_l2, up_src, G);
+      d11 -= __shfl_sync(kFull, o_d1, up_src, G); d12 -= __shfl_sync(kFull, o_d2, up_src, G);
+      ra -= __shfl_sync(kFull, o_r, up_src, G);
+      u1 = __shfl_sync(kFull, o_u1, dn_src, G);  u2 = __shfl_sync(kFull, o_u2, dn_src, G);
+      d21 -= __shfl_sync(kFull, o_e1, dn_src, G); d22 -= __shfl_sync(kFull, o_e2, dn_src, G);
+      rb -= __shfl_sync(kFull, o_s, dn_src, G);
+#else
       const double idet = fast_rcp(d11 * d22 - d12 * d21);
       const double i11 = d22 * idet, i12 = -d12 * idet, i21 = -d21 * idet, i22 = d11 * idet;
       const int up_src = (gl - s) & (G - 1), dn_src = (gl + s) & (G - 1);
@@ -432,6 +488,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       u1 = -b2 * N_u1;  u2 = -b2 * N_u2;
       d21 -= b1 * N_l1; d22 -= b1 * N_l2;
       rb -= b1 * N_ra + b2 * N_rb;
+#endif
     }
     double dh0, dq0;    // update of this lane's chain node
     {
@@ -440,6 +497,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       dq0 = (d11 * rb - d21 * ra) * idet;
     }
     // ------------------------------ back-substitution ------------------------------
+    // PHASE: back-substitution
     const double dhR = __shfl_down_sync(kFull, dh0, 1, G), dqR = __shfl_down_sync(kFull, dq0, 1, G);
     double dh[M], dq[M];
     dh[0] = dh0; dq[0] = dq0;
@@ -462,17 +520,18 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     }
 
     // ------------------------------ accept / update (preissmann.py:146-156) ------------------------------
+    // PHASE: accept/update
     // a boundary evaluation the reference would abort on (brentq without a sign change) fails the member at once
     bool bc_failed;
     if (G == 32) bc_failed = __any_sync(kFull, (is_first && U.fail) || (owns_last && D.fail));
     else bc_failed = (__ballot_sync(kFull, (is_first && U.fail) || (owns_last && D.fail)) & ((((1u << (G & 31)) - 1u) << (lane - gl)))) != 0u;
-    const bool converged = !bc_failed && err < p.tol;
+    const bool converged = !bc_failed && err2 < p.tol2;
     if (active) {
       if (converged) {
         store_level(level, false);                     // stored level = iterate BEFORE the update
         if (is_first) {
           if (p.iters) p.iters[(size_t)member * (L - 1) + (level - 1)] = it;
-          if (p.final_error) p.final_error[(size_t)member * (L - 1) + (level - 1)] = err;
+          if (p.final_error) p.final_error[(size_t)member * (L - 1) + (level - 1)] = sqrt(err2);
         }
         if (owns_last) {
           double hl, ql;
@@ -496,11 +555,14 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
         level += 1; it = 0;
         if (level >= L) active = false;
       } else if (it >= p.max_iter || bc_failed) {
-        status = (err == err && !bc_failed) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
-        fail_level = level;
+        failed = true;
+        if (member_valid && is_first) {
+          if (p.status) p.status[member] = (err2 == err2 && !bc_failed) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
+          if (p.fail_level) p.fail_level[member] = level;
+        }
         if (is_first) {
           if (p.iters) p.iters[(size_t)member * (L - 1) + (level - 1)] = it;
-          if (p.final_error) p.final_error[(size_t)member * (L - 1) + (level - 1)] = err;
+          if (p.final_error) p.final_error[(size_t)member * (L - 1) + (level - 1)] = sqrt(err2);
         }
         for (int kk = level; kk < L; ++kk) {
           store_level(kk, true);
@@ -514,14 +576,27 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       }
     }
   }
+  // PHASE: epilogue
+  if (member_valid && is_first && !failed) {
+    if (p.status) p.status[member] = PR_STATUS_OK;
+    if (p.fail_level) p.fail_level[member] = 0;
+  }
+  __syncwarp();                      // the per-warp scratch is reused by the next member
+  }                                  // next ticket
+#undef PR_HYD
 #undef PC
 #undef EL
 #undef XW
 #undef PR_NODE
-  if (member_valid && is_first) {
-    if (p.status) p.status[member] = status;
-    if (p.fail_level) p.fail_level[member] = fail_level;
-  }
+}
+
+// Tickets and grid of a persistent launch: one ticket = the members of one warp pass (32/G of them); one CTA per SM
+// (the kernels are built for one resident CTA), fewer when the ensemble is smaller than that.
+inline unsigned persistent_grid(DevParams& q, int members_per_warp, int warps_per_cta) {
+  q.n_tickets = (int)((q.M + members_per_warp - 1) / members_per_warp);
+  const int ctas = (q.n_tickets + warps_per_cta - 1) / warps_per_cta;
+  const int sms = q.sm_count > 0 ? q.sm_count : 148;
+  return (unsigned)(ctas < sms ? ctas : sms);
 }
 
 // Launch of one (lanes per member, nodes per lane) family (all CURV x RM variants); defined in pr_ensemble_*.cu so
@@ -538,9 +613,9 @@ int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
     auto kern = pr_ensemble_kernel<G_, M_, W_, CURV, RM, EXACT, GST>;                                        \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                     \
-    constexpr int per_cta = W_ * (32 / G_);                                                                  \
-    const unsigned grid = (unsigned)((p.M + per_cta - 1) / per_cta);                                         \
-    kern<<<grid, W_ * 32, smem, s>>>(p);                                                                     \
+    DevParams q = p;                                                                                         \
+    const unsigned grid = persistent_grid(q, 32 / G_, W_);                                                   \
+    kern<<<grid, W_ * 32, smem, s>>>(q);                                                                     \
     return (int)cudaGetLastError();                                                                          \
   }                                                                                                          \
   template <bool CURV, int RM, bool EXACT>                                                                   \
@@ -587,7 +662,9 @@ int launch_ensemble_irregular(const DevParams& p, bool curv, cudaStream_t s);
     auto kern = pr_ensemble_kernel<32, M_, W_, CURV, 4, false, true, true>;                                  \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                     \
-    kern<<<(unsigned)((p.M + W_ - 1) / W_), W_ * 32, smem, s>>>(p);                                          \
+    DevParams q = p;                                                                                         \
+    const unsigned grid = persistent_grid(q, 1, W_);                                                         \
+    kern<<<grid, W_ * 32, smem, s>>>(q);                                                                     \
     return (int)cudaGetLastError();                                                                          \
   }                                                                                                          \
   template <>                                                                                                \

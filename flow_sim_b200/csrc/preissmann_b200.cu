@@ -5,11 +5,13 @@
 // and launching.  No CPU implementation of the scheme lives here: if CUDA is unavailable every entry
 // point fails with PR_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -238,7 +240,51 @@ int make_bc(const pr_bc& b, const char* which, bool downstream, const pr_config&
   return PR_OK;
 }
 
-int check_config(const pr_config* cfg) {
+// Every entry point runs on cfg->device and leaves the calling thread's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess || device < 0 || device == prev) return e;
+    e = cudaSetDevice(device);
+    changed = (e == cudaSuccess);
+    return e;
+  }
+};
+
+// Per-device facts and the ticket counters of the persistent fused kernel.  A launch takes the next counter of a ring
+// and zeroes it on its stream, so launches on different streams never share one (the ring is far longer than any
+// plausible number of launches in flight).
+struct DeviceInfo {
+  int sm_count = 0;
+  unsigned int* tickets = nullptr;
+  unsigned next = 0;
+};
+constexpr unsigned kTicketRing = 4096;
+std::mutex g_dev_mu;
+DeviceInfo g_dev[64];
+
+int device_info(cudaStream_t s, int& sm_count, unsigned int*& ticket) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(PR_ERR_CUDA, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (!d.tickets) {
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaMalloc(&d.tickets, kTicketRing * sizeof(unsigned int)));
+  }
+  sm_count = d.sm_count;
+  ticket = d.tickets + (d.next++ % kTicketRing);
+  CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+  return PR_OK;
+}
+
+int check_config(const pr_config* cfg, DeviceGuard& guard) {
   if (!cfg) return fail(PR_ERR_ARG, "cfg is NULL");
   if (cfg->abi_version != PR_ABI_VERSION)
     return fail(PR_ERR_ARG, "abi_version %d != library %d", cfg->abi_version, PR_ABI_VERSION);
@@ -247,7 +293,7 @@ int check_config(const pr_config* cfg) {
   if (cfg->n_members < 1) return fail(PR_ERR_ARG, "n_members must be >= 1");
   if (cfg->mem != PR_MEM_HOST && cfg->mem != PR_MEM_DEVICE) return fail(PR_ERR_ARG, "mem must be HOST or DEVICE");
   if (!(cfg->dt > 0) || !(cfg->dx > 0)) return fail(PR_ERR_ARG, "dt and dx must be positive");
-  if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
+  CUDA_TRY(guard.enter(cfg->device));
   return PR_OK;
 }
 
@@ -289,6 +335,22 @@ int any_irregular(const pr_config& cfg, const pr_geom* g, bool& found) {
   else CUDA_TRY(cudaMemcpy(kinds.data(), g->kind, kinds.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
   for (int32_t kd : kinds) found |= (kd == PR_XS_IRREGULAR);
   return PR_OK;
+}
+
+// Tuning hook (tools/ab_build.sh): PR_M4_VARIANT=<variant .so> replaces the 32-lane x 4-node family of this library by
+// the one in that file, so that A/B builds of the headline kernel need not carry the whole library.
+using m4_variant_fn = int (*)(const pr::DevParams*, int, cudaStream_t);
+m4_variant_fn m4_variant() {
+  static m4_variant_fn fn = []() -> m4_variant_fn {
+    const char* path = std::getenv("PR_M4_VARIANT");
+    if (!path || !*path) return nullptr;
+    void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) { std::fprintf(stderr, "PR_M4_VARIANT: %s\n", dlerror()); std::abort(); }
+    void* f = dlsym(h, "pr_variant_launch_m4");
+    if (!f) { std::fprintf(stderr, "PR_M4_VARIANT: no pr_variant_launch_m4 in %s\n", path); std::abort(); }
+    return reinterpret_cast<m4_variant_fn>(f);
+  }();
+  return fn;
 }
 
 int launch_family(int rc_cuda) {
@@ -336,7 +398,8 @@ int64_t pr_launch_count(void) { return g_launches.load(); }
 
 int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upstream, const pr_bc* downstream,
                     const pr_state* initial, const pr_outputs* out, void* cuda_stream) {
-  if (int rc = check_config(cfg)) return rc;
+  DeviceGuard guard;
+  if (int rc = check_config(cfg, guard)) return rc;
   if (!upstream || !downstream || !initial || !out) return fail(PR_ERR_ARG, "a struct pointer is NULL");
   if (!initial->depth || !initial->flow) return fail(PR_ERR_ARG, "initial conditions are NULL");
   if (initial->member_stride != 0 && initial->member_stride < cfg->n_nodes)
@@ -349,7 +412,7 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   pr::DevParams p;
   std::memset(&p, 0, sizeof p);
   p.N = (int)N; p.L = (int)L; p.M = (int)M; p.max_iter = cfg->max_iter; p.out_mode = cfg->out_mode;
-  p.theta = cfg->theta; p.dt = cfg->dt; p.dx = cfg->dx; p.tol = cfg->tol; p.g = cfg->g;
+  p.theta = cfg->theta; p.dt = cfg->dt; p.dx = cfg->dx; p.tol = cfg->tol; p.tol2 = cfg->tol * cfg->tol; p.g = cfg->g;
   p.i2dt = 1.0 / (2.0 * cfg->dt);
   p.th_dx = cfg->theta / cfg->dx;
   p.hth = 0.5 * cfg->theta;
@@ -394,12 +457,16 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   p.fail_level = st.out(out->fail_level, M);
   p.storage_stage = st.out(out->storage_stage, M * L);
   p.final_error = st.out(out->final_error, M * (L > 1 ? L - 1 : 1));
+  p.member_order = st.in(cfg->member_order, M);
   if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
+  if (int rc = device_info(s, p.sm_count, p.ticket)) return rc;
 
   // Lanes per member G and nodes per lane M: the chain has ceil(cells / M) + 1 <= G block rows.  Short reaches pack
   // 4 or 2 members into a warp (G = 8, 16) so that neither lanes nor parallel-cyclic-reduction steps are wasted.
   const int cells = (int)N - 1;
-  const int lpm = cfg->lanes_per_member;
+  int lpm = cfg->lanes_per_member;
+  if (lpm == 0)                         // tuning: PR_FORCE_LANES=8|16|32 overrides the automatic choice
+    if (const char* e = std::getenv("PR_FORCE_LANES")) lpm = std::atoi(e);
   if (lpm != 0 && lpm != -1 && lpm != 8 && lpm != 16 && lpm != 32)
     return fail(PR_ERR_ARG, "lanes_per_member=%d: must be 0 (auto), 8, 16, 32 or -1 (long-reach path)", lpm);
   auto fits = [&](int G, int M) { return (lpm == 0 || lpm == G) && cells <= (G - 1) * M; };
@@ -420,7 +487,7 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   else if (fits(32, 1)) rc = launch_family(pr::launch_ensemble_family<32, 1, 16>(p, has_curv, s));
   else if (fits(16, 4)) rc = launch_family(pr::launch_ensemble_family<16, 4, 16>(p, has_curv, s));
   else if (fits(32, 2)) rc = launch_family(pr::launch_ensemble_family<32, 2, 16>(p, has_curv, s));
-  else if (fits(32, 4)) rc = launch_family(pr::launch_ensemble_family<32, 4, PR_W4>(p, has_curv, s));
+  else if (fits(32, 4)) rc = launch_family(m4_variant() ? m4_variant()(&p, has_curv, s) : pr::launch_ensemble_family<32, 4, PR_W4>(p, has_curv, s));
   else if (fits(32, 8)) rc = launch_family(pr::launch_ensemble_family<32, 8, 7>(p, has_curv, s));
   else if (lpm != 0) return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: no instantiation holds %d nodes", lpm, (int)N);
   else rc = pr::long_reach_run(p, has_curv, has_compound, false, s, g_launches, g_err);
@@ -433,7 +500,8 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
 int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const double* q0, int64_t q0_member_stride,
                               const double* downstream_depth, int64_t downstream_depth_member_stride,
                               double* ic_depth, double* ic_flow, int32_t* status, void* cuda_stream) {
-  if (int rc = check_config(cfg)) return rc;
+  DeviceGuard guard;
+  if (int rc = check_config(cfg, guard)) return rc;
   if (!q0 || !downstream_depth || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "q0 / downstream_depth / ic buffers are NULL");
 
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
@@ -476,7 +544,8 @@ int pr_gvf_initial_conditions(const pr_config* cfg, const pr_geom* geom, const d
 int pr_rating_objective(const pr_config* cfg, const double* up_flow, const double* up_depth, double z0,
                         const double* q_query, const double* h_target, int32_t n_query, double* levels_out,
                         double* rmse_out, void* cuda_stream) {
-  if (int rc = check_config(cfg)) return rc;
+  DeviceGuard guard;
+  if (int rc = check_config(cfg, guard)) return rc;
   if (!up_flow || !up_depth || !q_query || !h_target || n_query < 1) return fail(PR_ERR_ARG, "objective: NULL input");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t L = cfg->n_levels, M = cfg->n_members;
@@ -501,7 +570,8 @@ int pr_rating_objective(const pr_config* cfg, const double* up_flow, const doubl
 int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* depth, const double* flow,
                        double* level, double* area, double* top_width, double* froude, double* velocity,
                        double* celerity, void* cuda_stream) {
-  if (int rc = check_config(cfg)) return rc;
+  DeviceGuard guard;
+  if (int rc = check_config(cfg, guard)) return rc;
   {
     bool irr = false;
     if (int rc = any_irregular(*cfg, geom, irr)) return rc;
@@ -543,7 +613,8 @@ int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* 
 int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom, const double* bed_slope,
                                        const double* q0, int64_t q0_member_stride, double* ic_depth,
                                        double* ic_flow, void* cuda_stream) {
-  if (int rc = check_config(cfg)) return rc;
+  DeviceGuard guard;
+  if (int rc = check_config(cfg, guard)) return rc;
   {
     bool irr = false;
     if (int rc = any_irregular(*cfg, geom, irr)) return rc;

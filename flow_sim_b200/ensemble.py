@@ -46,8 +46,11 @@ class EnsembleRunner:
         return t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device, non_blocking=True)
 
     def solve(self, n_members: int, member_n_main=None, member_n_fp=None, up_series=None, ic_depth=None, ic_flow=None,
-              out_mode: int = abi.PR_OUT_UPSTREAM, stream=None, want_error: bool = False, member_ratings=None) -> dict:
-        """One pr_ensemble_run on device buffers; returns torch tensors (no synchronisation)."""
+              out_mode: int = abi.PR_OUT_UPSTREAM, stream=None, want_error: bool = False, member_ratings=None,
+              member_order=None) -> dict:
+        """One pr_ensemble_run on device buffers; returns torch tensors (no synchronisation).
+        member_order: optional permutation of the members (int32) - the order in which the persistent kernel hands
+        them to its warps; put the expensive members first."""
         f = copy.copy(self.flat)
         f.member_n_main = self._to_device(member_n_main)
         f.member_n_fp = self._to_device(member_n_fp)
@@ -61,7 +64,8 @@ class EnsembleRunner:
             f.up.series = self._to_device(up_series)
         if ic_depth is not None:
             f.ic_depth, f.ic_flow = self._to_device(ic_depth), self._to_device(ic_flow)
-        call = PreparedCall(f, n_members, out_mode, abi.PR_MEM_DEVICE, self.device, want_error=want_error)
+        call = PreparedCall(f, n_members, out_mode, abi.PR_MEM_DEVICE, self.device, want_error=want_error,
+                            member_order=member_order)
         import ctypes as C
 
         rc = self.lib.pr_ensemble_run(*call.args(), C.c_void_p(stream or 0))
@@ -81,8 +85,11 @@ class EnsembleRunner:
         h_dn = float(self.flat.meta["downstream_depth"] if downstream_depth is None else downstream_depth)
         q_init = self.flat.meta["initial_flow"] if q0 is None else q0
         ich, icq, ic_status = gvf_initial_conditions(f, M, q_init, h_dn, abi.PR_MEM_DEVICE, self.device, stream)
+        # the Newton iteration total of a member grows with its roughness (409 -> 676 across the gerd grid):
+        # rough members first, so that the launch ends on the cheap ones
+        order = self.torch.argsort(n_dev, descending=True).to(self.torch.int32)
         res = self.solve(M, member_n_main=n_dev, member_n_fp=nfp_dev, ic_depth=ich, ic_flow=icq, out_mode=out_mode,
-                         stream=stream)
+                         stream=stream, member_order=order)
         res["ic_status"] = ic_status
         if q_query is not None:
             if out_mode == abi.PR_OUT_UPSTREAM:

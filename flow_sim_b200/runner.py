@@ -15,23 +15,22 @@ class PreparedCall:
     """ctypes structs + the buffers behind them for one pr_ensemble_run-shaped call."""
 
     def __init__(self, flat: FlatCase, n_members: int | None = None, out_mode: int = abi.PR_OUT_FULL,
-                 mem: int = abi.PR_MEM_HOST, device=None, lanes: int = 0, want_error: bool = True):
+                 mem: int = abi.PR_MEM_HOST, device=None, lanes: int = 0, want_error: bool = True, member_order=None):
         M = int(n_members if n_members is not None else flat.n_members_hint)
         N, L = flat.n_nodes, flat.n_levels
         self.flat, self.M, self.N, self.L, self.out_mode, self.mem = flat, M, N, L, out_mode, mem
         ar = self.arena = abi.Arena(mem, device)
 
-        dev_index = -1
-        if mem == abi.PR_MEM_DEVICE:
-            import torch
-
-            dev_index = torch.device(device).index if device is not None else torch.cuda.current_device()
-            if dev_index is None:
-                dev_index = torch.cuda.current_device()
+        dev_index = _device_index(mem, device)
         self.cfg = abi.pr_config(abi_version=abi.PR_ABI_VERSION, n_nodes=N, n_levels=L, n_members=M,
                                  max_iter=flat.max_iter, out_mode=out_mode, mem=mem, device=dev_index,
                                  lanes_per_member=lanes, theta=flat.theta, dt=flat.dt, dx=flat.dx,
                                  tol=flat.tol, g=flat.g)
+
+        if member_order is not None:          # processing order of the members (a permutation; results stay in member order)
+            if len(member_order) != M:
+                raise ValueError("member_order must have one entry per member")
+            self.cfg.member_order = ar.put(member_order, np.int32)[0]
 
         self.geom = _geom_struct(flat, ar, M)
 
@@ -142,14 +141,18 @@ def _geom_struct(flat: FlatCase, arena: abi.Arena, M: int) -> abi.pr_geom:
     return g
 
 
-def _config(flat: FlatCase, M: int, mem: int, device, out_mode: int = abi.PR_OUT_UPSTREAM) -> abi.pr_config:
-    dev_index = -1
-    if mem == abi.PR_MEM_DEVICE:
-        import torch
+def _device_index(mem: int, device) -> int:
+    """CUDA ordinal the call's device buffers live on (-1 = the current device, host-memory calls)."""
+    if mem != abi.PR_MEM_DEVICE:
+        return -1
+    import torch
 
-        dev_index = torch.device(device).index if device is not None else None
-        if dev_index is None:
-            dev_index = torch.cuda.current_device()
+    idx = torch.device(device).index if device is not None else None
+    return torch.cuda.current_device() if idx is None else idx
+
+
+def _config(flat: FlatCase, M: int, mem: int, device, out_mode: int = abi.PR_OUT_UPSTREAM) -> abi.pr_config:
+    dev_index = _device_index(mem, device)
     return abi.pr_config(abi_version=abi.PR_ABI_VERSION, n_nodes=flat.n_nodes, n_levels=flat.n_levels, n_members=M,
                          max_iter=flat.max_iter, out_mode=out_mode, mem=mem, device=dev_index, lanes_per_member=0,
                          theta=flat.theta, dt=flat.dt, dx=flat.dx, tol=flat.tol, g=flat.g)
@@ -189,7 +192,8 @@ def rating_objective(n_levels: int, up_flow, up_depth, z0: float, q_query, h_tar
     ar = abi.Arena(mem, device)
     M = int(up_flow.shape[0])
     cfg = abi.pr_config(abi_version=abi.PR_ABI_VERSION, n_nodes=2, n_levels=n_levels, n_members=M, max_iter=1,
-                        out_mode=abi.PR_OUT_UPSTREAM, mem=mem, device=-1, theta=0.5, dt=1.0, dx=1.0, tol=1.0, g=9.80665)
+                        out_mode=abi.PR_OUT_UPSTREAM, mem=mem, device=_device_index(mem, device), theta=0.5, dt=1.0,
+                        dx=1.0, tol=1.0, g=9.80665)
     fq, _ = ar.put(up_flow)
     fh, _ = ar.put(up_depth)
     qq, qa = ar.put(np.asarray(q_query, dtype=np.float64) if not hasattr(q_query, "data_ptr") else q_query)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PR_ABI_VERSION 6
+#define PR_ABI_VERSION 7
 #define PR_MAX_POLY 12   /* max coefficients of a fitted numpy Polynomial rating curve */
 #define PR_MAX_GATES 8   /* Roseires: 7 spillway gates (roseires_rating_curve.py:11) */
 
@@ -86,6 +86,11 @@ typedef struct pr_config {
   double dx;            /* fitted spatial_step = L/(N-1) [m] */
   double tol;           /* run(tolerance): absolute bound on ||R||_2 (preissmann.py:149-153) */
   double g;             /* scipy.constants.g = 9.80665 */
+  /* Optional processing order of the members in pr_ensemble_run: a permutation of 0..M-1 ([M], in `mem` space), or
+   * NULL = 0, 1, 2, ...  The fused kernel is persistent - warps draw members from a counter until the ensemble is
+   * used up - so handing out the expensive members first (e.g. a roughness sweep in descending n: the Newton
+   * iteration total grows with n) shortens the tail of the launch.  Results are always written in member order. */
+  const int32_t* member_order;
 } pr_config;
 
 /* Per-node cross-sections in SoA form, i.e. Channel.xs_at_node after interpolation

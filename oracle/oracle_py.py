@@ -36,6 +36,8 @@ def lib():
         L.pr_oracle_run.argtypes = [C.POINTER(abi.pr_config), C.POINTER(abi.pr_geom), C.POINTER(abi.pr_bc),
                                     C.POINTER(abi.pr_bc), C.POINTER(abi.pr_state), C.POINTER(abi.pr_outputs)]
         L.pr_oracle_newton_step.restype = C.c_int
+        L.pr_oracle_trace_prev_error.restype = None
+        L.pr_oracle_trace_prev_error.argtypes = [abi.c_double_p]
         L.pr_oracle_gvf.restype = C.c_int
         L.pr_oracle_gvf.argtypes = [C.POINTER(abi.pr_config), C.POINTER(abi.pr_geom), abi.c_double_p, C.c_int64,
                                     abi.c_double_p, C.c_int64, abi.c_double_p, abi.c_double_p, abi.c_int32_p]
@@ -59,12 +61,25 @@ def _dp(a):
     return a.ctypes.data_as(abi.c_double_p)
 
 
-def run(flat, n_members=None, out_mode=abi.PR_OUT_FULL) -> dict:
+def run(flat, n_members=None, out_mode=abi.PR_OUT_FULL, trace_prev_error: bool = False) -> dict:
+    """trace_prev_error: also return res["prev_error"] [M, levels-1], ||R|| of the iteration before the accepted one."""
     call = PreparedCall(flat, n_members, out_mode, abi.PR_MEM_HOST)
-    rc = lib().pr_oracle_run(*call.args())
+    L = lib()
+    prev = None
+    if trace_prev_error:
+        prev = np.full((call.M, max(flat.n_levels - 1, 1)), np.nan)
+        L.pr_oracle_trace_prev_error(_dp(prev))
+    try:
+        rc = L.pr_oracle_run(*call.args())
+    finally:
+        if trace_prev_error:
+            L.pr_oracle_trace_prev_error(None)
     if rc != 0:
         raise RuntimeError(f"pr_oracle_run -> {rc}")
-    return call.results()
+    res = call.results()
+    if prev is not None:
+        res["prev_error"] = prev
+    return res
 
 
 def newton_step(flat, level, h0, q0, h1, q1, stage_record=None, member=0):

@@ -970,6 +970,11 @@ int pr_oracle_newton_step(const pr_config* cfg, const pr_geom* geom, const pr_bc
   return err;
 }
 
+/* Diagnostic trace for the near-tie analysis of the convergence test (tools/oracle_grid.py): when set, receives
+ * [M][levels-1] ||R||_2 of the iteration BEFORE the accepted one (NaN when the first iterate was accepted). */
+static double* g_trace_prev_error = NULL;
+void pr_oracle_trace_prev_error(double* buf) { g_trace_prev_error = buf; }
+
 /* PreissmannSolver.run, preissmann.py:101-163, for every member. */
 int pr_oracle_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* up_bc, const pr_bc* dn_bc,
                   const pr_state* ic, const pr_outputs* out) {
@@ -1014,9 +1019,10 @@ int pr_oracle_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* up_bc,
       bc_ctx up = {up_bc, &xs[0], m, k, cfg->dt, cfg->g, stage, &gate_up};
       bc_ctx dn = {dn_bc, &xs[N - 1], m, k, cfg->dt, cfg->g, stage, &gate_dn};
       int iteration = 0, converged = 0;
-      double error = NAN;
+      double error = NAN, prev_error = NAN;
       while (!converged) {
         iteration += 1;
+        prev_error = error;
         if (iteration - 1 >= cfg->max_iter) { status = PR_STATUS_MAX_ITER; iteration -= 1; break; }
         for (int i = 0; i < N; ++i) { hk1[i] = x[2 * i]; qk1[i] = x[2 * i + 1]; }   /* update_guesses */
         int err = assemble(&s, &up, &dn, R, J);
@@ -1040,6 +1046,7 @@ int pr_oracle_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* up_bc,
       if (status == PR_STATUS_MAX_ITER && !(error == error)) status = PR_STATUS_NAN;
       if (out->iters) out->iters[(size_t)m * (L - 1) + (k - 1)] = iteration;
       if (out->final_error) out->final_error[(size_t)m * (L - 1) + (k - 1)] = error;
+      if (g_trace_prev_error) g_trace_prev_error[(size_t)m * (L - 1) + (k - 1)] = prev_error;
       if (status != PR_STATUS_OK) {
         fail_level = k;
         for (int kk = k; kk < L; ++kk) {

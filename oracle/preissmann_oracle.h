@@ -9,6 +9,9 @@ extern "C" {
 #endif
 int pr_oracle_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* up, const pr_bc* down,
                   const pr_state* ic, const pr_outputs* out);
+/* diagnostic: buf [M][levels-1] receives ||R||_2 of the iteration before the accepted one on the next pr_oracle_run
+ * calls (NULL = off) */
+void pr_oracle_trace_prev_error(double* buf);
 int pr_oracle_newton_step(const pr_config* cfg, const pr_geom* geom, const pr_bc* up, const pr_bc* down,
                           int member, int level, const double* h0, const double* q0, const double* h1,
                           const double* q1, double* stage_record, double* R, double* J, double* delta);
