@@ -13,7 +13,7 @@ struct GvfParams {
   double dx, g;
   const double* h_down;
   long long h_down_stride;
-  double th_dx, hth, th_dx2;   // unused scheme constants node_eval reads (zero)
+  double th_dx, hth, th_dx2, theta, mtheta;   // unused scheme constants node_eval reads (zero)
   DevGeom geo;
   const double* q0;
   long long q0_stride;
@@ -191,7 +191,7 @@ struct NormalDepthParams {
   const double* q0;
   long long q0_stride;
   double *ic_h, *ic_q;
-  double th_dx, hth, th_dx2;   // unused scheme constants node_eval reads (zero)
+  double th_dx, hth, th_dx2, theta, mtheta;   // unused scheme constants node_eval reads (zero)
 };
 
 template <int RM>

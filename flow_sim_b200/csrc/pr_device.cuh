@@ -66,7 +66,7 @@ struct DevParams {
   int N, L, M, max_iter, out_mode;
   double theta, dt, dx, tol, tol2, g;       // tol2 = tol^2
   double i2dt, th_dx, hth, omt_dx, homt;   // 1/(2dt), theta/dx, theta/2, (1-theta)/dx, (1-theta)/2
-  double ghth, th_dx2;                     // g*theta/2, 2*theta/dx
+  double ghth, th_dx2, mtheta;             // g*theta/2, 2*theta/dx, -theta
   DevGeom geo;
   DevBC up, dn;
   const double *ic_h, *ic_q;
@@ -103,6 +103,14 @@ __device__ __forceinline__ double fast_sqrt(double a) {   // a >= 0; sqrt(0) = 0
   return fma(g, e * fma(e, 0.375, 0.5), g);
 }
 
+__device__ __forceinline__ double fast_sqrt_pos(double a) {   // a > 0: no guard against the infinite seed of 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double g = a * y;
+  const double e = fma(-g, y, 1.0);
+  return fma(g, e * fma(e, 0.375, 0.5), g);
+}
+
 __device__ __forceinline__ double fast_rsqrt(double a) {  // a > 0
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
@@ -112,7 +120,10 @@ __device__ __forceinline__ double fast_rsqrt(double a) {  // a > 0
 
 __device__ __forceinline__ double fast_rcbrt(double x) {  // x^(-1/3), x > 0 within float range
   const float xf = __double2float_rn(x);
-  const double r = (double)exp2f(-0.33333334f * __log2f(xf));   // ~2^-20 relative
+  float lg, sf;                                                 // raw SFU ops: no denormal fix-up code around them
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(-0.33333334f * lg));
+  const double r = (double)sf;                                  // ~2^-20 relative
   const double e = fma(-x * r, r * r, 1.0);  // x^(-1/3) = r (1 - e)^(-1/3) = r (1 + e/3 + 2e^2/9 + O(e^3))
   return fma(r, e * fma(e, 2.0 / 9.0, 1.0 / 3.0), r);
 }
@@ -259,16 +270,16 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       const double cnl = rough_fp<RM>(rg) ? rg.cnfp : GEO(F_CNL);
       const double cnr = rough_fp<RM>(rg) ? rg.cnfp : GEO(F_CNR);
       const double w = fast_rcp(Pl * Pr);
-      double Xo = (Am * Am) * fast_sqrt(Am) * (GEO(F_INVPM) * cnm);
+      double Xo = (Am * Am) * fast_sqrt_pos(Am) * (GEO(F_INVPM) * cnm);   // Am >= bankfull area > 0
       Xo = fma((Al * Al) * fast_sqrt(Al), (Pr * w) * cnl, Xo);
       Xo = fma((Ar * Ar) * fast_sqrt(Ar), (Pl * w) * cnr, Xo);
       A = over ? Ao : Ai;
       P = over ? Po : Pi;
       T = over ? To : Ti;
-      dPdh = 2.0 * (over ? sqfp : sqm);
+      dPdh = over ? sqfp : sqm;               // dP/dh / 2
       X = Xo;
     } else {
-      A = Ai; P = Pi; T = Ti; dPdh = 2.0 * sqm;
+      A = Ai; P = Pi; T = Ti; dPdh = sqm;
     }
   }
   const double PT = P * T;
@@ -285,12 +296,13 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
     const double na = nm * invA;
     invK2 = (na * na) * r4;
   }
-  const double dKA_over_K = (5.0 / 3.0) * invA - (2.0 / 3.0) * dPdh * invTP;
+  const double dKA_over_K = fma(-4.0 / 3.0, dPdh * invTP, (5.0 / 3.0) * invA);     // dPdh holds dP/dh / 2
   const double absQ = fabs(Q);
-  const double Sf = Q * absQ * invK2;                       // hydraulics.py:42-57
+  const double aq = absQ * invK2;
+  const double Sf = Q * aq;                                 // hydraulics.py:42-57
   double Se = Sf;
-  double dSeA = -2.0 * Sf * dKA_over_K;                     // hydraulics.py:59-75
-  double dSeQ = 2.0 * absQ * invK2;                         // hydraulics.py:77-92
+  double dSeA = -2.0 * Sf * dKA_over_K;                     // hydraulics.py:59-75   (dead code without curvature, see w2)
+  double dSeQ = 2.0 * aq;                                   // hydraulics.py:77-92
   double K = 0.0;
   if (WANT_K || CURV) {
     const double inm = rough_main<RM>(rg) ? rg.inm : GEO(F_INVNM);
@@ -315,7 +327,7 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
       const double den = (0.565 + sqf) * (rc * rc);
       Se += num / den;
       if (fabs(curv) > 1e-12) {
-        const double dRA = (P - A * dPdh * invT) * (invP * invP);
+        const double dRA = (P - A * (2.0 * dPdh) * invT) * (invP * invP);
         const double gD = k.g * (A * invT);
         const double rs = rsqrt(gD);                        // (gD)^-0.5, unclamped (quirk 7)
         const double dFrA = -0.5 * (Q * invA) * (rs * rs * rs) * k.g * invT + (-Q * invA * invA) * rs;
@@ -340,8 +352,13 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
   o.F = Q * QA;
   o.QA = QA;
   o.w1 = (k.th_dx * QA) * (QA * T);
-  o.w2 = (k.hth * dSeA) * T;
-  o.w3 = k.hth * dSeQ;
+  if (CURV) {
+    o.w2 = (k.hth * dSeA) * T;
+    o.w3 = k.hth * dSeQ;
+  } else {                                                  // (theta/2) * (-2 Sf dK/K) * T and (theta/2) * 2 |Q| / K^2
+    o.w2 = (k.mtheta * (Sf * dKA_over_K)) * T;
+    o.w3 = k.theta * aq;
+  }
   o.w4 = k.th_dx2 * QA;
   if (WANT_K) {
     kc->K = K;
@@ -349,7 +366,7 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
     kc->A = A;
     kc->Sf = Sf;
     kc->dSfA = -2.0 * Sf * dKA_over_K;
-    kc->dSfQ = 2.0 * absQ * invK2;
+    kc->dSfQ = 2.0 * aq;
   }
 #undef GEO
 }

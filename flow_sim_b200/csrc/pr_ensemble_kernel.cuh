@@ -440,7 +440,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     // every lane (rows beyond the chain are identity rows) holds finite data, so no guards are needed.
 #pragma unroll
     for (int s = 1; s < G; s <<= 1) {
-      if (s > Lc) break;      // uniform: the chain has Lc+1 rows
+      if (s > Lc) continue;   // uniform: the chain has Lc+1 rows (no break: the steps stay unrolled, no loop-carried moves)
 #if PR_PCR_V2
       // Elimination of the couplings to lanes gl-s (through l) and gl+s (through u).  The work for a neighbour's row
       // is done HERE, on the lane that owns the pivot block: the neighbours send their coupling vectors (2 + 2 values,
@@ -505,7 +505,14 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
       double rh = dhR, rq = dqR;       // right end of the span being unwound
 #pragma unroll
       for (int j = M - 1; j >= 1; --j) {
-        if (j < nc) {                  // node slot j was eliminated by merge j-1
+        if (EXACT) {                   // every lane holds M cells or none: no branch, padding lanes keep their copies
+          const double t1 = EL(j - 1, 6) - EL(j - 1, 4) * dh0 - EL(j - 1, 5) * dq0;
+          const double t2 = EL(j - 1, 8) - EL(j - 1, 7) * rh - p.th_dx * rq;
+          rh = EL(j - 1, 0) * t1 + EL(j - 1, 1) * t2;
+          rq = EL(j - 1, 2) * t1 + EL(j - 1, 3) * t2;
+          dh[j] = nc > 0 ? rh : 0.0;
+          dq[j] = nc > 0 ? rq : 0.0;
+        } else if (j < nc) {           // node slot j was eliminated by merge j-1
           const double t1 = EL(j - 1, 6) - EL(j - 1, 4) * dh0 - EL(j - 1, 5) * dq0;
           const double t2 = EL(j - 1, 8) - EL(j - 1, 7) * rh - p.th_dx * rq;
           dh[j] = EL(j - 1, 0) * t1 + EL(j - 1, 1) * t2;

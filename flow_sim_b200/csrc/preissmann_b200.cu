@@ -420,6 +420,7 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   p.homt = 0.5 * (1.0 - cfg->theta);
   p.ghth = cfg->g * 0.5 * cfg->theta;
   p.th_dx2 = 2.0 * cfg->theta / cfg->dx;
+  p.mtheta = -cfg->theta;
 
   // host-side look at the few geometry values the dispatch needs
   std::vector<double> curv, zb;
