@@ -107,7 +107,8 @@ LIB_PATH = os.environ.get("PR_B200_LIB") or os.path.join(_HERE, "csrc", "libprei
 #: every symbol include/preissmann_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["pr_abi_version", "pr_last_error", "pr_ensemble_run", "pr_gvf_initial_conditions",
                     "pr_rating_objective", "pr_fp64_peak", "pr_launch_count", "pr_math_probe",
-                    "pr_normal_depth_initial_conditions", "pr_derived_results", "pr_release_workspace"]
+                    "pr_normal_depth_initial_conditions", "pr_derived_results", "pr_release_workspace",
+                    "pr_long_last_trips"]
 
 _lib = None
 _lock = threading.Lock()
@@ -150,6 +151,7 @@ def load_library(path: str | None = None):
         lib.pr_derived_results.argtypes = [C.POINTER(pr_config), C.POINTER(pr_geom)] + [c_double_p] * 8 + [C.c_void_p]
         lib.pr_math_probe.restype = C.c_int
         lib.pr_release_workspace.restype = C.c_int
+        lib.pr_long_last_trips.restype = C.c_int64
         lib.pr_math_probe.argtypes = [c_double_p, C.c_int32, c_double_p]
         if lib.pr_abi_version() != PR_ABI_VERSION:
             raise PreissmannLibraryError(f"ABI mismatch: library {lib.pr_abi_version()} != python {PR_ABI_VERSION}")

@@ -22,6 +22,7 @@
 // 112 B (iterate read twice + 4 level constants per cell read twice + iterate written).
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <chrono>
 #include <cstdio>
@@ -46,35 +47,55 @@ struct LongParams {
   double *xh_out, *xq_out;   // next iterate (written by K3): tiles read their right neighbour's first node, so the
                              // update cannot be done in place
   double* pc;          // level constants [M][4][N]
-  double* tcell;       // condensed tile cells [M][T][10]
+  double* tcell;       // condensed tile cells [M][T][kTileRec]: 10 cell entries + the tile's partial ||R||^2
   double* dchain;      // updates of the tile-boundary nodes [M][T+1][2]
-  double* err2;        // [M] partial ||R||^2 (tiles)
   int *level, *it, *active, *conv, *out_level;   // [M] per-member state machine
+  int *status, *fail_level;                      // [M] the run's own record (copied to the caller's arrays when given)
   double *qprev_last, *stage_prev;               // [M] boundary bookkeeping
   GateState* gate;                               // [M] gate-controlled rating curve state
-  int* n_done;         // members finished so far
+  int* n_done;         // [0] members finished so far, [1] Newton trips made
   int T, Kc;
+  long long max_trips;
+  cudaGraphConditionalHandle loop;               // WHILE node of the trip loop (graph-driven runs)
 };
+constexpr int kTileRec = 11;
 
 static __global__ void pr_long_geometry(DevGeom g, int N, double* table) {
   stage_geometry(g, N, N, table, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, [](int i) { return i; });
 }
 
+// Device workspace of one long-reach run (iterate, level constants, tile cells: ~7 GB for config 5).  Workspaces are
+// kept in a pool and handed to one run at a time; a run returns its workspace with an event recorded behind its last
+// kernel, so the call itself need not wait for the GPU and two streams can each hold a workspace.
 struct LongWorkspace {
   static constexpr int kSlots = 32;
-  std::mutex mu;            // one long-reach run at a time per process: the cached buffers are shared
   void* ptr[kSlots] = {};
   size_t bytes[kSlots] = {};
   int device = -1;
+  bool taken = false;               // a host thread is enqueuing into it
+  cudaEvent_t done = nullptr;       // behind the last kernel of the run that used it
+  cudaStream_t capture = nullptr;   // private stream the trip loop is captured on
+  cudaGraph_t graph = nullptr;      // trip loop of the last run (kept until the workspace is taken again)
+  cudaGraphExec_t exec = nullptr;
+  int* host_flags = nullptr;        // pinned: (members done, trips) read back by polling runs
+  std::vector<std::pair<cudaGraph_t, cudaGraphExec_t>> retired;    // graphs of earlier runs, destroyed once the GPU is past them
+  void drop_graph(bool idle = true) {
+    if (graph || exec) retired.emplace_back(graph, exec);
+    exec = nullptr; graph = nullptr;
+    if (!idle) return;
+    for (auto& ge : retired) {
+      if (ge.second) cudaGraphExecDestroy(ge.second);
+      if (ge.first) cudaGraphDestroy(ge.first);
+    }
+    retired.clear();
+  }
   void release() {
+    drop_graph();
     for (int i = 0; i < kSlots; ++i) { if (ptr[i]) cudaFree(ptr[i]); ptr[i] = nullptr; bytes[i] = 0; }
   }
   void* get(int slot, size_t n, cudaError_t& e) {
     if (e != cudaSuccess) return nullptr;
     if (slot < 0 || slot >= kSlots) { e = cudaErrorInvalidValue; return nullptr; }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != device) { release(); device = dev; }
     if (bytes[slot] < n) {
       if (ptr[slot]) cudaFree(ptr[slot]);
       ptr[slot] = nullptr; bytes[slot] = 0;
@@ -84,7 +105,76 @@ struct LongWorkspace {
     return ptr[slot];
   }
 };
-inline LongWorkspace& long_workspace() { static LongWorkspace w; return w; }
+
+struct LongPool {
+  static constexpr int kPerDevice = 2;      // concurrent long-reach runs per device (each holds a full workspace)
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<LongWorkspace*> all;
+  int last_trips_device = -1;
+  const int* last_trips = nullptr;          // device counter of the most recent run (pr_long_last_trips)
+
+  // A workspace for a run on the current device whose kernels go to stream s: an idle one if there is one, a new one
+  // while fewer than kPerDevice exist, else the stream waits (on the GPU) for the one that frees up first.
+  LongWorkspace* acquire(cudaStream_t s, cudaError_t& e) {
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return nullptr;
+    std::unique_lock<std::mutex> lock(mu);
+    for (;;) {
+      LongWorkspace* pick = nullptr;
+      int mine = 0;
+      for (LongWorkspace* w : all) {
+        if (w->device != dev) continue;
+        ++mine;
+        if (w->taken) continue;
+        if (cudaEventQuery(w->done) == cudaSuccess) { pick = w; break; }     // idle
+        if (!pick) pick = w;                                                  // busy on the GPU only
+      }
+      (void)cudaGetLastError();                  // cudaErrorNotReady of the query is not an error
+      if (pick && cudaEventQuery(pick->done) != cudaSuccess && mine < kPerDevice) pick = nullptr;   // rather a fresh one
+      (void)cudaGetLastError();
+      if (!pick && mine < kPerDevice) {
+        pick = new LongWorkspace();
+        pick->device = dev;
+        e = cudaEventCreateWithFlags(&pick->done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pick->capture, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&pick->host_flags, 4 * sizeof(int));
+        if (e != cudaSuccess) { delete pick; return nullptr; }
+        all.push_back(pick);
+      }
+      if (pick) {
+        pick->taken = true;
+        const bool idle = cudaEventQuery(pick->done) == cudaSuccess;
+        (void)cudaGetLastError();
+        e = cudaStreamWaitEvent(s, pick->done, 0);      // orders our kernels behind the previous run (no-op when idle)
+        pick->drop_graph(idle);
+        return pick;
+      }
+      cv.wait(lock);                                     // every workspace of this device is being enqueued into
+    }
+  }
+  void give_back(LongWorkspace* w, cudaStream_t s) {
+    cudaEventRecord(w->done, s);
+    std::lock_guard<std::mutex> lock(mu);
+    w->taken = false;
+    cv.notify_all();
+  }
+  void release_all() {
+    std::unique_lock<std::mutex> lock(mu);
+    for (LongWorkspace* w : all) {
+      if (w->taken) continue;
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(w->device);
+      cudaEventSynchronize(w->done);
+      w->release();
+      cudaSetDevice(cur);
+    }
+    last_trips = nullptr;
+  }
+};
+inline LongPool& long_pool() { static LongPool p; return p; }
 
 template <bool CMP, bool CURV, bool IRR>
 int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches, std::string& err);
@@ -134,10 +224,10 @@ template <int MODE, bool CMP, bool CURV, bool IRR>
 __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const int lane = threadIdx.x & 31;
-  // grid = (tiles, ceil(M / 4)): the four warps of a CTA work on the SAME tile of four members, so the tile's
-  // geometry lines are fetched into L1 once per CTA
-  const int t = blockIdx.x;
-  const int m = blockIdx.y * 4 + (threadIdx.x >> 5);
+  // grid = (ceil(M / 4), tiles) - members on x, which has no 65 535 limit: the four warps of a CTA work on the SAME
+  // tile of four members, so the tile's geometry lines are fetched into L1 once per CTA
+  const int t = blockIdx.y;
+  const int m = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (m >= p.M) return;
   const int N = p.N;
   const int c0 = t * kTileCells + lane * kLongM;        // first cell / node of this lane
@@ -226,10 +316,10 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(kFull, ss, s);
     if (lane == 0) {
-      double* tc = q.tcell + ((size_t)m * q.T + t) * 10;
+      double* tc = q.tcell + ((size_t)m * q.T + t) * kTileRec;
       tc[0] = S.c1; tc[1] = S.c2; tc[2] = S.c3; tc[3] = S.c4; tc[4] = S.rc;
       tc[5] = S.m1; tc[6] = S.m2; tc[7] = S.m3; tc[8] = S.m4; tc[9] = S.rm;
-      atomicAdd(q.err2 + m, ss);
+      tc[10] = ss;      // summed in tile order by the chain kernel: the norm does not depend on the launch's timing
     }
     return;
   }
@@ -317,8 +407,10 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   int nt = T - t0;
   nt = nt < 0 ? 0 : (nt > Kc ? Kc : nt);
   Cell S;
+  double ss_tiles = 0.0;
   for (int j = 0; j < nt; ++j) {
-    const double* tc = q.tcell + ((size_t)m * T + t0 + j) * 10;
+    const double* tc = q.tcell + ((size_t)m * T + t0 + j) * kTileRec;
+    ss_tiles += tc[10];
     Cell e;
     e.c1 = tc[0]; e.c2 = tc[1]; e.c3 = tc[2]; e.c4 = tc[3]; e.rc = tc[4];
     e.m1 = tc[5]; e.m2 = tc[6]; e.m3 = tc[7]; e.m4 = tc[8]; e.rm = tc[9];
@@ -354,7 +446,9 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   }
   const double Ures = __shfl_sync(kFull, U.res, 0), Dres = __shfl_sync(kFull, D.res, Lc);
   const bool bc_failed = __any_sync(kFull, U.fail || D.fail);
-  const double err = sqrt(q.err2[m] + Ures * Ures + Dres * Dres);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) ss_tiles += __shfl_xor_sync(kFull, ss_tiles, s);      // fixed order
+  const double err = sqrt(ss_tiles + Ures * Ures + Dres * Dres);
   // ---- chain rows + PCR ----
   double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
   {
@@ -390,7 +484,6 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   // ---- the member's state machine (preissmann.py:122-161) ----
   if (lane == 0) {
     const bool converged = !bc_failed && err < p.tol;
-    q.err2[m] = 0.0;
     q.conv[m] = converged ? 1 : 0;
     q.out_level[m] = level;
     if (converged) {
@@ -403,9 +496,9 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
       if (it >= p.max_iter || bc_failed) {
         if (p.iters) p.iters[(size_t)m * (L - 1) + (level - 1)] = it;
         if (p.final_error) p.final_error[(size_t)m * (L - 1) + (level - 1)] = err;
-        if (p.status) p.status[m] = (err == err && !bc_failed) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
-        if (p.fail_level) p.fail_level[m] = level;
-        q.active[m] = 2;           // failed: K3 of this iteration is skipped by the host-side finaliser
+        q.status[m] = (err == err && !bc_failed) ? PR_STATUS_MAX_ITER : PR_STATUS_NAN;
+        q.fail_level[m] = level;
+        q.active[m] = 2;           // failed: the update pass of this trip skips the member, pr_long_retire clears it
         atomicAdd(q.n_done, 1);
       }
     }
@@ -428,6 +521,13 @@ static __global__ void pr_long_retire(const __grid_constant__ LongParams q) {
   if (m >= q.p.M) return;
   if (q.active[m] == 1 && q.level[m] >= q.p.L) { q.active[m] = 0; atomicAdd(q.n_done, 1); }
   if (q.active[m] == 2) q.active[m] = 0;
+}
+
+// End of a trip in a graph-driven run: one more trip while members are left (and the bound on the trips holds).
+static __global__ void pr_long_loop_control(const __grid_constant__ LongParams q, const int graph_driven) {
+  const int trips = q.n_done[1] + 1;
+  q.n_done[1] = trips;
+  if (graph_driven) cudaGraphSetConditional(q.loop, (q.n_done[0] < q.p.M && trips < q.max_trips) ? 1u : 0u);
 }
 
 static __global__ void pr_long_init_state(const __grid_constant__ LongParams q) {
@@ -460,27 +560,32 @@ static __global__ void pr_long_init_state(const __grid_constant__ LongParams q) 
     q.stage_prev[m] = st;
     gate_init(q.gate[m], p.dn.member_rc ? p.dn.member_rc[m] : p.dn.rc);
     if (p.storage_stage) p.storage_stage[(size_t)m * p.L] = st;
-    q.level[m] = 1; q.it[m] = 0; q.conv[m] = 0; q.out_level[m] = 0; q.err2[m] = 0.0;
+    q.level[m] = 1; q.it[m] = 0; q.conv[m] = 0; q.out_level[m] = 0;
     q.active[m] = p.L > 1 ? 1 : 0;
-    if (p.status) p.status[m] = PR_STATUS_OK;
-    if (p.fail_level) p.fail_level[m] = 0;
+    if (p.L <= 1) atomicAdd(q.n_done, 1);
+    q.status[m] = PR_STATUS_OK;
+    q.fail_level[m] = 0;
   }
 }
 
 // NaN-fill the levels a failed member never reached.
 static __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
-  const int m = blockIdx.y;
-  if (!p.status || p.status[m] == PR_STATUS_OK) return;
-  const int fl = p.fail_level[m];
+  const int m = blockIdx.x;          // members on x (no 65 535 limit), chunks of the member's rows on y
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    if (p.status) p.status[m] = q.status[m];
+    if (p.fail_level) p.fail_level[m] = q.fail_level[m];
+  }
+  if (q.status[m] == PR_STATUS_OK) return;
+  const int fl = q.fail_level[m];
   const size_t row = (p.out_mode == PR_OUT_FULL) ? (size_t)p.N : 1;
   const size_t n = (size_t)(p.L - fl) * row;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x) {
     const size_t o = ((size_t)m * p.L + fl) * row + i;
     if (p.out_h) p.out_h[o] = nan("");
     if (p.out_q) p.out_q[o] = nan("");
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
     for (int k = fl + 1; k < p.L; ++k) {
       if (p.iters) p.iters[(size_t)m * (p.L - 1) + (k - 1)] = 0;
       if (p.final_error) p.final_error[(size_t)m * (p.L - 1) + (k - 1)] = nan("");
@@ -489,26 +594,30 @@ static __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
   }
 }
 
-// Grow-only device workspace of the long-reach path, kept between calls (allocating and freeing ~7 GB per call
-// costs 50-200 ms); released by pr_release_workspace() or at process exit by the driver.
+// The run: set-up kernels, then Newton trips (K1, K2, K3, retire) until every member has finished.  The number of
+// trips is data dependent, so the trip loop is a CUDA-graph WHILE node whose condition the last kernel of a trip sets
+// on the device: the host enqueues one graph launch and returns - no per-trip synchronisation, no read-back.  (Two
+// trips per loop body because the iterate is double-buffered.)  PR_LONG_POLL=1, or a driver without conditional
+// nodes, falls back to a host loop that feeds trips in chunks and polls the done-counter one chunk behind.
 template <bool CMP, bool CURV, bool IRR>
 int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches,
                             std::string& err) {
   auto fail = [&](int code, const std::string& msg) { err = msg; return code; };
-  std::lock_guard<std::mutex> workspace_lock(long_workspace().mu);
   const int N = p.N, M = p.M;
   const int T = (N - 1 + kTileCells - 1) / kTileCells;
   const int Kc = (T + 30) / 31;           // tile cells per lane so that the chain has <= 32 rows
   if (Kc > kChainMaxK) return fail(PR_ERR_UNSUPPORTED, "long-reach path: n_nodes exceeds 32*64*128");
-  const bool timing = std::getenv("PR_LONG_TIMING") != nullptr;     // diagnostics: phase times on stderr
-  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t_start = now();
+  if (T > 65535) return fail(PR_ERR_UNSUPPORTED, "long-reach path: more than 65535 tiles");
+  cudaError_t e = cudaSuccess;
+  LongPool& pool = long_pool();
+  LongWorkspace* wsp = pool.acquire(s, e);
+  if (!wsp) return fail(PR_ERR_CUDA, std::string("long-reach workspace: ") + cudaGetErrorString(e));
+  LongWorkspace& ws = *wsp;
   LongParams q;
   q.p = p;
   q.T = T; q.Kc = Kc;
-  cudaError_t e = cudaSuccess;
+  q.max_trips = (long long)(p.L - 1) * (p.max_iter > 0 ? p.max_iter : 1) + 2;
   int slot = 0;
-  LongWorkspace& ws = long_workspace();
   auto dalloc = [&](size_t bytes) -> void* { return ws.get(slot++, bytes, e); };
   double* geo = (double*)dalloc(sizeof(double) * F_COUNT * (size_t)N);
   q.geo = geo;
@@ -517,55 +626,110 @@ int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>&
   q.xh_out = (double*)dalloc(sizeof(double) * (size_t)M * N);
   q.xq_out = (double*)dalloc(sizeof(double) * (size_t)M * N);
   q.pc = (double*)dalloc(sizeof(double) * (size_t)M * 4 * N);
-  q.tcell = (double*)dalloc(sizeof(double) * (size_t)M * T * 10);
+  q.tcell = (double*)dalloc(sizeof(double) * (size_t)M * T * kTileRec);
   q.dchain = (double*)dalloc(sizeof(double) * (size_t)M * (T + 1) * 2);
-  q.err2 = (double*)dalloc(sizeof(double) * M);
   q.qprev_last = (double*)dalloc(sizeof(double) * M);
   q.stage_prev = (double*)dalloc(sizeof(double) * M);
   q.gate = (GateState*)dalloc(sizeof(GateState) * M);
   q.level = (int*)dalloc(sizeof(int) * M); q.it = (int*)dalloc(sizeof(int) * M);
   q.active = (int*)dalloc(sizeof(int) * M); q.conv = (int*)dalloc(sizeof(int) * M);
   q.out_level = (int*)dalloc(sizeof(int) * M);
-  q.n_done = (int*)dalloc(sizeof(int));
-  auto cleanup = [&]() {};   // the workspace is cached
-  if (e != cudaSuccess) { cleanup(); return fail(PR_ERR_CUDA, std::string("long-reach workspace: ") + cudaGetErrorString(e)); }
-  const double t_alloc = now();
-  cudaMemsetAsync(q.n_done, 0, sizeof(int), s);
+  q.status = (int*)dalloc(sizeof(int) * M); q.fail_level = (int*)dalloc(sizeof(int) * M);
+  q.n_done = (int*)dalloc(sizeof(int) * 2);
+  auto bail = [&](const std::string& what) {
+    pool.give_back(wsp, s);
+    return fail(PR_ERR_CUDA, what + ": " + cudaGetErrorString(e));
+  };
+  if (e != cudaSuccess) return bail("long-reach workspace");
+  cudaMemsetAsync(q.n_done, 0, 2 * sizeof(int), s);
   cudaMemsetAsync(q.active, 0, sizeof(int) * M, s);
 
   pr_long_geometry<<<(N + 255) / 256, 256, 0, s>>>(p.geo, N, geo);
   const long long total = (long long)M * N;
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
-  const dim3 tile_grid((unsigned)T, (unsigned)((M + 3) / 4));
+  const dim3 tile_grid((unsigned)((M + 3) / 4), (unsigned)T);
   const size_t tile_smem = sizeof(double) * 4 * (kLongM - 1) * 9 * 32;   // elimination records, 4 warps per CTA
   pr_long_tile<LONG_INIT, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);
   launches.fetch_add(3);
   const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
   e = cudaFuncSetAttribute(pr_long_chain<IRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
-  int done = (p.L > 1) ? 0 : M;
-  const long long max_trips = (long long)(p.L - 1) * (p.max_iter > 0 ? p.max_iter : 1) + 1;
-  for (long long trip = 0; trip < max_trips && done < M && e == cudaSuccess; ++trip) {
-    pr_long_tile<LONG_CONDENSE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);
-    pr_long_chain<IRR><<<M, 32, chain_smem, s>>>(q);
-    pr_long_tile<LONG_UPDATE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);
-    pr_long_retire<<<(M + 127) / 128, 128, 0, s>>>(q);
-    launches.fetch_add(4);
+  if (e != cudaSuccess) return bail("long-reach chain kernel");
+  // one Newton trip of all members on stream cs; the iterate buffers swap roles after it
+  auto enqueue_trip = [&](cudaStream_t cs, int graph_driven) {
+    pr_long_tile<LONG_CONDENSE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, cs>>>(q);
+    pr_long_chain<IRR><<<M, 32, chain_smem, cs>>>(q);
+    pr_long_tile<LONG_UPDATE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, cs>>>(q);
+    pr_long_retire<<<(M + 127) / 128, 128, 0, cs>>>(q);
+    pr_long_loop_control<<<1, 1, 0, cs>>>(q, graph_driven);
     std::swap(q.xh, q.xh_out);
     std::swap(q.xq, q.xq_out);
-    e = cudaMemcpyAsync(&done, q.n_done, sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  };
+  bool graph_done = false;
+  if (p.L > 1 && !std::getenv("PR_LONG_POLL")) {
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t ge = cudaGraphCreate(&g, 0);
+    if (ge == cudaSuccess) ge = cudaGraphConditionalHandleCreate(&q.loop, g, 1, cudaGraphCondAssignDefault);
+    cudaGraph_t body = nullptr;
+    if (ge == cudaSuccess) {
+      cudaGraphNodeParams np = {};
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = q.loop;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      cudaGraphNode_t node;
+      ge = cudaGraphAddNode(&node, g, nullptr, 0, &np);
+      if (ge == cudaSuccess) body = np.conditional.phGraph_out[0];
+    }
+    if (ge == cudaSuccess) ge = cudaStreamBeginCaptureToGraph(ws.capture, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (ge == cudaSuccess) {
+      enqueue_trip(ws.capture, 1);
+      enqueue_trip(ws.capture, 1);
+      cudaGraph_t same = nullptr;
+      ge = cudaStreamEndCapture(ws.capture, &same);
+    }
+    if (ge == cudaSuccess) ge = cudaGraphInstantiate(&ex, g, 0);
+    if (ge == cudaSuccess) ge = cudaGraphLaunch(ex, s);
+    if (ge == cudaSuccess) {
+      ws.graph = g; ws.exec = ex;
+      launches.fetch_add(1);             // the trips are counted on the device (pr_long_last_trips)
+      graph_done = true;
+    } else {                             // no conditional nodes on this driver: clean up and poll instead
+      (void)cudaGetLastError();
+      if (ex) cudaGraphExecDestroy(ex);
+      if (g) cudaGraphDestroy(g);
+    }
   }
-  if (e == cudaSuccess) {
-    pr_long_nanfill<<<dim3(64, M), 256, 0, s>>>(q);
-    launches.fetch_add(1);
-    e = cudaStreamSynchronize(s);
+  if (!graph_done && p.L > 1) {
+    // host-fed trips, two per chunk; the done-counter of chunk c is read while chunk c+1 runs
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (auto& v : ev) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+    volatile int* flags = ws.host_flags;
+    flags[0] = flags[2] = 0;
+    for (long long chunk = 0; e == cudaSuccess && chunk * 2 < q.max_trips; ++chunk) {
+      enqueue_trip(s, 0);
+      enqueue_trip(s, 0);
+      launches.fetch_add(10);
+      const int k = (int)(chunk & 1);
+      e = cudaMemcpyAsync(ws.host_flags + 2 * k, q.n_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[k], s);
+      if (chunk > 0 && e == cudaSuccess) {
+        e = cudaEventSynchronize(ev[1 - k]);
+        if (flags[2 * (1 - k)] >= M) break;
+      }
+    }
+    for (auto& v : ev) if (v) cudaEventDestroy(v);
+    if (e != cudaSuccess) return bail("long-reach trips");
   }
-  if (e == cudaSuccess) e = cudaGetLastError();
-  const double t_loop = now();
-  cleanup();
-  if (timing)
-    fprintf(stderr, "[pr_long] N=%d M=%d tiles=%d Kc=%d: workspace alloc %.2f ms, kernels %.2f ms, free %.2f ms\n", N, M, T, Kc,
-            t_alloc - t_start, t_loop - t_alloc, now() - t_loop);
+  pr_long_nanfill<<<dim3((unsigned)M, 16), 256, 0, s>>>(q);
+  launches.fetch_add(1);
+  e = cudaGetLastError();
+  {
+    std::lock_guard<std::mutex> lock(pool.mu);
+    pool.last_trips = q.n_done + 1;
+    pool.last_trips_device = ws.device;
+  }
+  pool.give_back(wsp, s);
   if (e != cudaSuccess) return fail(PR_ERR_CUDA, std::string("long-reach path: ") + cudaGetErrorString(e));
   return PR_OK;
 }

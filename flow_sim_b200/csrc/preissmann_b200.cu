@@ -656,9 +656,24 @@ int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom
 }
 
 int pr_release_workspace(void) {
-  std::lock_guard<std::mutex> lock(pr::long_workspace().mu);
-  pr::long_workspace().release();
+  pr::long_pool().release_all();
   return PR_OK;
+}
+
+int64_t pr_long_last_trips(void) {
+  pr::LongPool& pool = pr::long_pool();
+  const int* ctr = nullptr;
+  int dev = -1;
+  {
+    std::lock_guard<std::mutex> lock(pool.mu);
+    ctr = pool.last_trips; dev = pool.last_trips_device;
+  }
+  if (!ctr) return -1;
+  DeviceGuard guard;
+  if (guard.enter(dev) != cudaSuccess) return -1;
+  int trips = 0;
+  if (cudaMemcpy(&trips, ctr, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;   // waits for the run
+  return trips;
 }
 
 int pr_math_probe(const double* x_host, int32_t n, double* out_host) {

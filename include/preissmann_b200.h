@@ -216,7 +216,8 @@ const char* pr_last_error(void);
  * update_guesses -> compute_residual_vector -> compute_jacobian -> spsolve -> unknowns += delta ->
  * euclidean_norm(R) < tolerance, for every time level.  Synchronous w.r.t. host buffers when
  * cfg->mem == PR_MEM_HOST; with PR_MEM_DEVICE the work is only enqueued on `cuda_stream`
- * (a cudaStream_t, NULL = default stream). */
+ * (a cudaStream_t, NULL = default stream) - also on the long-reach path, whose data-dependent number of Newton trips
+ * runs as a CUDA-graph WHILE loop on the device. */
 int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upstream,
                     const pr_bc* downstream, const pr_state* initial, const pr_outputs* out,
                     void* cuda_stream);
@@ -255,10 +256,16 @@ int pr_rating_objective(const pr_config* cfg, const double* up_flow, const doubl
  * asks for.  Runs a register-resident DFMA kernel for about `millis` ms. */
 int pr_fp64_peak(double millis, double* tflops_out);
 
-/* The long-reach path (n_nodes > 249) keeps its device workspace (iterate, level constants, tile cells) between
- * calls; this frees it.  Every entry point may be called from several host threads (pr_last_error is per thread);
- * long-reach runs share that workspace and therefore run one at a time per process. */
+/* The long-reach path (n_nodes > 249) keeps device workspaces (iterate, level constants, tile cells: ~7 GB for
+ * 100 001 nodes x 1 024 members) in a pool, up to two per device, so that two streams can run long reaches side by
+ * side; a third concurrent run waits on the GPU for the first workspace that frees up.  This call waits for the idle
+ * ones and frees them.  Every entry point may be called from several host threads (pr_last_error is per thread). */
 int pr_release_workspace(void);
+
+/* Newton trips (one trip = one iteration of every unfinished member) of the most recent long-reach run; waits for
+ * that run.  Each trip is 5 kernel launches issued from a CUDA-graph loop on the device, which pr_launch_count cannot
+ * see.  -1 when no long-reach run has been made. */
+int64_t pr_long_last_trips(void);
 
 /* Diagnostics: evaluates the device's branch-free FP64 primitives (reciprocal, square root, reciprocal square
  * root, reciprocal cube root - csrc/pr_device.cuh) and their raw SFU seeds on n HOST values;

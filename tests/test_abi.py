@@ -34,7 +34,7 @@ def test_ctypes_structs_match_header_constants():
     for name in ("PR_ABI_VERSION", "PR_MAX_POLY", "PR_MAX_GATES"):
         assert int(re.search(rf"#define {name} (\d+)", src).group(1)) == getattr(abi, name)
     # field order of the structs is what the C side reads: spot-check sizes against the documented layout
-    assert C.sizeof(abi.pr_config) == 10 * 4 + 5 * 8
+    assert C.sizeof(abi.pr_config) == 10 * 4 + 5 * 8 + 8   # + member_order (ABI 7)
     assert C.sizeof(abi.pr_geom) == 23 * 8        # 18 per-node / per-member arrays + 5 irregular-section arrays
     assert C.sizeof(abi.pr_state) == 24 and C.sizeof(abi.pr_outputs) == 7 * 8
 

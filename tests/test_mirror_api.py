@@ -183,3 +183,27 @@ def test_long_reach_builder_shapes():
     s, _ = akbari_firoozi.build_long_reach(n_nodes=501, n_steps=4)
     assert s.number_of_nodes == 501 and s.number_of_time_levels == 5
     assert np.allclose(s.channel.initial_conditions[:, 0], s.channel.initial_conditions[0, 0])
+
+
+def test_vectorised_long_reach_builder_is_bit_identical_with_the_object_model():
+    """Config 5's set-up without 100 000 section objects: every geometry column, the boundaries and the hydrograph
+    table equal what flattening the object model gives (2 001-node clone), bit for bit."""
+    from flow_sim_b200.cases.akbari_firoozi import (build_long_reach, build_long_reach_flat, flood_wave,
+                                                    flood_wave_series)
+    from flow_sim_b200.flatten import flatten_solver
+
+    solver, kw = build_long_reach(n_nodes=2001, n_steps=16)
+    a = flatten_solver(solver, tolerance=kw["tolerance"])
+    b = build_long_reach_flat(n_nodes=2001, n_steps=16)
+    assert set(a.geom) == set(b.geom)
+    for k in a.geom:
+        assert np.array_equal(a.geom[k], b.geom[k]) and a.geom[k].dtype == b.geom[k].dtype, k
+    assert (a.n_nodes, a.n_levels, a.theta, a.dt, a.dx, a.tol, a.max_iter, a.g) == (b.n_nodes, b.n_levels, b.theta, b.dt, b.dx, b.tol, b.max_iter, b.g)
+    for ba, bb in ((a.up, b.up), (a.down, b.down)):
+        assert ba.type == bb.type and ba.bed_level == bb.bed_level
+        assert (ba.series is None and bb.series is None) or np.array_equal(ba.series, bb.series)
+    assert a.down.bed_slope == b.down.bed_slope
+    assert np.array_equal(a.meta["bed_slope"], b.meta["bed_slope"]) and a.meta["z0"] == b.meta["z0"]
+    peaks = [100.0, 237.5, 300.0]
+    ref = np.array([[flood_wave(peak_flow=p)(k * a.dt) for k in range(a.n_levels)] for p in peaks])
+    assert np.array_equal(flood_wave_series(peaks, a.n_levels, a.dt), ref)

@@ -41,23 +41,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from flow_sim_b200 import abi
-    from flow_sim_b200.cases.akbari_firoozi import build_long_reach, flood_wave
+    from flow_sim_b200.cases.akbari_firoozi import build_long_reach_flat, flood_wave_series
     from flow_sim_b200.ensemble import EnsembleRunner, gather_members, shard_members
-    from flow_sim_b200.flatten import flatten_solver
+    from flow_sim_b200.runner import normal_depth_initial_conditions
 
+    dev = torch.device("cuda", local)
+    torch.cuda.synchronize()
     t0 = time.time()
-    solver, kw = build_long_reach(n_nodes=a.nodes, n_steps=a.steps)
-    flat = flatten_solver(solver, tolerance=kw["tolerance"])
+    flat = build_long_reach_flat(n_nodes=a.nodes, n_steps=a.steps)        # array arithmetic, no per-node objects
     L = flat.n_levels
     # Q_p,m = 100 + 200 m/(M-1)  
     total = a.members * world
     peaks = 100.0 + 200.0 * shard_members(total, rank, world) / max(total - 1, 1)
-    series = np.empty((a.members, L))
-    for m, pk in enumerate(peaks):
-        f = flood_wave(peak_flow=pk)
-        series[m] = [f(k * flat.dt) for k in range(L)]
+    series = flood_wave_series(peaks, L, flat.dt)
+    # steady uniform initial state: normal depth per node on the device (Channel._steady_conditions)
+    ich, icq = normal_depth_initial_conditions(flat, 1, flat.meta["initial_flow"], mem=abi.PR_MEM_DEVICE, device=dev)
+    flat.ic_depth, flat.ic_flow = ich[0].cpu().numpy(), icq[0].cpu().numpy()
     setup_s = time.time() - t0
-    dev = torch.device("cuda", local)
     runner = EnsembleRunner(flat, dev)
     ser_dev = torch.from_numpy(series).to(dev)
     times = []
@@ -101,7 +101,7 @@ def main():
         "roofline": {"bound": "hbm", "algorithmic_bytes_per_node_iteration": 48, "achieved": node_iters * 48 / secs / 1e9 / world,
                      "peak": hbm, "unit": "GB/s per GPU", "frac": node_iters * 48 / secs / 1e9 / hbm / world,
                      "moved_bytes_per_node_iteration_this_version": 112},
-        "host_setup_s": setup_s,
+        "host_setup_s": setup_s, "newton_trips": int(abi.load_library().pr_long_last_trips()),
     }
     if world > 1:
         dist.barrier()
