@@ -5,13 +5,22 @@ configs[3]: 65,536 members x 121 nodes x 32 time steps, FP64).
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores
 
-One "step" = one pass of the hot path over one batch of members: GVF initial profile per member
-(it depends on the roughness), the whole implicit time loop (32 levels, Newton + block-tridiagonal solve per
-level), and the calibration objective.  N > 1: one process per GPU under torchrun, members sharded across
-ranks (weak scaling: --members is per GPU), no traffic inside the time loop, one NCCL all_gather of the
-per-member RMSE at the end of each step.
+One "step" = one pass of the hot path over one batch of members: GVF initial profile per member (it depends on the
+roughness), the whole implicit time loop (32 levels, Newton + block-tridiagonal solve per level), and the calibration
+objective.  N > 1: one process per GPU under torchrun, members dealt round-robin over the ranks, no traffic inside the
+time loop, one NCCL all_gather at the end of each step.
 
-Prints ONE JSON line on rank 0.
+The JSON line (rank 0) carries, beside the contract's keys:
+  value / e2e     weak scaling: --members (65,536) per GPU; e2e = the same through the public API with host buffers
+  e2e_full        e2e with everything the API hands back copied to the host (iteration counts, upstream series)
+  strong          the north star's own configuration: 65,536 members IN TOTAL over the N GPUs, gather of RMSE +
+                  iteration counts + status + upstream series (43.8 MB)
+  config5         BASELINE configs[4]: 100,000-node prismatic reach x 1,024 inflow scenarios (long-reach path), with its
+                  HBM roofline (48 algorithmic bytes per node-iteration)
+  single_runs     configs 1-3 as single-member runs on the GPU next to the reference's own wall times
+  cpu_baseline    the unmodified Python reference on the host cores when it is staged (oracle/_ref), and the C port
+  parity          members of this very run against the oracle; iteration counts of the WHOLE grid against the committed
+                  oracle record (tests/golden/gerd_grid65536.oracle.npz)
 """
 from __future__ import annotations
 
@@ -29,7 +38,6 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 
-
 def load_case():
     """The gerd_roseires calibration set-up (cases/gerd_roseires/n_calibrate.py:5-17) built on the mirror API and
     flattened; bit-identical to the inputs flattened from the reference's own objects (tests/test_mirror_api.py)."""
@@ -39,12 +47,16 @@ def load_case():
     solver, kw = build_gerd(n_main=0.020, calibration=True)
     return flatten_solver(solver, tolerance=kw["tolerance"])
 
+
 Q_QUERY = np.array([1562.5, 3850, 6000, 10000, 14000, 21000.0])     # cases/gerd_roseires/n_calibrate.py:30
 H_TARGET = np.array([497.5, 500, 502, 505, 507, 510.0])             # cases/gerd_roseires/n_calibrate.py:29
 METRIC = "Preissmann node-steps/s (members x nodes x steps)"
 UNIT = "node-steps/s"
+GRID = 65536                                                        # members of the headline calibration grid
 # algorithmic FP64 flops per node per Newton iteration (FMA = 2, every other op = 1)
 F_ITER_INBANK, F_ITER_OVERBANK = 136.0, 162.0
+# the reference's own wall times of configs 1-3 (one core of the build container)
+REFERENCE_SECONDS = {"example": 0.347, "akbari_firoozi": 0.383, "gerd_roseires": 674.0}
 
 
 def member_roughness(members: np.ndarray, total: int) -> np.ndarray:
@@ -69,7 +81,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -102,7 +114,8 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (or, in the build container, the live Python reference) on the host cores
+# CPU arm: the C port of the reference algorithm (oracle/), and - where oracle/stage_reference.py has staged it - the
+# unmodified Python reference itself, on the host cores
 # ----------------------------------------------------------------------------------------------
 
 def _cpu_worker(args):
@@ -122,7 +135,7 @@ def _cpu_worker(args):
 
 
 def cpu_sample(total_members: int, per_core: int, cores: int):
-    """Times `cores*per_core` evenly spaced members of the ensemble, one process per core.
+    """Times `cores*per_core` evenly spaced members of the ensemble on the C port, one process per core.
     Returns (node-steps/s aggregate, wall seconds, members, iterations)."""
     from multiprocessing import get_context
 
@@ -144,6 +157,42 @@ def cpu_sample(total_members: int, per_core: int, cores: int):
     return node_steps / wall, wall, n_sample, sum(r[1] for r in res)
 
 
+def _pyref_worker(n_main):
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import ref_harness
+
+    secs, iters = ref_harness.time_member(float(n_main))
+    return secs, iters
+
+
+def python_reference_sample(total_members: int, cores: int, nodes: int, steps: int) -> dict | None:
+    """One member per host core through the UNMODIFIED reference (PreissmannSolver.run of cve-mohd/flow-sim, staged by
+    oracle/stage_reference.py; numpy/scipy/pandas/scikit-learn from the image).  None when it is not staged or does
+    not import.  About 30-50 s of wall time."""
+    from multiprocessing import get_context
+
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    try:
+        import ref_harness
+
+        if not ref_harness.reference_available():
+            return None
+        idx = np.linspace(0, total_members - 1, cores).round().astype(np.int64)
+        n_all = member_roughness(idx, total_members)
+        t0 = time.perf_counter()
+        with get_context("spawn").Pool(cores) as pool:      # spawn: the harness changes directory and patches pandas
+            res = pool.map(_pyref_worker, list(n_all))
+        wall = time.perf_counter() - t0
+    except Exception as exc:                                 # missing scipy / sklearn on the box, ...
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    run_s = [r[0] for r in res]
+    value = cores * nodes * steps / max(run_s)              # solver.run() only, as SURVEY.md 8d prescribes
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "per_core": value / cores,
+            "sample": f"{cores} evenly spaced members of the {total_members}-member ensemble, one per core, through the "
+                      f"unmodified Python reference (PreissmannSolver.run only; slowest member {max(run_s):.1f} s, pool wall "
+                      f"{wall:.1f} s incl. imports and set-up); Newton iterations {sum(r[1] for r in res)}"}
+
+
 def run_reference_arm(args) -> dict:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -151,23 +200,25 @@ def run_reference_arm(args) -> dict:
     cores = os.cpu_count() or 1
     total = args.members * args.gpus
     per_core = max(1, args.cpu_members_per_core)
+    flat = load_case()
+    pyref = None if args.no_python_reference else python_reference_sample(total, cores, flat.n_nodes, flat.n_levels - 1)
     vals, walls, iters = [], [], 0
     for s in range(args.warmup + args.steps):
         v, w, n_sample, it = cpu_sample(total, per_core, cores)
         if s >= args.warmup:
             vals.append(v); walls.append(w); iters += it
     value = float(np.mean(vals))
-    flat = load_case()
     sample = (f"{cores * per_core} evenly spaced members of the {total}-member ensemble per step "
-              f"({per_core} per core), C port of the reference algorithm (oracle/preissmann_oracle.c); the "
-              "reference itself is pure Python and is not present on the GPU box")
+              f"({per_core} per core), C port of the reference algorithm (oracle/preissmann_oracle.c) - about 100x faster "
+              "per core than the Python reference, so a ratio against this arm understates the speed-up over the reference")
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean(walls) * 1e3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"gerd_roseires Manning-n calibration ensemble: {total} members x {flat.n_nodes} nodes x "
                                f"{flat.n_levels - 1} steps (bounded sample, see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "per_core": value / cores, "sample": sample},
+        "python_reference": pyref,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -182,7 +233,7 @@ def run_gpu_arm(args) -> dict | None:
     import torch.distributed as dist
 
     from flow_sim_b200 import abi
-    from flow_sim_b200.ensemble import EnsembleRunner, gather_members, shard_members
+    from flow_sim_b200.ensemble import EnsembleRunner, gather_members, gather_packed, nvtx_range, shard_members
     from flow_sim_b200.runner import gvf_initial_conditions, rating_objective
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,113 +248,161 @@ def run_gpu_arm(args) -> dict | None:
         dist.init_process_group("nccl", device_id=dev)
 
     lib = abi.load_library()
-    flat = load_case()
+    with nvtx_range("flatten: case -> SoA"):
+        flat = load_case()
     N, L = flat.n_nodes, flat.n_levels
-    M = args.members                      # per GPU (weak scaling)
-    total = M * world
     runner = EnsembleRunner(flat, dev)
-    n_host = torch.from_numpy(member_roughness(shard_members(total, rank, world), total)).pin_memory()   # round-robin deal
-    n_dev = n_host.to(dev)
     q_dev = torch.from_numpy(Q_QUERY).to(dev)
     h_dev = torch.from_numpy(H_TARGET).to(dev)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
-
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def step_device(timed: dict | None):
-        """Inputs resident in HBM.  Returns the result dict (device tensors)."""
-        e = [ev() for _ in range(5)]
-        e[0].record()
-        f = runner.flat
-        import copy
-
-        f = copy.copy(f)
-        f.member_n_main = n_dev
-        ich, icq, _ = gvf_initial_conditions(f, M, flat.meta["initial_flow"], flat.meta["downstream_depth"],
-                                             abi.PR_MEM_DEVICE, dev, stream)
-        e[1].record()
-        res = runner.solve(M, member_n_main=n_dev, ic_depth=ich, ic_flow=icq, out_mode=abi.PR_OUT_UPSTREAM, stream=stream)
-        e[2].record()
-        lv, rm = rating_objective(L, res["flow"], res["depth"], flat.meta["z0"], q_dev, h_dev, abi.PR_MEM_DEVICE, dev, stream)
-        e[3].record()
-        if world > 1:
-            res["rmse_all"] = gather_members(rm, total, rank, world)      # the one collective of the run
-        e[4].record()
-        res["rmse"] = rm
-        if timed is not None:
-            timed["events"] = e
-        return res
-
-    def step_e2e():
-        """Through the public API with HOST buffers: pinned H2D of the per-member inputs, D2H of the results."""
-        res = runner.roughness_sweep(n_host, q_query=q_dev, h_target=h_dev, out_mode=abi.PR_OUT_UPSTREAM, stream=stream)
-        rmse = res["rmse"].to("cpu", non_blocking=False)
-        status = res["status"].to("cpu", non_blocking=False)
-        return rmse, status
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ----
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def make_step(members_local: int, total: int, full_gather: bool):
+        """One step with the per-member inputs resident in HBM.  Returns (step(timed) -> result dict, n_host)."""
+        import copy
+
+        n_host = torch.from_numpy(member_roughness(shard_members(total, rank, world), total)).pin_memory()   # round-robin deal
+        n_dev = n_host.to(dev)
+
+        def step(timed: dict | None):
+            e = [ev() for _ in range(5)]
+            e[0].record()
+            f = copy.copy(runner.flat)
+            f.member_n_main = n_dev
+            with nvtx_range("gvf initial conditions"):
+                ich, icq, _ = gvf_initial_conditions(f, members_local, flat.meta["initial_flow"], flat.meta["downstream_depth"],
+                                                     abi.PR_MEM_DEVICE, dev, stream)
+            e[1].record()
+            with nvtx_range("newton time loop"):
+                order = torch.argsort(n_dev, descending=True).to(torch.int32)     # rough (expensive) members first
+                res = runner.solve(members_local, member_n_main=n_dev, ic_depth=ich, ic_flow=icq, out_mode=abi.PR_OUT_UPSTREAM,
+                                   stream=stream, member_order=order)
+            e[2].record()
+            with nvtx_range("rating objective"):
+                lv, rm = rating_objective(L, res["flow"], res["depth"], flat.meta["z0"], q_dev, h_dev, abi.PR_MEM_DEVICE, dev, stream)
+            e[3].record()
+            res["rmse"] = rm
+            if world > 1:
+                with nvtx_range("gather"):                                     # the one collective of the run
+                    if full_gather:
+                        res["gathered"] = gather_packed(res, total, rank, world)
+                    else:
+                        res["rmse_all"] = gather_members(rm, total, rank, world)
+            e[4].record()
+            if timed is not None:
+                timed["events"] = e
+            return res
+
+        return step, n_host
+
+    def time_steps(step, n_steps: int, warm: int):
+        for _ in range(warm):
+            res = step(None)
+        barrier()
+        per = {"step": [], "gvf": [], "solve": [], "obj": [], "gather": []}
+        for _ in range(n_steps):
+            flush.zero_()                       # L2 flush between timed iterations (not timed)
+            barrier()
+            timed = {}
+            res = step(timed)
+            barrier()
+            e = timed["events"]
+            per["step"].append(e[0].elapsed_time(e[4])); per["gvf"].append(e[0].elapsed_time(e[1]))
+            per["solve"].append(e[1].elapsed_time(e[2])); per["obj"].append(e[2].elapsed_time(e[3]))
+            per["gather"].append(e[3].elapsed_time(e[4]))
+        return res, per
+
+    # ---- headline: weak scaling, --members per GPU, inputs resident in HBM ----
+    M = args.members
+    total = M * world
+    step_device, n_host = make_step(M, total, full_gather=False)
+    n_dev = n_host.to(dev)
+    sampler = ClockSampler(local)
     for _ in range(max(args.warmup, 3)):
         res = step_device(None)
     barrier()
-
-    # ---- timed: device-resident ----
-    sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
     launches0 = lib.pr_launch_count()
     t_wall0 = time.time()
-    step_ms, gvf_ms, solve_ms, obj_ms = [], [], [], []
-    for _ in range(args.steps):
-        flush.zero_()                       # L2 flush between timed iterations (not timed)
-        barrier()
-        timed = {}
-        res = step_device(timed)
-        barrier()
-        e = timed["events"]
-        step_ms.append(e[0].elapsed_time(e[4]))
-        gvf_ms.append(e[0].elapsed_time(e[1]))
-        solve_ms.append(e[1].elapsed_time(e[2]))
-        obj_ms.append(e[2].elapsed_time(e[3]))
+    res, per = time_steps(step_device, args.steps, 0)
     t_wall1 = time.time()
     launches = lib.pr_launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
-
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)      # max over ranks
-    total_s = float(total_ms.item()) * 1e-3
+    total_s = max_over_ranks(sum(per["step"])) * 1e-3
     node_steps_per_step = total * N * (L - 1)
     value = node_steps_per_step * args.steps / total_s
+    solve_ms = per["solve"]
 
-    # ---- timed: end to end through the public API (host buffers) ----
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e2e_ms = []
-    for _ in range(args.steps):
-        flush.zero_()
+    # ---- end to end through the public API (host buffers) ----
+    def step_e2e(full: bool):
+        """Pinned H2D of the per-member inputs, the sweep, D2H of the results: RMSE + status, or (full) everything the
+        API hands back - iteration counts and the upstream stage / discharge series as well."""
+        r = runner.roughness_sweep(n_host, q_query=q_dev, h_target=h_dev, out_mode=abi.PR_OUT_UPSTREAM, stream=stream)
+        with nvtx_range("d2h: results"):
+            out = [r["rmse"].to("cpu", non_blocking=False), r["status"].to("cpu", non_blocking=False)]
+            if full:
+                out += [r["iters"].to("cpu"), r["depth"].to("cpu"), r["flow"].to("cpu")]
+        return out
+
+    def time_e2e(full: bool, n_steps: int):
+        for _ in range(2):
+            step_e2e(full)
         barrier()
-        a, b = ev(), ev()
-        a.record()
-        rmse_host, status_host = step_e2e()
-        b.record()
-        barrier()
-        e2e_ms.append(a.elapsed_time(b))
-    e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-    e2e_value = node_steps_per_step * args.steps / (float(e2e_total.item()) * 1e-3)
+        ms = []
+        for _ in range(n_steps):
+            flush.zero_()
+            barrier()
+            a, b = ev(), ev()
+            a.record()
+            step_e2e(full)
+            b.record()
+            barrier()
+            ms.append(a.elapsed_time(b))
+        tot = max_over_ranks(sum(ms))
+        return node_steps_per_step * n_steps / (tot * 1e-3), tot / n_steps
+
+    e2e_value, e2e_ms = time_e2e(False, args.steps)
+    e2e_full_value, e2e_full_ms = time_e2e(True, max(2, min(args.steps, 5)))
+    d2h_small = int(M * 8 + M * 4)
+    d2h_full = int(d2h_small + M * (L - 1) * 4 + 2 * M * L * 8)
+
+    # ---- strong scaling: the north star's configuration, 65,536 members in total over the N GPUs ----
+    strong = None
+    if args.no_strong:
+        pass
+    elif total != GRID or world > 1:
+        if GRID % world == 0:
+            s_local = GRID // world
+            step_strong, _ = make_step(s_local, GRID, full_gather=True)
+            res_s, per_s = time_steps(step_strong, args.steps, 3)
+            s_total = max_over_ranks(sum(per_s["step"])) * 1e-3
+            gathered = res_s.get("gathered")
+            strong = {"members_total": GRID, "members_per_gpu": s_local, "n_gpus": world,
+                      "value": GRID * N * (L - 1) * args.steps / s_total, "unit": UNIT, "ms_per_step": s_total * 1e3 / args.steps,
+                      "kernel_ms": {"gvf_initial_conditions": float(np.mean(per_s["gvf"])), "ensemble_newton": float(np.mean(per_s["solve"])),
+                                    "objective": float(np.mean(per_s["obj"])), "gather": float(np.mean(per_s["gather"]))},
+                      "gather": "one all_gather of RMSE + iteration counts + status + upstream stage / discharge series",
+                      "gather_bytes": int(gathered["bytes_per_member"]) * GRID if gathered else 0}
+    else:
+        strong = {"members_total": GRID, "members_per_gpu": M, "n_gpus": 1, "value": value, "unit": UNIT,
+                  "ms_per_step": total_s * 1e3 / args.steps, "note": "at one GPU the strong and the weak configuration coincide"}
 
     # ---- work model for the roofline (SURVEY.md 8d) ----
     iters_sum = int(res["iters"].sum().item())                # Newton iterations of this rank's members
     n_bad = int((res["status"] != 0).sum().item())
-    # over-bank share of node evaluations from a 32-member full-output sample
     sidx = torch.linspace(0, M - 1, min(32, M)).round().long()
     samp = runner.roughness_sweep(n_dev[sidx.to(dev)], out_mode=abi.PR_OUT_FULL, stream=stream)
     hb = torch.from_numpy(flat.geom["h_bank"]).to(dev)
@@ -321,15 +420,15 @@ def run_gpu_arm(args) -> dict | None:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     out_bytes = M * L * 16.0 + M * (L - 1) * 4.0 + M * 8.0    # boundary series + iteration counts + status
-    traffic, pipe_pct = None, None
+    traffic, prof_note = None, None
     try:
         prof = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
         traffic = prof.get("ensemble_kernel_dram_bytes_per_launch")
-        pipe_pct = prof.get("ensemble_kernel_fp64_pipe_pct_ncu")
+        prof_note = prof.get("note")
     except Exception:
         pass
 
-    # ---- parity spot check of this very run against the CPU oracle (outside every timed region) ----
+    # ---- parity of this very run (outside every timed region) ----
     parity = None
     if rank == 0 and not args.no_parity:
         sys.path.insert(0, os.path.join(REPO, "oracle"))
@@ -349,15 +448,54 @@ def run_gpu_arm(args) -> dict | None:
             "iterations_equal": bool(np.array_equal(res["iters"][pick].cpu().numpy(), ora["iters"])),
             "against": "oracle/preissmann_oracle.c (C port pinned to the live reference)",
         }
+        # every member of this rank against the oracle's record of the whole 65,536-member grid
+        gold_path = os.path.join(REPO, "tests", "golden", "gerd_grid65536.oracle.npz")
+        if total == GRID and os.path.exists(gold_path):
+            gold = np.load(gold_path)
+            mine = shard_members(total, rank, world)
+            gi, oi = res["iters"].cpu().numpy(), gold["iters"][mine].astype(np.int32)
+            diff = gi != oi
+            flipped = np.nonzero(diff.any(axis=1))[0]
+            tol = float(gold["tol"])
+            ties = {(int(m), int(k)): (float(fe), float(pe)) for m, k, fe, pe in
+                    zip(gold["tie_member"], gold["tie_level"], gold["tie_final_error"], gold["tie_prev_error"])}
+            flips = []
+            for j in flipped:
+                k = int(np.argmax(diff[j])) + 1
+                d = int(gi[j, k - 1]) - int(oi[j, k - 1])
+                fe, pe = ties.get((int(mine[j]), k), (float("nan"), float("nan")))
+                norm = fe if d > 0 else pe
+                flips.append({"member": int(mine[j]), "level": k, "gpu_iters": int(gi[j, k - 1]), "oracle_iters": int(oi[j, k - 1]),
+                              "oracle_norm_at_decision": norm, "rel_distance_from_tol": abs(norm - tol) / tol})
+            rel_rmse = np.abs(res["rmse"].cpu().numpy() - gold["rmse"][mine]) / np.abs(gold["rmse"][mine])
+            parity["whole_grid"] = {"members": int(len(mine)), "level_steps": int(gi.size), "iteration_flips": len(flips), "flips": flips,
+                                    "max_rel_rmse_other_members": float(np.max(np.delete(rel_rmse, flipped))) if len(flipped) < len(mine) else None,
+                                    "against": "tests/golden/gerd_grid65536.oracle.npz (tools/oracle_grid.py: the oracle over the whole grid)"}
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v, w, n_sample, _ = cpu_sample(total, args.cpu_members_per_core, cores)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{n_sample} evenly spaced members of the ensemble ({w:.1f} s wall on {cores} processes); "
-                                  "C port of the reference algorithm - the Python reference itself measured 79-129 "
-                                  "node-steps/s per core on this case (BASELINE.md)"}
+    # ---- BASELINE configs[4]: the long-reach path ----
+    config5 = None
+    if not args.no_config5:
+        config5 = bench_config5(args, torch, dist, dev, rank, world, hbm_peak, max_over_ranks, barrier)
+
+    # ---- configs 1-3 as single runs; CPU baselines (rank 0, one GPU) ----
+    single = None
+    cpu_baseline, cpu_port = None, None
+    if rank == 0 and world == 1:
+        if not args.no_single_runs:
+            single = bench_single_runs(torch)
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, w, n_sample, _ = cpu_sample(total, args.cpu_members_per_core, cores)
+            cpu_port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "per_core": v / cores,
+                        "sample": f"{n_sample} evenly spaced members of the ensemble ({w:.1f} s wall on {cores} processes), "
+                                  "C port of the reference algorithm (oracle/preissmann_oracle.c)"}
+            pyref = None if args.no_python_reference else python_reference_sample(total, cores, N, L - 1)
+            if pyref and "value" in pyref:
+                cpu_baseline = pyref
+            else:
+                cpu_baseline = dict(cpu_port)
+                if pyref:
+                    cpu_baseline["python_reference"] = pyref
 
     if world > 1:
         dist.barrier()
@@ -374,27 +512,136 @@ def run_gpu_arm(args) -> dict | None:
                    "parallelism": f"members dealt round-robin over {world} GPU(s), no traffic in the time loop, one all_gather of RMSE" if world > 1 else "1 GPU",
                    "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events summed",
                    "failed_members": n_bad},
-        "kernel_ms": {"gvf_initial_conditions": float(np.mean(gvf_ms)), "ensemble_newton": float(np.mean(solve_ms)),
-                      "objective": float(np.mean(obj_ms))},
+        "kernel_ms": {"gvf_initial_conditions": float(np.mean(per["gvf"])), "ensemble_newton": float(np.mean(solve_ms)),
+                      "objective": float(np.mean(per["obj"]))},
         "newton_iterations_per_step": iters_sum / (M * (L - 1)),
         "node_iterations_per_s": iters_sum * N * world / solve_s,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8), "d2h_bytes_per_step": int(M * 8 + M * 4),
-                "ms_per_step": float(e2e_total.item()) / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8), "d2h_bytes_per_step": d2h_small,
+                "ms_per_step": e2e_ms, "copies_back": "calibration RMSE and status per member (what the calibration loop consumes)"},
+        "e2e_full": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8), "d2h_bytes_per_step": d2h_full,
+                     "ms_per_step": e2e_full_ms,
+                     "copies_back": "everything the API returns: RMSE, status, Newton iteration counts per level, upstream stage and discharge series"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s",
                      "frac": achieved_tf / tf.value if tf.value > 0 else None, "traffic": traffic,
-                     "kernel": "pr_ensemble_kernel<G=32, M=4, W=16, CURV=0, RM=1, EXACT=1>",
+                     "kernel": "pr_ensemble_kernel<G=32, M=4, W=16, CURV=0, RM=1, EXACT=1> (persistent warps)",
                      "flops_per_node_iteration": f_iter, "overbank_share": over,
-                     "fp64_pipe_pct_ncu": pipe_pct,     # from the committed ncu capture (profiles/), not this run
-
+                     "traffic_source": prof_note,
                      "peak_source": "pr_fp64_peak: register-resident DFMA microbenchmark measured in this run "
                                     "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
                      "hbm_view": {"algorithmic_bytes_per_launch": out_bytes, "achieved_gbs": out_bytes / solve_s / 1e9,
                                   "peak_gbs": hbm_peak, "note": "state stays on chip; HBM is not the bound"}},
+        "strong": strong,
+        "config5": config5,
+        "single_runs": single,
         "cpu_baseline": cpu_baseline,
+        "cpu_port": cpu_port,
         "parity": parity,
     }
+
+
+def bench_config5(args, torch, dist, dev, rank, world, hbm_peak, max_over_ranks, barrier) -> dict | None:
+    """BASELINE configs[4]: prismatic channel, 100,000 nodes x 1,024 inflow scenarios x 16 steps through the long-reach
+    path (tile kernels + chain kernel, trip loop as a CUDA-graph WHILE node).  The 1,024 scenarios are dealt over the
+    ranks (strong scaling); one gather of the upstream series at the end."""
+    from flow_sim_b200 import abi
+    from flow_sim_b200.cases.akbari_firoozi import build_long_reach_flat, flood_wave_series
+    from flow_sim_b200.ensemble import EnsembleRunner, gather_members, shard_members
+    from flow_sim_b200.runner import normal_depth_initial_conditions
+
+    lib = abi.load_library()
+    nodes, total, steps = args.config5_nodes, args.config5_members, 16
+    if total % world:
+        return None
+    torch.cuda.synchronize()
+    t0 = time.time()
+    flat = build_long_reach_flat(n_nodes=nodes, n_steps=steps)           # array arithmetic, no per-node objects
+    L = flat.n_levels
+    mine = shard_members(total, rank, world)
+    series = flood_wave_series(100.0 + 200.0 * mine / max(total - 1, 1), L, flat.dt)       # Q_p,m = 100 + 200 m/(M-1)
+    ich, icq = normal_depth_initial_conditions(flat, 1, flat.meta["initial_flow"], mem=abi.PR_MEM_DEVICE, device=dev)
+    flat.ic_depth, flat.ic_flow = ich[0].cpu().numpy(), icq[0].cpu().numpy()
+    setup_s = time.time() - t0
+    runner = EnsembleRunner(flat, dev)
+    ser_dev = torch.from_numpy(series).to(dev)
+    m_local = len(mine)
+    ms = []
+    for r in range(1 + max(2, min(args.steps, 3))):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = runner.solve(m_local, up_series=ser_dev, out_mode=abi.PR_OUT_UPSTREAM)
+        if world > 1:
+            gather_members(res["depth"], total, rank, world)
+        e1.record()
+        barrier()
+        if r > 0:
+            ms.append(e0.elapsed_time(e1))
+    trips = int(lib.pr_long_last_trips())
+    secs = max_over_ranks(float(np.mean(ms))) * 1e-3
+    it_t = res["iters"].sum().double().reshape(1)
+    bad_t = (res["status"] != 0).sum().double().reshape(1)
+    if world > 1:
+        dist.all_reduce(it_t); dist.all_reduce(bad_t)
+    iters = int(it_t.item())
+    node_iters = iters * nodes
+    out = {
+        "workload": f"prismatic channel (BASELINE configs[4]): {nodes} nodes x {total} inflow scenarios x {L - 1} steps, "
+                    f"dx = 100 m, dt = 600 s, theta = 0.6; {m_local} scenarios per GPU",
+        "n_gpus": world, "ms": secs * 1e3, "value": total * nodes * (L - 1) / secs, "unit": UNIT,
+        "node_iterations_per_s": node_iters / secs, "newton_iterations_per_step": iters / (total * (L - 1)),
+        "newton_trips": trips, "kernel_launches_per_trip": 5, "failed_members": int(bad_t.item()),
+        "roofline": {"bound": "hbm", "algorithmic_bytes_per_node_iteration": 48,
+                     "achieved": node_iters * 48 / secs / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": node_iters * 48 / secs / 1e9 / hbm_peak / world,
+                     "traffic": None, "moved_bytes_per_node_iteration": 112,
+                     "note": "48 B = read level-k state + read and write the iterate (SURVEY.md 8d); this version also reads the "
+                             "iterate and the level constants a second time for the back-substitution pass"},
+        "host_setup_s": setup_s,
+    }
+    if rank == 0 and not args.no_parity:
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import copy
+
+        import oracle_py
+
+        pick = np.array([0])
+        f2 = copy.copy(flat); f2.up = copy.copy(flat.up); f2.up.series = series[pick]
+        ora = oracle_py.run(f2, n_members=1, out_mode=abi.PR_OUT_UPSTREAM)
+        gh = res["depth"][pick].cpu().numpy()
+        out["parity"] = {"members_checked": 1, "max_rel_depth": float(np.max(np.abs(gh - ora["depth"]) / np.abs(ora["depth"]))),
+                         "iterations_equal": bool(np.array_equal(res["iters"][pick].cpu().numpy(), ora["iters"])),
+                         "against": "oracle/preissmann_oracle.c on the same member"}
+    lib.pr_release_workspace()
+    return out
+
+
+def bench_single_runs(torch) -> dict:
+    """BASELINE configs[0..2] - the three shipped cases as single-member runs through the mirror API's
+    PreissmannSolver.run() (host buffers, one member = one warp of the GPU): latency, not throughput."""
+    from flow_sim_b200.cases import build_akbari, build_example, build_gerd
+
+    out = {}
+    for name, build in (("example", build_example), ("akbari_firoozi", build_akbari), ("gerd_roseires", lambda: build_gerd())):
+        try:
+            best = None
+            for _ in range(3):
+                solver, kw = build()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                solver.run(verbose=0, **kw)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            steps = solver.number_of_time_levels - 1
+            out[name] = {"nodes": int(solver.number_of_nodes), "steps": int(steps), "newton_iterations": int(np.sum(solver.iterations)),
+                         "run_seconds": best, "node_steps_per_s": solver.number_of_nodes * steps / best,
+                         "reference_seconds": REFERENCE_SECONDS[name], "speedup_vs_reference": REFERENCE_SECONDS[name] / best}
+        except Exception as exc:
+            out[name] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    out["note"] = ("wall time of PreissmannSolver.run() incl. flattening, H2D / D2H and one kernel launch; reference_seconds = "
+                   "the reference's own run() on one core of the build container (BASELINE.md)")
+    return out
 
 
 def main():
@@ -403,10 +650,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--members", type=int, default=65536, help="ensemble members per GPU")
+    ap.add_argument("--members", type=int, default=GRID, help="ensemble members per GPU (weak scaling)")
     ap.add_argument("--cpu-members-per-core", type=int, default=24)
+    ap.add_argument("--config5-nodes", type=int, default=100_000)
+    ap.add_argument("--config5-members", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-single-runs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         line = run_reference_arm(args)

@@ -17,6 +17,31 @@ from .flatten import FlatCase, flatten_rating
 from .runner import PreparedCall, gvf_initial_conditions, rating_objective
 
 
+class nvtx_range:
+    """NVTX range around a host-side phase (flatten / H2D / GVF / Newton / objective / gather), visible in nsys / ncu
+    timelines; a no-op where torch was built without NVTX."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        try:
+            import torch
+
+            torch.cuda.nvtx.range_push(self.name)
+            self._on = True
+        except Exception:
+            self._on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self._on:
+            import torch
+
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class EnsembleRunner:
     """Holds one reach (geometry + boundary description) resident on a device and runs member batches."""
 
@@ -77,28 +102,33 @@ class EnsembleRunner:
         """The calibration ensemble (config 4): for every n_main[m] recompute the GVF initial profile
         (it depends on the roughness), run the whole simulation and, when q_query / h_target are given,
         evaluate the rating objective.  Inputs may be pinned host tensors; outputs stay on the device."""
-        n_dev = self._to_device(n_main)
-        nfp_dev = self._to_device(n_fp)
+        with nvtx_range("h2d: per-member inputs"):
+            n_dev = self._to_device(n_main)
+            nfp_dev = self._to_device(n_fp)
         M = int(n_dev.shape[0])
         f = copy.copy(self.flat)
         f.member_n_main, f.member_n_fp = n_dev, nfp_dev
         h_dn = float(self.flat.meta["downstream_depth"] if downstream_depth is None else downstream_depth)
         q_init = self.flat.meta["initial_flow"] if q0 is None else q0
-        ich, icq, ic_status = gvf_initial_conditions(f, M, q_init, h_dn, abi.PR_MEM_DEVICE, self.device, stream)
+        with nvtx_range("gvf initial conditions"):
+            ich, icq, ic_status = gvf_initial_conditions(f, M, q_init, h_dn, abi.PR_MEM_DEVICE, self.device, stream)
         # the Newton iteration total of a member grows with its roughness (409 -> 676 across the gerd grid):
         # rough members first, so that the launch ends on the cheap ones
         order = self.torch.argsort(n_dev, descending=True).to(self.torch.int32)
-        res = self.solve(M, member_n_main=n_dev, member_n_fp=nfp_dev, ic_depth=ich, ic_flow=icq, out_mode=out_mode,
-                         stream=stream, member_order=order)
+        with nvtx_range("newton time loop"):
+            res = self.solve(M, member_n_main=n_dev, member_n_fp=nfp_dev, ic_depth=ich, ic_flow=icq, out_mode=out_mode,
+                             stream=stream, member_order=order)
         res["ic_status"] = ic_status
+        _fail_rejected_profiles(res, ic_status)
         if q_query is not None:
             if out_mode == abi.PR_OUT_UPSTREAM:
                 upq, uph = res["flow"], res["depth"]
             else:
                 upq, uph = res["flow"][:, :, 0].contiguous(), res["depth"][:, :, 0].contiguous()
-            lv, rm = rating_objective(self.flat.n_levels, upq, uph, float(self.flat.meta["z0"]),
-                                      self._to_device(q_query), self._to_device(h_target), abi.PR_MEM_DEVICE,
-                                      self.device, stream)
+            with nvtx_range("rating objective"):
+                lv, rm = rating_objective(self.flat.n_levels, upq, uph, float(self.flat.meta["z0"]),
+                                          self._to_device(q_query), self._to_device(h_target), abi.PR_MEM_DEVICE,
+                                          self.device, stream)
             res["levels"], res["rmse"] = lv, rm
         return res
 
@@ -127,7 +157,45 @@ class EnsembleRunner:
         res = self.solve(M, member_n_main=f.member_n_main, member_n_fp=f.member_n_fp, up_series=up_series,
                          ic_depth=ich, ic_flow=icq, out_mode=out_mode, stream=stream, member_ratings=ratings)
         res["ic_status"] = ic_status
+        _fail_rejected_profiles(res, ic_status)
         return res
+
+
+def _fail_rejected_profiles(res: dict, ic_status) -> None:
+    """The reference refuses to start from a backwater profile that turned supercritical (RuntimeError,
+    channel.py:328-332).  In an ensemble such members are failed instead: status PR_STATUS_SUPERCRITICAL, fail level 0,
+    results NaN - never a status-0 member with meaningless numbers."""
+    import torch
+
+    bad = ic_status != 0
+    res["status"] = torch.where(bad, torch.full_like(res["status"], abi.PR_STATUS_SUPERCRITICAL), res["status"])
+    res["fail_level"] = torch.where(bad, torch.zeros_like(res["fail_level"]), res["fail_level"])
+    nan = float("nan")
+    for k in ("depth", "flow"):
+        shape = (-1,) + (1,) * (res[k].dim() - 1)
+        res[k] = torch.where(bad.view(shape), torch.full_like(res[k], nan), res[k])
+    res["iters"] = torch.where(bad.view(-1, 1), torch.zeros_like(res["iters"]), res["iters"])
+
+
+def gather_packed(res: dict, total: int, rank: int, world: int, layout: str = "strided") -> dict:
+    """The end-of-run gather of SURVEY.md 8e as ONE collective: per member the calibration RMSE, the Newton iteration
+    counts per level, the status and the upstream stage / discharge series (8 + 4 (L-1) + 4 + 16 L bytes: 668 B for the
+    gerd grid, 43.8 MB for 65,536 members) are packed into one byte row, gathered, and unpacked in member order."""
+    import torch
+
+    parts = [("rmse", res["rmse"].reshape(-1, 1)), ("iters", res["iters"]), ("status", res["status"].reshape(-1, 1)),
+             ("depth", res["depth"]), ("flow", res["flow"])]
+    rows = [t.contiguous().view(torch.uint8).reshape(t.shape[0], -1) for _, t in parts]
+    packed = torch.cat(rows, dim=1)
+    allp = gather_members(packed, total, rank, world, layout)
+    out, col = {}, 0
+    for (name, t), r in zip(parts, rows):
+        w = r.shape[1]
+        out[name] = allp[:, col:col + w].contiguous().view(t.dtype).reshape((total,) + tuple(t.shape[1:]))
+        col += w
+    out["rmse"], out["status"] = out["rmse"].reshape(-1), out["status"].reshape(-1)
+    out["bytes_per_member"] = int(packed.shape[1])
+    return out
 
 
 def to_host(res: dict) -> dict:

@@ -29,7 +29,8 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PR_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyref")     # oracle/stage_reference.py
+REFERENCE_ROOT = os.environ.get("PR_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference") else _STAGED)
 
 
 def reference_available() -> bool:
