@@ -334,7 +334,10 @@ def run_gpu_arm(args) -> dict | None:
         res = step_device(None)
     barrier()
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(1.0)                         # nvidia-smi's own start-up (NVML init) can stall a running kernel: keep it out of the timed steps
+    for _ in range(2):
+        step_device(None)                   # the GPU idled during that second: back to load clocks
+    barrier()
     launches0 = lib.pr_launch_count()
     t_wall0 = time.time()
     res, per = time_steps(step_device, args.steps, 0)
@@ -514,6 +517,7 @@ def run_gpu_arm(args) -> dict | None:
                    "failed_members": n_bad},
         "kernel_ms": {"gvf_initial_conditions": float(np.mean(per["gvf"])), "ensemble_newton": float(np.mean(solve_ms)),
                       "objective": float(np.mean(per["obj"]))},
+        "step_ms": [round(v, 3) for v in per["step"]],
         "newton_iterations_per_step": iters_sum / (M * (L - 1)),
         "node_iterations_per_s": iters_sum * N * world / solve_s,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8), "d2h_bytes_per_step": d2h_small,

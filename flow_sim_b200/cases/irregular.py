@@ -14,16 +14,22 @@ def inflow(t):
     return 60 + 40 * sin(pi * min(t, 6 * TIME_STEP) / (6 * TIME_STEP)) ** 2
 
 
-def section(invert, shift, bar=False):
-    """Main channel between stations 14 and 36, rougher overbanks; ``bar`` adds a mid-channel bar that splits low flows."""
+def section(invert, shift, bar=False, pocket=False):
+    """Main channel between stations 14 and 36, rougher overbanks.  ``bar`` adds a mid-channel bar that splits low
+    flows into two equal sub-channels (the reference's Newton iteration diverges on it); ``pocket`` adds a side pocket
+    behind a ridge on the right bank - a small second sub-channel that joins the main one once the ridge is overtopped
+    (split-flow conveyance, cross_section.py:329-439; pinned by a reference run, tests/golden/irregular_pocket.*)."""
     x = [0, 10, 14, 20, 24, 26, 30, 36, 40, 50.0] if bar else [0, 10, 14, 20, 30, 36, 40, 50.0]
     z = [6, 3.0, 1.2, 0.0, 2.6, 2.6, 0.1, 1.5, 3.2, 6.0] if bar else [6, 3.0, 1.2, 0.0, 0.1, 1.5, 3.2, 6.0]
+    if pocket:
+        x = [0, 10, 14, 20, 30, 36, 38, 39, 41, 42, 50.0]
+        z = [6, 3.0, 1.2, 0.0, 0.1, 1.5, 3.2, 1.9, 1.9, 3.2, 6.0]
     s = IrregularSection(x=np.array(x) + shift, z=np.array(z) + invert, n=0.03, bed_slope=BED_SLOPE)
     s.set_roughness_para((0.05, 0.03, 0.06, 14.0 + shift, 36.0 + shift))
     return s
 
 
-def build(bar=False, levels=8, curved=False):
+def build(bar=False, levels=8, curved=False, pocket=False):
     up = Boundary("flow_hydrograph", chainage=0, bed_level=BED_SLOPE * LENGTH, initial_depth=2.0,
                   hydrograph=Hydrograph(function=inflow))
     down = Boundary("fixed_depth", chainage=LENGTH, bed_level=0.0, initial_depth=2.0)
@@ -33,9 +39,9 @@ def build(bar=False, levels=8, curved=False):
         sx = np.linspace(0.0, LENGTH, 25)
         ch.set_coords(coords=np.column_stack([sx, 600.0 * np.sin(2 * np.pi * sx / LENGTH)]), chainages=sx * 1.0)
         stations = [0.0, 4000.0, 8000.0, LENGTH]
-        ch.set_cross_sections(stations, [section(BED_SLOPE * (LENGTH - c), c / LENGTH, bar) for c in stations])
+        ch.set_cross_sections(stations, [section(BED_SLOPE * (LENGTH - c), c / LENGTH, bar, pocket) for c in stations])
     else:
-        ch.set_cross_sections([0.0, LENGTH], [section(BED_SLOPE * LENGTH, 0.0, bar), section(0.0, 1.0, bar)])
+        ch.set_cross_sections([0.0, LENGTH], [section(BED_SLOPE * LENGTH, 0.0, bar, pocket), section(0.0, 1.0, bar, pocket)])
     solver = PreissmannSolver(channel=ch, theta=0.6, time_step=TIME_STEP, spatial_step=1000.0,
                               simulation_time=levels * TIME_STEP)
     return solver, dict(tolerance=1e-6, max_iter=60)

@@ -4,8 +4,9 @@
 // section's points in global memory, not register arithmetic.
 //
 // One wetted sub-channel (get_subchannels, :329-372) takes the base-class formulas the reference falls back to
-// (:374-439 -> :114-141).  Two or more (a bar or levee splitting the flow) are NOT evaluated: the slope comes back
-// NaN and the member stops with PR_STATUS_NAN.
+// (:374-439 -> :114-141).  Two or more (a bar or a ridge splitting the flow): every sub-channel is evaluated as a
+// section of its own and the conveyances are combined, K = (sum K_j^1.5)^(2/3), exactly as the reference does
+// (irr_split_K below; a sub-channel of more than kIrrSubMax points is refused: NaN, PR_STATUS_NAN).
 #pragma once
 #include "pr_device.cuh"
 
@@ -76,6 +77,91 @@ __device__ inline double irr_sub_K(const double* x, const double* z, int n, doub
   return A * pow(A / P, 2.0 / 3.0) / n_value;                 // hydraulics.conveyance (hydraulics.py:15-26)
 }
 
+// IrregularSection.properties / get_equivalent_n / conveyance / dR_dA / dK_dA of the polyline (x, z)[0..n) with
+// composite-roughness limits and values (cross_section.py:247-327, 441-532).
+struct IrrSec {
+  double A, P, T, R;        // properties(hw)
+  double A1, A2;            // area(hw -/+ 1e-6): dA_dh = (A2 - A1) / 2e-6 (:534-539)
+  double n_eq, dRA, K, dKA;
+};
+
+__device__ inline void irr_section(const double* x, const double* z, int n, double hw, double lim_l, double lim_r,
+                                   double nl, double nm, double nr, IrrSec& s) {
+  const double dh = 1e-6;
+  double P1, T1, P2, T2;
+  irr_properties(x, z, 0, n - 1, hw, s.A, s.P, s.T);
+  irr_properties(x, z, 0, n - 1, hw - dh, s.A1, P1, T1);
+  irr_properties(x, z, 0, n - 1, hw + dh, s.A2, P2, T2);
+  s.R = s.P > 0.0 ? s.A / s.P : 0.0;
+  const double R1 = P1 > 0.0 ? s.A1 / P1 : 0.0, R2 = P2 > 0.0 ? s.A2 / P2 : 0.0;
+  // get_equivalent_n (:441-500)
+  s.n_eq = nm;
+  if (s.A > 0.0 && s.P > 0.0) {
+    const double Kl = irr_sub_K(x, z, n, hw, x[0], lim_l, nl);
+    const double Km = irr_sub_K(x, z, n, hw, lim_l, lim_r, nm);
+    const double Kr = irr_sub_K(x, z, n, hw, lim_r, x[n - 1], nr);
+    const double K_total = pow(pow(Kl, 1.5) + pow(Km, 1.5) + pow(Kr, 1.5), 2.0 / 3.0);
+    if (K_total > 0.0) s.n_eq = (s.A * pow(s.R, 2.0 / 3.0)) / K_total;
+  }
+  // conveyance (:502-510), dR_dA (:524-532), dK_dA (:512-522 with hydraulics.dK_dA_, hydraulics.py:28-40)
+  s.K = 0.0; s.dKA = 0.0;
+  s.dRA = (s.A2 - s.A1) == 0.0 ? 0.0 : (R2 - R1) / (s.A2 - s.A1);
+  if (s.A > 0.0) {
+    s.K = s.A * pow(s.R, 2.0 / 3.0) / s.n_eq;
+    s.dKA = (pow(s.R, 2.0 / 3.0) + s.A * 2. / 3. * pow(s.R, 2.0 / 3.0 - 1.0) * s.dRA) / s.n_eq;
+  }
+}
+
+// numpy.interp(x, [xp0, xp1], [fp0, fp1]) as get_subchannels calls it (:357,361).  On the LEFT edge of a sub-channel
+// the reference passes xp = [z[start-1], z[start]], which decreases; numpy then leaves through its "beyond the last
+// abscissa" exit and returns fp1 - the first submerged point itself, not the intersection, so the sub-channel gets a
+// vertical wall there.  Reproduced as is.
+__device__ inline double irr_np_interp2(double x, double xp0, double xp1, double fp0, double fp1) {
+  if (x != x) return x;
+  if (x > xp1) return fp1;
+  if (x < xp0) return fp0;
+  if (x == xp1) return fp1;
+  const double slope = (fp1 - fp0) / (xp1 - xp0);
+  double r = slope * (x - xp0) + fp0;
+  if (r != r) {
+    r = slope * (x - xp1) + fp1;
+    if (r != r && fp0 == fp1) r = fp0;
+  }
+  return r;
+}
+
+constexpr int kIrrSubMax = 64;      // points of one wetted sub-channel, its two water-surface points included
+
+// Split flow (IrregularSection.friction_slope / dSf_dA / dSf_dQ with several sub-channels, :374-439): each run of
+// >= 2 submerged points plus the points where it meets the water surface becomes a section of its own with the
+// parent's roughness limits and values; K_eq = (sum K_j^1.5)^(2/3), dK_eq/dA = 2/3 (sum K_j^1.5)^(-1/3) sum 1.5 K_j^0.5 dK_j/dA_j.
+__device__ inline bool irr_split_K(const double* __restrict__ x, const double* __restrict__ z, int n, double hw,
+                                   double lim_l, double lim_r, double nl, double nm, double nr, double& K_eq,
+                                   double& dKA_eq) {
+  double K_sum = 0.0, dK_sum = 0.0;
+  double lx[kIrrSubMax], lz[kIrrSubMax];
+  bool ok = true;
+  for (int i = 0; i < n;) {
+    if (!(z[i] < hw)) { ++i; continue; }
+    const int start = i;
+    while (i < n && z[i] < hw) ++i;
+    const int end = i;
+    if (end - start < 2) continue;
+    if (end - start + 2 > kIrrSubMax) { ok = false; continue; }
+    int m = 0;
+    if (start > 0 && z[start - 1] > hw) { lx[m] = irr_np_interp2(hw, z[start - 1], z[start], x[start - 1], x[start]); lz[m] = hw; ++m; }
+    for (int k = start; k < end; ++k) { lx[m] = x[k]; lz[m] = z[k]; ++m; }
+    if (end < n && z[end - 1] < hw && z[end] > hw) { lx[m] = irr_np_interp2(hw, z[end - 1], z[end], x[end - 1], x[end]); lz[m] = hw; ++m; }
+    IrrSec sub;
+    irr_section(lx, lz, m, hw, lim_l, lim_r, nl, nm, nr, sub);
+    K_sum += pow(sub.K, 1.5);
+    dK_sum += 1.5 * pow(sub.K, 0.5) * sub.dKA;
+  }
+  K_eq = pow(K_sum, 2.0 / 3.0);
+  dKA_eq = (2.0 / 3.0) * pow(K_sum, -1.0 / 3.0) * dK_sum;
+  return ok;
+}
+
 // Everything the scheme needs from an irregular node: the counterpart of node_eval.
 //   T is Solver.dA_dh = the central difference of the area (:534-539), which is what the Jacobian uses.
 //   top_width (optional): the geometric top width of `properties`, which the GVF initial profile uses (channel.py:320).
@@ -90,30 +176,13 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   const double nm = rg.om ? rg.nm : g.nm[node];
   const double nl = rg.ofp ? rg.nfp : g.nl[node], nr = rg.ofp ? rg.nfp : g.nr[node];
   const double dh = 1e-6;
-  double A, P, T, A1, P1, T1, A2, P2, T2;
-  irr_properties(x, z, 0, n - 1, hw, A, P, T);
-  irr_properties(x, z, 0, n - 1, hw - dh, A1, P1, T1);
-  irr_properties(x, z, 0, n - 1, hw + dh, A2, P2, T2);
-  const double R = P > 0.0 ? A / P : 0.0;
-  const double R1 = P1 > 0.0 ? A1 / P1 : 0.0, R2 = P2 > 0.0 ? A2 / P2 : 0.0;
-  // get_equivalent_n (:441-500)
-  double n_eq = nm;
-  if (A > 0.0 && P > 0.0) {
-    const double lim_l = g.irr_left[node], lim_r = g.irr_right[node];
-    const double Kl = irr_sub_K(x, z, n, hw, x[0], lim_l, nl);
-    const double Km = irr_sub_K(x, z, n, hw, lim_l, lim_r, nm);
-    const double Kr = irr_sub_K(x, z, n, hw, lim_r, x[n - 1], nr);
-    const double K_total = pow(pow(Kl, 1.5) + pow(Km, 1.5) + pow(Kr, 1.5), 2.0 / 3.0);
-    if (K_total > 0.0) n_eq = (A * pow(R, 2.0 / 3.0)) / K_total;
-  }
-  // conveyance (:502-510), dR_dA (:524-532), dK_dA (:512-522 with hydraulics.dK_dA_, hydraulics.py:28-40)
-  double K = 0.0, dKA = 0.0;
-  const double dRA = (A2 - A1) == 0.0 ? 0.0 : (R2 - R1) / (A2 - A1);
-  if (A > 0.0) {
-    K = A * pow(R, 2.0 / 3.0) / n_eq;
-    dKA = (pow(R, 2.0 / 3.0) + A * 2. / 3. * pow(R, 2.0 / 3.0 - 1.0) * dRA) / n_eq;
-  }
-  // more than one wetted sub-channel (z < hw runs of >= 2 points): not evaluated
+  const double lim_l = g.irr_left[node], lim_r = g.irr_right[node];
+  IrrSec sec;
+  irr_section(x, z, n, hw, lim_l, lim_r, nl, nm, nr, sec);
+  const double A = sec.A, T = sec.T, R = sec.R, A1 = sec.A1, A2 = sec.A2, n_eq = sec.n_eq, dRA = sec.dRA;
+  const double K = sec.K, dKA = sec.dKA;
+  // wetted sub-channels (z < hw runs of >= 2 points): with more than one the friction slope and its derivatives take
+  // the combined conveyance of the sub-channels; everything else stays with the whole section
   int runs = 0;
   for (int i = 0; i < n;) {
     if (!(z[i] < hw)) { ++i; continue; }
@@ -121,10 +190,13 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
     while (i < n && z[i] < hw) ++i;
     runs += (i - s >= 2) ? 1 : 0;
   }
+  double Kf = K, dKAf = dKA;
+  bool refused = false;
+  if (runs > 1) refused = !irr_split_K(x, z, n, hw, lim_l, lim_r, nl, nm, nr, Kf, dKAf);
   const double absQ = fabs(Q);
-  double Sf = Q * absQ / (K * K);                              // hydraulics.Sf (hydraulics.py:42-57)
-  if (runs > 1) Sf = nan("");
-  const double dSfA = -2 * Sf * (dKA / K), dSfQ = 2 * absQ / (K * K);
+  double Sf = Q * absQ / (Kf * Kf);                            // hydraulics.Sf (hydraulics.py:42-57)
+  if (refused) Sf = nan("");
+  const double dSfA = -2 * Sf * (dKAf / Kf), dSfQ = 2 * absQ / (Kf * Kf);
   const double dAdh = (A2 - A1) / (2 * dh);
   double Se = Sf, dSeA = dSfA, dSeQ = dSfQ;
   if (CURV) {

@@ -336,24 +336,62 @@ class IrregularSection(CrossSection):
             return 0.0
         return hydraulics.dK_dA_(A=A, n=self.get_equivalent_n(hw), R=self.hydraulic_radius(hw), dR_dA=self.dR_dA(hw))
 
-    def _single_channel(self, hw):
-        if self.sub_channels(hw) > 1:
-            raise NotImplementedError("IrregularSection split into several wetted sub-channels")
+    def get_subchannels(self, hw):
+        """The separately wetted parts of the section as point lists: every run of at least two submerged points, with
+        the points where it meets the water surface added at its ends (cross_section.py:329-372).  The edge stations
+        come from ``np.interp`` called exactly as the reference calls it - on the left edge with a decreasing abscissa
+        pair, for which numpy returns the first submerged station itself (a vertical wall), not the intersection."""
+        x, z = self.x, self.z
+        parts = []
+        for first, last in self._runs(z < hw):
+            if last - first + 1 < 2:
+                continue
+            px, pz = x[first:last + 1], z[first:last + 1]
+            if first > 0 and z[first - 1] > hw:
+                px = np.insert(px, 0, np.interp(hw, [z[first - 1], z[first]], [x[first - 1], x[first]]))
+                pz = np.insert(pz, 0, hw)
+            if last + 1 < x.size and z[last] < hw and z[last + 1] > hw:
+                px = np.append(px, np.interp(hw, [z[last], z[last + 1]], [x[last], x[last + 1]]))
+                pz = np.append(pz, hw)
+            parts.append({"x": px, "z": pz})
+        return parts
+
+    def _split_conveyance(self, hw):
+        """(sum K_j^1.5, sum 1.5 K_j^0.5 dK_j/dA_j) over the sub-channels, each taken as a section of its own with this
+        section's roughness limits and values (cross_section.py:380-392, 406-414); None for a single channel."""
+        parts = self.get_subchannels(hw)
+        if len(parts) <= 1:
+            return None
+        k_sum = dk_sum = 0.0
+        for part in parts:
+            sub = IrregularSection(x=part["x"], z=part["z"])
+            sub.set_roughness_para(self.get_roughness_para())
+            k = sub.conveyance(hw)
+            k_sum += k ** 1.5
+            dk_sum += 1.5 * (k ** 0.5) * sub.dK_dA(hw)
+        return k_sum, dk_sum
 
     def friction_slope(self, h, Q):
         hw = h + self.z_min
-        self._single_channel(hw)
-        return hydraulics.Sf(Q=Q, K=self.conveyance(hw))
+        split = self._split_conveyance(hw)
+        if split is None:
+            return hydraulics.Sf(Q=Q, K=self.conveyance(hw))
+        return hydraulics.Sf(Q=Q, K=split[0] ** (2.0 / 3.0))
 
     def dSf_dA(self, h, Q):
         hw = h + self.z_min
-        self._single_channel(hw)
-        return hydraulics.dSf_dA(Q=Q, K=self.conveyance(hw), dK_dA=self.dK_dA(hw))
+        split = self._split_conveyance(hw)
+        if split is None:
+            return hydraulics.dSf_dA(Q=Q, K=self.conveyance(hw), dK_dA=self.dK_dA(hw))
+        k_sum, dk_sum = split
+        return hydraulics.dSf_dA(Q=Q, K=k_sum ** (2.0 / 3.0), dK_dA=(2.0 / 3.0) * k_sum ** (-1.0 / 3.0) * dk_sum)
 
     def dSf_dQ(self, h, Q):
         hw = h + self.z_min
-        self._single_channel(hw)
-        return hydraulics.dSf_dQ(Q=Q, K=self.conveyance(hw))
+        split = self._split_conveyance(hw)
+        if split is None:
+            return hydraulics.dSf_dQ(Q=Q, K=self.conveyance(hw))
+        return hydraulics.dSf_dQ(Q=Q, K=split[0] ** (2.0 / 3.0))
 
     # the curvature slope only needs properties / n_eq / dR_dA / dA_dh, which both section families provide
     curvature_slope = TrapezoidalSection.curvature_slope

@@ -326,9 +326,63 @@ static double xs_dK_dA(const xs_t* s, double hw) {
 static double hy_Sf(double Q, double K) { return Q * fabs(Q) / (K * K); }
 
 /* CrossSection.friction_slope / dSf_dA / dSf_dQ, cross_section.py:114-141 */
-/* IrregularSection overrides (:374-439): one wetted sub-channel -> the base-class formulas; two or more (a levee
- * splitting the flow) are NOT restated - the evaluation returns NaN and the member stops with PR_STATUS_NAN. */
+/* IrregularSection overrides (:374-439): one wetted sub-channel -> the base-class formulas.  Two or more (a bar or a
+ * ridge splitting the flow): every sub-channel is made a section of its own - its submerged points plus the points
+ * where it meets the water surface, with the PARENT's roughness limits and values (:385-387) - and the conveyances are
+ * combined as K = (sum K_j^1.5)^(2/3) (:389-392), dK/dA = 2/3 (sum K_j^1.5)^(-1/3) sum 1.5 K_j^0.5 dK_j/dA_j (:408-418). */
 static int xs_split(const xs_t* s, double hw) { return s->kind == PR_XS_IRREGULAR && irr_subchannels(s, hw) > 1; }
+
+/* numpy.interp(x, [xp0, xp1], [fp0, fp1]) as get_subchannels calls it (:357,361).  On the LEFT edge the reference passes
+ * xp = [z[start-1], z[start]], which DEcreases; numpy's interp then takes its "x beyond the last abscissa" exit and
+ * returns fp1 - the first submerged point itself, not the intersection: the sub-channel gets a vertical wall there.
+ * Reproduced as is (compiled_base.c: arr_interp). */
+static double np_interp2(double x, double xp0, double xp1, double fp0, double fp1) {
+  if (x != x) return x;
+  if (x > xp1) return fp1;
+  if (x < xp0) return fp0;
+  if (x == xp1) return fp1;
+  const double slope = (fp1 - fp0) / (xp1 - xp0);
+  double r = slope * (x - xp0) + fp0;
+  if (r != r) {                       /* numpy retries from the right end, then gives up */
+    r = slope * (x - xp1) + fp1;
+    if (r != r && fp0 == fp1) r = fp0;
+  }
+  return r;
+}
+
+/* Sum over the sub-channels of K_j^1.5 and of 1.5 K_j^0.5 dK_j/dA_j (:380-392, :406-414). */
+static void irr_split_sums(const xs_t* s, double hw, double* K_sum, double* dK_sum) {
+  *K_sum = 0.0; *dK_sum = 0.0;
+  const int n = s->np;
+  double* buf = (double*)malloc(sizeof(double) * 2 * (n + 2));
+  double *xs = buf, *zs = buf + (n + 2);
+  int i = 0;
+  while (i < n) {
+    if (!(s->pz[i] < hw)) { i += 1; continue; }
+    const int start = i;
+    while (i < n && s->pz[i] < hw) i += 1;
+    const int end = i;                                  /* one past the last submerged point */
+    if (end - start < 2) continue;
+    int m = 0;
+    if (start > 0 && s->pz[start - 1] > hw) {
+      xs[m] = np_interp2(hw, s->pz[start - 1], s->pz[start], s->px[start - 1], s->px[start]); zs[m] = hw; ++m;
+    }
+    for (int k = start; k < end; ++k) { xs[m] = s->px[k]; zs[m] = s->pz[k]; ++m; }
+    if (end < n && s->pz[end - 1] < hw && s->pz[end] > hw) {
+      xs[m] = np_interp2(hw, s->pz[end - 1], s->pz[end], s->px[end - 1], s->px[end]); zs[m] = hw; ++m;
+    }
+    /* IrregularSection(x=..., z=...) sorts by x (:226-228); the points are increasing already, and numpy's argsort
+     * keeps ties in place for arrays this short (insertion sort), which is the vertical wall of the left edge */
+    xs_t sub = *s;
+    sub.px = xs; sub.pz = zs; sub.np = m;
+    sub.z = zs[0];
+    for (int k = 1; k < m; ++k) if (zs[k] < sub.z) sub.z = zs[k];
+    const double K_j = irr_conveyance(&sub, hw);
+    *K_sum += pow(K_j, 1.5);
+    *dK_sum += 1.5 * pow(K_j, 0.5) * irr_dK_dA(&sub, hw);
+  }
+  free(buf);
+}
 
 /* CrossSection.dA_dh: top width for the trapezoids (:792-793), central difference for polylines (:534-539) */
 static double xs_dA_dh(const xs_t* s, double hw) {
@@ -339,17 +393,36 @@ static double xs_dA_dh(const xs_t* s, double hw) {
 }
 
 static double xs_friction_slope(const xs_t* s, double h, double Q) {
-  if (xs_split(s, h + s->z)) return NAN;
-  return hy_Sf(Q, xs_conveyance(s, h + s->z));
+  const double hw = h + s->z;
+  if (xs_split(s, hw)) {
+    double K_sum, dK_sum;
+    irr_split_sums(s, hw, &K_sum, &dK_sum);
+    return hy_Sf(Q, pow(K_sum, 2.0 / 3.0));
+  }
+  return hy_Sf(Q, xs_conveyance(s, hw));
 }
 static double xs_dSf_dA(const xs_t* s, double h, double Q) {
   double hw = h + s->z;
+  if (xs_split(s, hw)) {
+    double K_sum, dK_sum;
+    irr_split_sums(s, hw, &K_sum, &dK_sum);
+    const double K_eq = pow(K_sum, 2.0 / 3.0);
+    const double dK_dA_eq = (2.0 / 3.0) * pow(K_sum, -1.0 / 3.0) * dK_sum;
+    return -2 * hy_Sf(Q, K_eq) * (dK_dA_eq / K_eq);
+  }
   double K = xs_conveyance(s, hw);
   double dK = xs_dK_dA(s, hw);
   return -2 * hy_Sf(Q, K) * (dK / K);
 }
 static double xs_dSf_dQ(const xs_t* s, double h, double Q) {
-  double K = xs_conveyance(s, h + s->z);
+  const double hw = h + s->z;
+  if (xs_split(s, hw)) {
+    double K_sum, dK_sum;
+    irr_split_sums(s, hw, &K_sum, &dK_sum);
+    const double K_eq = pow(K_sum, 2.0 / 3.0);
+    return 2 * fabs(Q) / (K_eq * K_eq);
+  }
+  double K = xs_conveyance(s, hw);
   return 2 * fabs(Q) / (K * K);
 }
 

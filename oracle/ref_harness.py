@@ -288,7 +288,7 @@ if __name__ == "__main__":
     print("example iters", r["iters"].tolist(), r["depth"].sum(), r["flow"].sum(), r["seconds"])
 
 
-def build_irregular(levee: bool = False, curved: bool = False):
+def build_irregular(levee: bool = False, curved: bool = False, pocket: bool = False):
     """Synthetic companion case for IrregularSection (no shipped case instantiates it): a 12 km
     reach between two surveyed-style polylines with composite roughness, interpolated node by node
     (cross_section.py:933-969), flow hydrograph upstream, fixed depth downstream."""
@@ -314,6 +314,11 @@ def build_irregular(levee: bool = False, curved: bool = False):
         if levee:       # a mid-channel bar that splits low flows into two wetted sub-channels
             x = np.array([0, 10, 14, 20, 24, 26, 30, 36, 40, 50.0]) + shift
             z = np.array([6, 3.0, 1.2, 0.0, 2.6, 2.6, 0.1, 1.5, 3.2, 6.0]) + z0
+        if pocket:      # a side pocket behind a ridge on the right bank: a second, small wetted sub-channel at low stages
+            # (split-flow conveyance, cross_section.py:329-439) that joins the main channel once the ridge is overtopped;
+            # unlike the bar of `levee`, the reference's Newton iteration survives this one
+            x = np.array([0, 10, 14, 20, 30, 36, 38, 39, 41, 42, 50.0]) + shift
+            z = np.array([6, 3.0, 1.2, 0.0, 0.1, 1.5, 3.2, 1.9, 1.9, 3.2, 6.0]) + z0
         s = IrregularSection(x=x, z=z, n=0.03, bed_slope=S0)
         s.set_roughness_para((0.05, 0.03, 0.06, 14.0 + shift, 36.0 + shift))
         return s

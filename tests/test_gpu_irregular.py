@@ -83,16 +83,50 @@ def test_mixed_reach_and_other_boundaries():
 
 
 def test_split_flow_is_refused_per_member_not_emulated():
-    """A mid-channel bar that splits low flows into two wetted sub-channels: the reference switches to its
-    multi-sub-channel conveyance there, which is not built; oracle and device both stop the member with
-    PR_STATUS_NAN instead of returning single-channel numbers."""
+    """A mid-channel bar that splits low flows into two equal sub-channels.  The reference's own Newton iteration
+    diverges on this case (negative depths and a ZeroDivisionError in level 1); with the split-flow conveyance built,
+    oracle and device follow it there and stop the member in the same level with PR_STATUS_NAN."""
     import oracle_py
 
     flat = util.golden_inputs("irregular_levee")        # oracle/ref_harness.build_irregular(levee=True)
     ora = oracle_py.run(flat)
     out = run_flat(flat)
     assert ora["status"][0] == abi.PR_STATUS_NAN and out["status"][0] == abi.PR_STATUS_NAN
-    assert out["fail_level"][0] == ora["fail_level"][0]
+    assert out["fail_level"][0] == ora["fail_level"][0] == 1
+
+
+@pytest.mark.parametrize("lanes", [0, -1])
+def test_split_flow_reach_matches_the_reference_run(lanes):
+    """Split flow the reference survives (tests/golden/irregular_pocket.*: a side pocket behind a ridge; 75 of its 117
+    node-levels run on the multi-sub-channel conveyance, the rest on the single-channel formulas, with the switch in
+    the middle of the run): fused kernel and tile kernels against the reference's own run."""
+    flat = util.golden_inputs("irregular_pocket")
+    ref = util.golden_outputs("irregular_pocket")
+    out = run_flat(flat, lanes=lanes)
+    assert out["status"][0] == abi.PR_STATUS_OK
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], f"irregular_pocket, lanes={lanes}")
+    assert np.array_equal(out["iters"][0], ref["iters"])
+
+
+def test_split_flow_roughness_ensemble():
+    """64 roughness members of the side-pocket reach (GVF profile per member on the device, split and single-channel
+    nodes side by side) against the oracle."""
+    import oracle_py
+    from flow_sim_b200.runner import gvf_initial_conditions
+
+    flat = util.golden_inputs("irregular_pocket")
+    M = 64
+    flat.member_n_main = np.linspace(0.024, 0.036, M)
+    h, q, st = gvf_initial_conditions(flat, M, 60.0, 2.0)
+    oh, oq, ost = oracle_py.gvf(flat, 60.0, 2.0, n_members=M)
+    assert np.array_equal(st, ost) and util.max_rel(h, oh) <= 1e-11
+    flat.ic_depth, flat.ic_flow = oh, oq
+    ora = oracle_py.run(flat, n_members=M, out_mode=abi.PR_OUT_UPSTREAM, trace_prev_error=True)
+    out = run_flat(flat, n_members=M, out_mode=abi.PR_OUT_UPSTREAM)
+    assert np.array_equal(out["status"], ora["status"])
+    ok = np.nonzero(ora["status"] == 0)[0]
+    assert len(ok) > M // 2
+    util.assert_iteration_parity(out, ora, flat.tol, "irregular_pocket ensemble", members=ok)
 
 
 def test_refused_combinations():
@@ -143,8 +177,13 @@ def test_mirror_solver_run_with_polyline_sections():
     util.assert_parity(solver.depth, solver.flow, ref["depth"], ref["flow"], "mirror run, irregular")
     assert np.array_equal(solver.iterations, ref["iters"])
     assert solver.area.shape == solver.depth.shape and np.all(solver.top_width > 0) and np.all(solver.froude_number < 1)
-    with pytest.raises(ValueError, match="Convergence|NaN"):
+    with pytest.raises(ValueError, match="Convergence|NaN"):      # the bar case: the reference itself diverges in level 1
         build_irregular(bar=True)[0].run(verbose=0, **kw)
+    pocket, kw = build_irregular(pocket=True)                     # split flow through the mirror API
+    pocket.run(verbose=0, **kw)
+    ref = util.golden_outputs("irregular_pocket")
+    util.assert_parity(pocket.depth, pocket.flow, ref["depth"], ref["flow"], "mirror run, irregular_pocket")
+    assert np.array_equal(pocket.iterations, ref["iters"])
 
 
 def test_general_storage_with_head_losses_behind_a_polyline_node():

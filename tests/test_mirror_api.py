@@ -43,6 +43,7 @@ def _same_flat(a, b):
     ("irregular", lambda: build_irregular()),
     ("irregular_levee", lambda: build_irregular(bar=True)),
     ("irregular_curved", lambda: build_irregular(curved=True)),
+    ("irregular_pocket", lambda: build_irregular(pocket=True)),
 ])
 def test_case_builders_reproduce_reference_inputs(case, builder):
     solver, kw = builder()
@@ -98,8 +99,26 @@ def test_irregular_section_mirror_equals_the_oracle_restatement():
                 assert abs(got[k] - v) <= 1e-13 * abs(v), k
     bar = build_irregular(bar=True)[0].channel.xs_at_node[4]
     assert bar.sub_channels(bar.z_min + 1.0) == 2 and bar.sub_channels(bar.z_min + 4.0) == 1
-    with pytest.raises(NotImplementedError, match="sub-channels"):
-        bar.friction_slope(1.0, 60.0)
+
+
+def test_split_flow_conveyance_equals_the_reference():
+    """Several wetted sub-channels (cross_section.py:329-439): friction slope and its derivatives of the side-pocket
+    sections, on the oracle and on the mirror, against values computed by the live reference when the fixture was made
+    (tests/golden/irregular_pocket_probe.npz: 252 probes, 114 of them split) - bit for bit."""
+    import oracle_py
+
+    fx = np.load(f"{util.GOLD}/irregular_pocket_probe.npz")
+    rows = fx["rows"]
+    assert (rows[:, 3] > 1).sum() > 100
+    flat = util.golden_inputs("irregular_pocket")
+    sections = build_irregular(pocket=True)[0].channel.xs_at_node
+    for node, h, Q, nsub, Sf, dSfA, dSfQ, K, dKA, A, dAdh in rows:
+        got = oracle_py.section_probe(flat, int(node), h, Q)
+        assert (got["Sf"], got["dSf_dA"], got["dSf_dQ"]) == (Sf, dSfA, dSfQ), (node, h)
+        xs = sections[int(node)]
+        assert len(xs.get_subchannels(h + xs.z_min)) == int(nsub)
+        assert (xs.friction_slope(h, Q), xs.dSf_dA(h, Q), xs.dSf_dQ(h, Q)) == (Sf, dSfA, dSfQ), (node, h)
+        assert (xs.conveyance(h + xs.z_min), xs.dK_dA(h + xs.z_min)) == (K, dKA)
 
 
 def test_flat_roundtrip(tmp_path):
