@@ -140,6 +140,7 @@ struct DerivedParams {
   int N;
   double g;
   const double* geo;
+  DevGeom raw;       // polylines of the IrregularSection nodes
   const double *depth, *flow;
   double *level, *area, *top_width, *froude, *velocity, *celerity;
 };
@@ -152,14 +153,19 @@ __global__ void __launch_bounds__(128) pr_derived_kernel(const __grid_constant__
 #define GEO(f) p.geo[(size_t)(f) * p.N + nd]
   const double z = GEO(F_Z), b = GEO(F_B), hb = GEO(F_HB), m2 = 2.0 * GEO(F_M);
   const double mfp = GEO(F_MFP), bl = GEO(F_BL), br = GEO(F_BR), amf = GEO(F_AMF), wb = GEO(F_WB);
+  const bool irregular = GEO(F_KIND) == (double)PR_XS_IRREGULAR;
 #undef GEO
+  const int poly_off = irregular ? p.raw.irr_offset[nd] : 0, poly_n = irregular ? p.raw.irr_offset[nd + 1] - poly_off : 0;
   for (long long r = blockIdx.y; r < p.rows; r += gridDim.y) {
     const size_t i = (size_t)r * p.N + nd;
     const double h = p.depth[i], Q = p.flow[i];
     const double hw = z + h;
     const double d = fmax(0.0, hw - z);
     double A, T;
-    if (d <= hb) {               // rectangle / simple trapezoid / compound in bank (h_bank staged as 1e300 otherwise)
+    if (irregular) {             // IrregularSection.properties (cross_section.py:247-327): area and geometric top width
+      double P;
+      irr_properties(p.raw.irr_x + poly_off, p.raw.irr_z + poly_off, 0, poly_n - 1, hw, A, P, T);
+    } else if (d <= hb) {        // rectangle / simple trapezoid / compound in bank (h_bank staged as 1e300 otherwise)
       T = b + m2 * d;
       A = (b + T) / 2.0 * d;
       if (d <= 0.0) { A = 0.0; T = 0.0; }
@@ -201,6 +207,15 @@ __device__ __forceinline__ double normal_flow_residual(const NormalDepthParams& 
   const double z = p.geo[(size_t)F_Z * p.N + nd];
   const double depth = hw - z;
   if (!(depth > 0.0)) return Qt;                    // K(0) = 0
+  if (p.geo[(size_t)F_KIND * p.N + nd] == (double)PR_XS_IRREGULAR) {
+    // IrregularSection.conveyance of the whole section (normal_flow does not split, cross_section.py:177-182, 502-510)
+    const int off = p.raw.irr_offset[nd], n = p.raw.irr_offset[nd + 1] - off;
+    const double nm = rg.om ? rg.nm : p.raw.nm[nd];
+    const double nl = rg.ofp ? rg.nfp : p.raw.nl[nd], nr = rg.ofp ? rg.nfp : p.raw.nr[nd];
+    IrrSec sec;
+    irr_section(p.raw.irr_x + off, p.raw.irr_z + off, n, hw, p.raw.irr_left[nd], p.raw.irr_right[nd], nl, nm, nr, sec);
+    return Qt - sec.K * sqrt(S0);
+  }
   NodeVals nv;
   NodeConv kc;
   node_eval<false, RM, true, NormalDepthParams>(p.geo, p.N, nd, depth, 0.0, rg, p, nv, &kc);

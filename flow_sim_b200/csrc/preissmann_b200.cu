@@ -326,17 +326,6 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
   return PR_OK;
 }
 
-// true when some node is an IrregularSection (the setup kernels below take the trapezoid kinds only)
-int any_irregular(const pr_config& cfg, const pr_geom* g, bool& found) {
-  found = false;
-  if (!g || !g->kind) return fail(PR_ERR_ARG, "geom is incomplete");
-  std::vector<int32_t> kinds((size_t)cfg.n_nodes);
-  if (cfg.mem == PR_MEM_HOST) std::memcpy(kinds.data(), g->kind, kinds.size() * sizeof(int32_t));
-  else CUDA_TRY(cudaMemcpy(kinds.data(), g->kind, kinds.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  for (int32_t kd : kinds) found |= (kd == PR_XS_IRREGULAR);
-  return PR_OK;
-}
-
 // Tuning hook (tools/ab_build.sh): PR_M4_VARIANT=<variant .so> replaces the 32-lane x 4-node family of this library by
 // the one in that file, so that A/B builds of the headline kernel need not carry the whole library.
 using m4_variant_fn = int (*)(const pr::DevParams*, int, cudaStream_t);
@@ -573,11 +562,6 @@ int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* 
                        double* celerity, void* cuda_stream) {
   DeviceGuard guard;
   if (int rc = check_config(cfg, guard)) return rc;
-  {
-    bool irr = false;
-    if (int rc = any_irregular(*cfg, geom, irr)) return rc;
-    if (irr) return fail(PR_ERR_UNSUPPORTED, "derived result arrays on the device: irregular sections are not covered");
-  }
   if (!depth || !flow) return fail(PR_ERR_ARG, "derived results: depth / flow are NULL");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t N = cfg->n_nodes, total = (size_t)cfg->n_members * cfg->n_levels * N;
@@ -594,6 +578,7 @@ int pr_derived_results(const pr_config* cfg, const pr_geom* geom, const double* 
   if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
   st.allocs.push_back(table);
   p.geo = table;
+  p.raw = dg;
   pr::pr_long_geometry<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(dg, (int)N, table);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -616,11 +601,6 @@ int pr_normal_depth_initial_conditions(const pr_config* cfg, const pr_geom* geom
                                        double* ic_flow, void* cuda_stream) {
   DeviceGuard guard;
   if (int rc = check_config(cfg, guard)) return rc;
-  {
-    bool irr = false;
-    if (int rc = any_irregular(*cfg, geom, irr)) return rc;
-    if (irr) return fail(PR_ERR_UNSUPPORTED, "normal-depth initial conditions on the device: irregular sections are not covered");
-  }
   if (!bed_slope || !q0 || !ic_depth || !ic_flow) return fail(PR_ERR_ARG, "normal depth: NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t N = cfg->n_nodes, M = cfg->n_members;

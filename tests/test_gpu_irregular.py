@@ -129,14 +129,31 @@ def test_split_flow_roughness_ensemble():
     util.assert_iteration_parity(out, ora, flat.tol, "irregular_pocket ensemble", members=ok)
 
 
-def test_refused_combinations():
-    from flow_sim_b200.abi import PreissmannLibraryError
-    from flow_sim_b200.runner import gvf_initial_conditions
+def test_derived_arrays_and_normal_depth_on_polyline_sections():
+    """The set-up and post-processing kernels take IrregularSection nodes: derived result arrays (area, top width,
+    Froude number, velocity, celerity - Solver.prepare_results) and the steady normal-depth initial state
+    (Channel._steady_conditions) against the mirror's host-side section objects."""
+    from flow_sim_b200.cases import build_irregular
+    from flow_sim_b200.flatten import flatten_solver
+    from flow_sim_b200.runner import derived_results, normal_depth_initial_conditions
 
-    from flow_sim_b200.runner import derived_results
-    flat = util.golden_inputs("irregular")
-    with pytest.raises(PreissmannLibraryError, match="irregular"):
-        derived_results(flat, np.full((1, flat.n_levels, flat.n_nodes), 2.0), np.full((1, flat.n_levels, flat.n_nodes), 60.0))
+    solver, kw = build_irregular(pocket=True)
+    flat = flatten_solver(solver, **kw)
+    xs = solver.channel.xs_at_node
+    rng = np.random.default_rng(4)
+    M, L, N = 3, flat.n_levels, flat.n_nodes
+    depth = rng.uniform(0.6, 4.5, (M, L, N))
+    flow = rng.uniform(20.0, 120.0, (M, L, N))
+    got = derived_results(flat, depth, flow)
+    area = np.array([[[xs[i].area(depth[m, k, i] + xs[i].z_min) for i in range(N)] for k in range(L)] for m in range(M)])
+    top = np.array([[[xs[i].top_width(depth[m, k, i] + xs[i].z_min) for i in range(N)] for k in range(L)] for m in range(M)])
+    assert util.max_rel(got["area"], area) <= 1e-13 and util.max_rel(got["top_width"], top) <= 1e-13
+    assert util.max_rel(got["velocity"], flow / area) <= 1e-13
+    assert util.max_rel(got["wave_celerity"], flow / area + np.sqrt(flat.g * area / top)) <= 1e-13
+    # normal depth: the root of Q - K(hw) sqrt(S0) per node, brentq on the host / Brent's method on the device
+    h, q = normal_depth_initial_conditions(flat, 1, 60.0)
+    host = np.array([s.normal_depth(Q_target=60.0) for s in xs])
+    assert np.max(np.abs(h[0] - host)) <= 1e-10 and np.all(q == 60.0)
 
 
 def test_backwater_profile_and_roughness_sweep_on_polyline_sections():
