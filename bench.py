@@ -599,9 +599,13 @@ def bench_config5(args, torch, dist, dev, rank, world, hbm_peak, max_over_ranks,
         "roofline": {"bound": "hbm", "algorithmic_bytes_per_node_iteration": 48,
                      "achieved": node_iters * 48 / secs / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
                      "frac": node_iters * 48 / secs / 1e9 / hbm_peak / world,
-                     "traffic": None, "moved_bytes_per_node_iteration": 112,
-                     "note": "48 B = read level-k state + read and write the iterate (SURVEY.md 8d); this version also reads the "
-                             "iterate and the level constants a second time for the back-substitution pass"},
+                     "algorithmic_bytes_per_launch": 48.0 * nodes * m_local,
+                     "traffic": 74.0 * nodes * m_local, "moved_bytes_per_node_iteration": 64,
+                     "note": "48 B = read level-k state + read and write the iterate (SURVEY.md 8d); the fused tile kernel moves 64 B "
+                             "(level-k state kept as four constants per cell) plus 32 B where a level is accepted - measured "
+                             "1.24 GB read + 0.43-0.83 GB written per trip of 25.6 M nodes (profiles/r02d_ncu_long_fused_launches.csv); "
+                             "traffic = 74 B per node per launch of the tile kernel, from that capture scaled to this launch; "
+                             "the kernel is bound by FP64 latency, not by HBM"},
         "host_setup_s": setup_s,
     }
     if rank == 0 and not args.no_parity:

@@ -1,25 +1,22 @@
 // pr_long_kernels.cuh - long-reach path (N > 249 nodes: one member no longer fits one warp's registers).
 //
 // State (current iterate, level constants) lives in HBM; a reach is cut into TILES of 128 cells, one warp per
-// (member, tile), lane l owning 4 consecutive cells exactly as in the fused kernel.  One Newton iteration of
-// ALL members is three launches:
+// (member, tile), lane l owning 4 consecutive cells exactly as in the fused kernel.  One Newton trip of ALL members:
 //
-//   K1  pr_long_tile<CONDENSE>   per tile: node pass, cell pass, per-lane Schur condensation, warp tree-merge
-//                                -> ONE condensed cell per tile (10 doubles) + partial ||R||^2
-//   K2  pr_long_chain            per member (one warp): the <= 32*Kc tile cells + both boundary rows:
-//                                serial condensation per lane, parallel cyclic reduction, back-substitution
-//                                -> update of every tile-boundary node; convergence test, level/iteration
-//                                bookkeeping (the member's state machine lives here)
-//   K3  pr_long_tile<UPDATE>     per tile: re-assemble (recomputing is cheaper than storing 9 doubles per
-//                                node), solve the tile interior with its two end nodes known, x += delta;
-//                                when the level was accepted also write the stored level and refresh the
-//                                level constants
+//   pr_long_chain   per member (one warp): the <= 32*Kc condensed tile cells + both boundary rows: serial condensation
+//                   per lane, parallel cyclic reduction, back-substitution -> update of every tile-boundary node;
+//                   convergence test, level / iteration bookkeeping (the member's state machine lives here)
+//   pr_long_retire, pr_long_loop_control   member retirement; one more trip? (the WHILE condition of the graph loop)
+//   pr_long_fused   per tile: finish the trip (re-assemble - cheaper than storing 9 doubles per node -, solve the tile
+//                   interior with its two end nodes known, x += delta; when the level was accepted write it out and
+//                   refresh the level constants) and start the next one on the new iterate (node pass, cell pass,
+//                   per-lane Schur condensation, warp tree-merge -> ONE condensed cell per tile + partial ||R||^2)
 //
 // Same algebra as pr_ensemble_kernel.cuh (cell_assemble / merge_cells / PCR); block cyclic reduction is
 // applied hierarchically: lane (4 cells) -> tile (32 lanes) -> chain (<= 32 x Kc tiles).
-// The iterate is double-buffered (K3 reads a tile's right neighbour node while that neighbour's tile updates it).
-// Algorithmic HBM traffic is 48 B per node per Newton iteration; this first version moves
-// 112 B (iterate read twice + 4 level constants per cell read twice + iterate written).
+// The iterate is double-buffered (a tile reads its right neighbour's first node while that tile rewrites it).
+// Algorithmic HBM traffic is 48 B per node per Newton iteration; the fused tile kernel moves 64 B
+// (iterate read, 4 level constants per cell read, iterate written) + the constants rewritten at accepted levels.
 #pragma once
 #include <atomic>
 #include <condition_variable>
@@ -44,7 +41,7 @@ struct LongParams {
   DevParams p;
   const double* geo;   // derived geometry table [F_COUNT][N] (stage_geometry layout, NP = N)
   double *xh, *xq;     // current iterate [M][N] (read)
-  double *xh_out, *xq_out;   // next iterate (written by K3): tiles read their right neighbour's first node, so the
+  double *xh_out, *xq_out;   // next iterate (written by the tile kernel): tiles read their right neighbour's first node, so the
                              // update cannot be done in place
   double* pc;          // level constants [M][4][N]
   double* tcell;       // condensed tile cells [M][T][kTileRec]: 10 cell entries + the tile's partial ||R||^2
@@ -180,32 +177,34 @@ template <bool CMP, bool CURV, bool IRR>
 int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>& launches, std::string& err);
 
 #ifndef PR_LONG_DECLARE_ONLY   // the kernels and the driver loop: compiled once per variant in pr_long_v*.cu
-enum LongMode { LONG_INIT = 0, LONG_CONDENSE = 1, LONG_UPDATE = 2 };
 
 
-// PCR over the 32 lanes of a warp for block rows  [l | d | u] y = r  with rank-1 couplings (see the fused kernel).
+// PCR over the 32 lanes of a warp for block rows  [l | d | u] y = r  with rank-1 couplings (see the fused kernel:
+// the lane that owns a pivot block does the elimination work for its two neighbours - 14 values exchanged per step).
 __device__ __forceinline__ void pcr32(double& l1, double& l2, double& d11, double& d12, double& d21, double& d22,
                                       double& u1, double& u2, double& ra, double& rb, const int rows, const int lane,
                                       double& y1, double& y2) {
+#define SH(v, src) __shfl_sync(kFull, v, src)
 #pragma unroll
   for (int s = 1; s < 32; s <<= 1) {
-    if (s >= rows) break;
+    if (s >= rows) continue;
+    const int up = (lane - s) & 31, dn = (lane + s) & 31;
+    const double Dl1 = SH(l1, dn), Dl2 = SH(l2, dn);       // l of lane + s
+    const double Uu1 = SH(u1, up), Uu2 = SH(u2, up);       // u of lane - s
     const double idet = fast_rcp(d11 * d22 - d12 * d21);
     const double i11 = d22 * idet, i12 = -d12 * idet, i21 = -d21 * idet, i22 = d11 * idet;
-    const int up = (lane - s) & 31, dn = (lane + s) & 31;
-#define SH(v, src) __shfl_sync(kFull, v, src)
-    const double a1 = l1 * SH(i11, up) + l2 * SH(i21, up), a2 = l1 * SH(i12, up) + l2 * SH(i22, up);
-    const double b1 = u1 * SH(i11, dn) + u2 * SH(i21, dn), b2 = u1 * SH(i12, dn) + u2 * SH(i22, dn);
-    const double Pl1 = SH(l1, up), Pl2 = SH(l2, up), Pu1 = SH(u1, up), Pu2 = SH(u2, up), Pra = SH(ra, up), Prb = SH(rb, up);
-    const double Nl1 = SH(l1, dn), Nl2 = SH(l2, dn), Nu1 = SH(u1, dn), Nu2 = SH(u2, dn), Nra = SH(ra, dn), Nrb = SH(rb, dn);
-#undef SH
-    l1 = -a1 * Pl1;  l2 = -a1 * Pl2;
-    d11 -= a2 * Pu1; d12 -= a2 * Pu2;
-    ra -= a1 * Pra + a2 * Prb;
-    u1 = -b2 * Nu1;  u2 = -b2 * Nu2;
-    d21 -= b1 * Nl1; d22 -= b1 * Nl2;
-    rb -= b1 * Nra + b2 * Nrb;
+    const double a1 = Dl1 * i11 + Dl2 * i21, a2 = Dl1 * i12 + Dl2 * i22;
+    const double o_l1 = -a1 * l1, o_l2 = -a1 * l2, o_d1 = a2 * u1, o_d2 = a2 * u2, o_r = a1 * ra + a2 * rb;
+    const double b1 = Uu1 * i11 + Uu2 * i21, b2 = Uu1 * i12 + Uu2 * i22;
+    const double o_u1 = -b2 * u1, o_u2 = -b2 * u2, o_e1 = b1 * l1, o_e2 = b1 * l2, o_s = b1 * ra + b2 * rb;
+    l1 = SH(o_l1, up);  l2 = SH(o_l2, up);
+    d11 -= SH(o_d1, up); d12 -= SH(o_d2, up);
+    ra -= SH(o_r, up);
+    u1 = SH(o_u1, dn);  u2 = SH(o_u2, dn);
+    d21 -= SH(o_e1, dn); d22 -= SH(o_e2, dn);
+    rb -= SH(o_s, dn);
   }
+#undef SH
   const double idet = fast_rcp(d11 * d22 - d12 * d21);
   y1 = (d22 * ra - d12 * rb) * idet;
   y2 = (d11 * rb - d21 * ra) * idet;
@@ -220,8 +219,23 @@ __device__ __forceinline__ Cell shfl_cell(const Cell& c, int src) {
   return o;
 }
 
-template <int MODE, bool CMP, bool CURV, bool IRR>
-__global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ LongParams q) {
+// The tile kernel of a Newton trip.  For every (member, tile) one warp:
+//   U  finishes trip k-1 - re-assembles the tile on the iterate x_{k-1} (recomputing is cheaper than storing 9 doubles
+//      per node), solves the tile interior with its two end nodes known from the chain kernel (PCR), x_k = x_{k-1} +
+//      delta; when the chain kernel accepted the level, x_{k-1} is written out as that level and its level constants
+//      replace the old ones;
+//   C  starts trip k - node pass and cell pass on x_k, per-lane Schur condensation, warp tree-merge -> ONE condensed
+//      cell for the tile and the tile's part of ||R||^2, for the chain kernel.
+// U and C used to be two launches (K3 of one trip, K1 of the next), each reading the iterate and the level constants
+// from HBM; fused, a trip reads them once and writes the iterate once: 64 B per node-iteration (16 read + 32 read +
+// 16 written) instead of 112, plus the constants rewritten when a level is accepted.
+// FIRST (trip 0): no U part; the level constants of the initial state are formed instead.
+#ifndef PR_LONG_CTAS
+#define PR_LONG_CTAS 4      // resident CTAs per SM the tile kernel is compiled for (registers = 65536 / (128 * this)): 4 x 128
+                            // registers with 72 bytes of spills ran 6 % faster than 3 x 168 without (config 5)
+#endif
+template <bool FIRST, bool CMP, bool CURV, bool IRR>
+__global__ void __launch_bounds__(128, (IRR || CURV || CMP) ? 2 : PR_LONG_CTAS) pr_long_fused(const __grid_constant__ LongParams q) {
   const DevParams& p = q.p;
   const int lane = threadIdx.x & 31;
   // grid = (ceil(M / 4), tiles) - members on x, which has no 65 535 limit: the four warps of a CTA work on the SAME
@@ -240,8 +254,8 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
   double* pc = q.pc + (size_t)m * 4 * N;
   // Every global load of this warp's state is issued here, before anything depends on one of them, so the warp pays
   // the DRAM latency once instead of once per dependent group of loads.
-  const int act = q.active[m];
-  const int conv = (MODE == LONG_UPDATE) ? q.conv[m] : 0;
+  const int act = q.active[m];             // 1 running, 3 last level accepted (its output is still to be written)
+  const int conv = FIRST ? 0 : q.conv[m];
   double h[kLongM + 1], qq[kLongM + 1], pcv[kLongM][4];
 #pragma unroll
   for (int j = 0; j <= kLongM; ++j) {
@@ -253,11 +267,16 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
   for (int j = 0; j < kLongM; ++j) {
     const int c = c0 + j < N - 1 ? c0 + j : N - 2;
 #pragma unroll
-    for (int f = 0; f < 4; ++f) pcv[j][f] = (MODE != LONG_INIT) ? pc[(size_t)f * N + c] : 0.0;
+    for (int f = 0; f < 4; ++f) pcv[j][f] = FIRST ? 0.0 : pc[(size_t)f * N + c];
   }
-  if (!act) return;
+  double yL1 = 0.0, yL2 = 0.0, yR1 = 0.0, yR2 = 0.0;      // updates of the tile's first node / of the next tile's
+  if (!FIRST) {
+    const double* dc = q.dchain + ((size_t)m * (q.T + 1) + t) * 2;
+    yL1 = dc[0]; yL2 = dc[1]; yR1 = dc[2]; yR2 = dc[3];
+  }
+  if (act != 1 && act != 3) return;
   const Rough rg = load_rough<4>(p.geo, m);
-  // elimination records of the UPDATE pass live in shared memory ([record][field][lane] per warp)
+  // elimination records of the U part live in shared memory ([record][field][lane] per warp)
   extern __shared__ double long_smem[];
   double* elw = long_smem + (size_t)(threadIdx.x >> 5) * ((kLongM - 1) * 9 * 32);
 #define LEL(j, c) elw[((j)*9 + (c)) * 32 + lane]
@@ -267,123 +286,129 @@ __global__ void __launch_bounds__(128) pr_long_tile(const __grid_constant__ Long
     if (IRR && q.geo[F_KIND * N + nd] == (double)PR_XS_IRREGULAR) node_eval_irregular<DevParams, CURV>(p.geo, nd, hh, qv, rg, p, out, nullptr);
     else node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, nd, hh, qv, rg, p, out);
   };
-  eval_node(c0 < N ? c0 : N - 1, h[0], qq[0], nv[0]);
-  double ss = 0.0;
-  Cell S;
+  // One pass over the lane's cells on the state (h, qq): residuals + Jacobian per cell and the Schur condensation into S.
+  //   RECORDS: keep the elimination records (U part);  REFRESH: this state is (becomes) the stored level - its level
+  //   constants replace the old ones, in memory and in pcv, once the old ones have been used for this cell
+  auto pass = [&](const bool records, const bool refresh, Cell& S, double& ss) {
+    eval_node(c0 < N ? c0 : N - 1, h[0], qq[0], nv[0]);
 #pragma unroll
-  for (int j = 0; j < kLongM; ++j) {
-    const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
-    eval_node(nd, h[j + 1], qq[j + 1], nv[(j + 1) & 1]);
-    if (j < nc) {
-      const int c = c0 + j;
-      Cell e;
-      ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, pcv[j][0], pcv[j][1], pcv[j][2], pcv[j][3], e);
-      if (MODE == LONG_INIT || (MODE == LONG_UPDATE && conv)) {
-        // this state is (becomes) the stored level: its level constants replace the old ones, which this lane
-        // has just consumed and nobody else reads
-        double nC, nM, nA, nS;
-        level_constants(nv[j & 1], nv[(j + 1) & 1], p, nC, nM, nA, nS);
-        pc[c] = nC; pc[N + c] = nM; pc[2 * N + c] = nA; pc[3 * N + c] = nS;
-      }
-      if (j == 0) S = e;
-      else {
-        Elim el;
-        merge_cells(S, e, el);
-        if (MODE == LONG_UPDATE) {
-          LEL(j - 1, 0) = el.i11; LEL(j - 1, 1) = el.i12; LEL(j - 1, 2) = el.i21; LEL(j - 1, 3) = el.i22;
-          LEL(j - 1, 4) = el.m1;  LEL(j - 1, 5) = el.m2;  LEL(j - 1, 6) = el.rm;
-          LEL(j - 1, 7) = el.c3;  LEL(j - 1, 8) = el.rc;
+    for (int j = 0; j < kLongM; ++j) {
+      const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
+      eval_node(nd, h[j + 1], qq[j + 1], nv[(j + 1) & 1]);
+      if (j < nc) {
+        const int c = c0 + j;
+        Cell e;
+        ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, pcv[j][0], pcv[j][1], pcv[j][2], pcv[j][3], e);
+        if (refresh) {
+          level_constants(nv[j & 1], nv[(j + 1) & 1], p, pcv[j][0], pcv[j][1], pcv[j][2], pcv[j][3]);
+          pc[c] = pcv[j][0]; pc[N + c] = pcv[j][1]; pc[2 * N + c] = pcv[j][2]; pc[3 * N + c] = pcv[j][3];
+        }
+        if (j == 0) S = e;
+        else {
+          Elim el;
+          merge_cells(S, e, el);
+          if (records) {
+            LEL(j - 1, 0) = el.i11; LEL(j - 1, 1) = el.i12; LEL(j - 1, 2) = el.i21; LEL(j - 1, 3) = el.i22;
+            LEL(j - 1, 4) = el.m1;  LEL(j - 1, 5) = el.m2;  LEL(j - 1, 6) = el.rm;
+            LEL(j - 1, 7) = el.c3;  LEL(j - 1, 8) = el.rc;
+          }
         }
       }
     }
-  }
-
-  if (MODE == LONG_INIT) return;   // level 0: only the level constants of the initial state were needed
-
-  if (MODE == LONG_CONDENSE) {
-    // warp tree-merge of the per-lane cells -> one cell for the tile
-    int cnt = nc;
+  };
+  Cell S;
+  double ss = 0.0;
+  if (FIRST) {
+    // level 0: the level constants of the initial state (the cells assembled on the way are not used)
+    pass(false, true, S, ss);
+  } else {
+    // ---------------- U: tile interior of trip k-1 with both end nodes known ----------------
+    pass(true, conv != 0, S, ss);
+    const int lanes = (N - 1 - t * kTileCells + kLongM - 1) / kLongM;  // lanes of this tile that own cells
+    const int Lt = lanes < 32 ? lanes : 32;
+    double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
+    {
+      const Cell Pv = shfl_cell(S, (lane - 1) & 31);
+      if (lane == 0 || lane >= Lt) { l1 = l2 = 0.0; d11 = 1.0; d12 = 0.0; ra = (lane == 0) ? yL1 : 0.0; }
+      else { l1 = Pv.m1; l2 = Pv.m2; d11 = Pv.m3; d12 = Pv.m4; ra = Pv.rm; }
+      if (lane == 0 || lane >= Lt) { d21 = 0.0; d22 = 1.0; u1 = u2 = 0.0; rb = (lane == 0) ? yL2 : 0.0; }
+      else if (lane == Lt - 1) { d21 = S.c1; d22 = S.c2; u1 = u2 = 0.0; rb = S.rc - S.c3 * yR1 - S.c4 * yR2; }
+      else { d21 = S.c1; d22 = S.c2; u1 = S.c3; u2 = S.c4; rb = S.rc; }
+    }
+    double dh0, dq0;
+    pcr32(l1, l2, d11, d12, d21, d22, u1, u2, ra, rb, Lt, lane, dh0, dq0);
+    double dhR = __shfl_sync(kFull, dh0, (lane + 1) & 31), dqR = __shfl_sync(kFull, dq0, (lane + 1) & 31);
+    if (lane == Lt - 1 || lane == 31) { dhR = yR1; dqR = yR2; }
+    double dh[kLongM + 1], dq[kLongM + 1];
+    dh[0] = dh0; dq[0] = dq0;
+    {
+      double rh = dhR, rq = dqR;
 #pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-      const Cell R = shfl_cell(S, (lane + s) & 31);
-      const int rcnt = __shfl_sync(kFull, cnt, (lane + s) & 31);
-      if ((lane & (2 * s - 1)) == 0 && lane + s < 32 && rcnt > 0) {
-        if (cnt > 0) { Elim dummy; merge_cells(S, R, dummy); }
-        else S = R;
-        cnt += rcnt;
+      for (int j = kLongM - 1; j >= 1; --j) {
+        if (j < nc) {
+          const double t1 = LEL(j - 1, 6) - LEL(j - 1, 4) * dh0 - LEL(j - 1, 5) * dq0;
+          const double t2 = LEL(j - 1, 8) - LEL(j - 1, 7) * rh - p.th_dx * rq;
+          dh[j] = LEL(j - 1, 0) * t1 + LEL(j - 1, 1) * t2;
+          dq[j] = LEL(j - 1, 2) * t1 + LEL(j - 1, 3) * t2;
+          rh = dh[j]; rq = dq[j];
+        } else { dh[j] = 0.0; dq[j] = 0.0; }
       }
     }
+    // the node right of the lane's cell nc-1 (slot nc) is the next lane's / next tile's first node
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(kFull, ss, s);
-    if (lane == 0) {
-      double* tc = q.tcell + ((size_t)m * q.T + t) * kTileRec;
-      tc[0] = S.c1; tc[1] = S.c2; tc[2] = S.c3; tc[3] = S.c4; tc[4] = S.rc;
-      tc[5] = S.m1; tc[6] = S.m2; tc[7] = S.m3; tc[8] = S.m4; tc[9] = S.rm;
-      tc[10] = ss;      // summed in tile order by the chain kernel: the norm does not depend on the launch's timing
+    for (int j = 1; j <= kLongM; ++j)
+      if (j == nc) { dh[j] = dhR; dq[j] = dqR; }
+      else if (j > nc) { dh[j] = 0.0; dq[j] = 0.0; }
+    // nodes written by this lane: its own cells' left nodes; the very last node N-1 is written by the lane whose
+    // last cell ends there
+    const int lvl = q.out_level[m];
+    const size_t orow = ((size_t)m * p.L + lvl) * (size_t)N;
+    const bool last_lane = nc > 0 && c0 + nc == N - 1;       // this lane's last cell ends at the downstream boundary node
+#pragma unroll
+    for (int j = 0; j <= kLongM; ++j) {
+      if (j < nc || (j == nc && last_lane)) {
+        const int nd = c0 + j;
+        if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[j]; if (p.out_q) p.out_q[orow + nd] = qq[j]; }
+      }
     }
-    return;
-  }
-
-  // ---------------- LONG_UPDATE: tile interior with both end nodes known ----------------
-  const double* dc = q.dchain + ((size_t)m * (q.T + 1) + t) * 2;
-  const double yL1 = dc[0], yL2 = dc[1], yR1 = dc[2], yR2 = dc[3];   // first node of this tile / of the next
-  const int lanes = (N - 1 - t * kTileCells + kLongM - 1) / kLongM;  // lanes of this tile that own cells
-  const int Lt = lanes < 32 ? lanes : 32;
-  double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
-  {
-    const Cell Pv = shfl_cell(S, (lane - 1) & 31);
-    if (lane == 0 || lane >= Lt) { l1 = l2 = 0.0; d11 = 1.0; d12 = 0.0; ra = (lane == 0) ? yL1 : 0.0; }
-    else { l1 = Pv.m1; l2 = Pv.m2; d11 = Pv.m3; d12 = Pv.m4; ra = Pv.rm; }
-    if (lane == 0 || lane >= Lt) { d21 = 0.0; d22 = 1.0; u1 = u2 = 0.0; rb = (lane == 0) ? yL2 : 0.0; }
-    else if (lane == Lt - 1) { d21 = S.c1; d22 = S.c2; u1 = u2 = 0.0; rb = S.rc - S.c3 * yR1 - S.c4 * yR2; }
-    else { d21 = S.c1; d22 = S.c2; u1 = S.c3; u2 = S.c4; rb = S.rc; }
-  }
-  double dh0, dq0;
-  pcr32(l1, l2, d11, d12, d21, d22, u1, u2, ra, rb, Lt, lane, dh0, dq0);
-  double dhR = __shfl_sync(kFull, dh0, (lane + 1) & 31), dqR = __shfl_sync(kFull, dq0, (lane + 1) & 31);
-  if (lane == Lt - 1 || lane == 31) { dhR = yR1; dqR = yR2; }
-  double dh[kLongM], dq[kLongM];
-  dh[0] = dh0; dq[0] = dq0;
-  {
-    double rh = dhR, rq = dqR;
-#pragma unroll
-    for (int j = kLongM - 1; j >= 1; --j) {
-      if (j < nc) {
-        const double t1 = LEL(j - 1, 6) - LEL(j - 1, 4) * dh0 - LEL(j - 1, 5) * dq0;
-        const double t2 = LEL(j - 1, 8) - LEL(j - 1, 7) * rh - p.th_dx * rq;
-        dh[j] = LEL(j - 1, 0) * t1 + LEL(j - 1, 1) * t2;
-        dq[j] = LEL(j - 1, 2) * t1 + LEL(j - 1, 3) * t2;
-        rh = dh[j]; rq = dq[j];
-      } else { dh[j] = 0.0; dq[j] = 0.0; }
+    if (conv && p.out_mode == PR_OUT_UPSTREAM && t == 0 && lane == 0) {
+      if (p.out_h) p.out_h[(size_t)m * p.L + lvl] = h[0];
+      if (p.out_q) p.out_q[(size_t)m * p.L + lvl] = qq[0];
     }
-  }
-  // nodes written by this lane: its own cells' left nodes; the very last node N-1 is written by the lane whose
-  // last cell ends there
-  const int lvl = q.out_level[m];
-  const size_t orow = ((size_t)m * p.L + lvl) * (size_t)N;
+    if (act == 3) return;            // the member's last level: nothing left to solve
 #pragma unroll
-  for (int j = 0; j < kLongM; ++j) {
-    if (j < nc) {
-      const int nd = c0 + j;
-      if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = h[j]; if (p.out_q) p.out_q[orow + nd] = qq[j]; }
-      xh_out[nd] = h[j] + dh[j];
-      xq_out[nd] = qq[j] + dq[j];
+    for (int j = 0; j <= kLongM; ++j) { h[j] += dh[j]; qq[j] += dq[j]; }       // x_k
+#pragma unroll
+    for (int j = 0; j <= kLongM; ++j) {
+      if (j < nc || (j == nc && last_lane)) {
+        xh_out[c0 + j] = h[j];
+        xq_out[c0 + j] = qq[j];
+      }
     }
-  }
-  if (nc > 0 && c0 + nc == N - 1) {      // this lane's last cell ends at the downstream boundary node
-    const int nd = N - 1;
-    double hl = h[1], ql = qq[1];          // h[nc] without dynamic indexing of a register array
-#pragma unroll
-    for (int j = 2; j <= kLongM; ++j)
-      if (j == nc) { hl = h[j]; ql = qq[j]; }
-    if (conv && p.out_mode == PR_OUT_FULL) { if (p.out_h) p.out_h[orow + nd] = hl; if (p.out_q) p.out_q[orow + nd] = ql; }
-    xh_out[nd] = hl + yR1;
-    xq_out[nd] = ql + yR2;
+    __syncwarp();
   }
 #undef LEL
-  if (conv && p.out_mode == PR_OUT_UPSTREAM && t == 0 && lane == 0) {
-    if (p.out_h) p.out_h[(size_t)m * p.L + lvl] = h[0];
-    if (p.out_q) p.out_q[(size_t)m * p.L + lvl] = qq[0];
+  // ---------------- C: condensed cell of the tile on x_k ----------------
+  ss = 0.0;
+  pass(false, false, S, ss);
+  int cnt = nc;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const Cell R = shfl_cell(S, (lane + s) & 31);
+    const int rcnt = __shfl_sync(kFull, cnt, (lane + s) & 31);
+    if ((lane & (2 * s - 1)) == 0 && lane + s < 32 && rcnt > 0) {
+      if (cnt > 0) { Elim dummy; merge_cells(S, R, dummy); }
+      else S = R;
+      cnt += rcnt;
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(kFull, ss, s);
+  if (lane == 0) {
+    double* tc = q.tcell + ((size_t)m * q.T + t) * kTileRec;
+    tc[0] = S.c1; tc[1] = S.c2; tc[2] = S.c3; tc[3] = S.c4; tc[4] = S.rc;
+    tc[5] = S.m1; tc[6] = S.m2; tc[7] = S.m3; tc[8] = S.m4; tc[9] = S.rm;
+    tc[10] = ss;      // summed in tile order by the chain kernel: the norm does not depend on the launch's timing
   }
 }
 
@@ -394,7 +419,7 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   extern __shared__ double rec[];
   const DevParams& p = q.p;
   const int m = blockIdx.x, lane = threadIdx.x;
-  if (!q.active[m]) return;
+  if (q.active[m] != 1) return;
   const int N = p.N, L = p.L, T = q.T, Kc = q.Kc;
   const int level = q.level[m];
   const int it = q.it[m] + 1;
@@ -515,12 +540,14 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   }
 }
 
-// After K3: retire members whose last level was just accepted.
+// After the chain kernel: retire members whose last level was accepted (one trip later: the tile pass in between writes that level out).
 static __global__ void pr_long_retire(const __grid_constant__ LongParams q) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= q.p.M) return;
-  if (q.active[m] == 1 && q.level[m] >= q.p.L) { q.active[m] = 0; atomicAdd(q.n_done, 1); }
-  if (q.active[m] == 2) q.active[m] = 0;
+  const int a = q.active[m];
+  if (a == 1 && q.level[m] >= q.p.L) q.active[m] = 3;                 // last level accepted: the next tile pass writes it out
+  else if (a == 3) { q.active[m] = 0; atomicAdd(q.n_done, 1); }       // ... which has happened
+  else if (a == 2) q.active[m] = 0;                                   // failed in this trip (counted by the chain kernel)
 }
 
 // End of a trip in a graph-driven run: one more trip while members are left (and the bound on the trips holds).
@@ -594,7 +621,7 @@ static __global__ void pr_long_nanfill(const __grid_constant__ LongParams q) {
   }
 }
 
-// The run: set-up kernels, then Newton trips (K1, K2, K3, retire) until every member has finished.  The number of
+// The run: set-up kernels, then Newton trips (chain, retire, loop control, fused tile kernel) until every member has finished.  The number of
 // trips is data dependent, so the trip loop is a CUDA-graph WHILE node whose condition the last kernel of a trip sets
 // on the device: the host enqueues one graph launch and returns - no per-trip synchronisation, no read-back.  (Two
 // trips per loop body because the iterate is double-buffered.)  PR_LONG_POLL=1, or a driver without conditional
@@ -649,18 +676,17 @@ int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>&
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
   const dim3 tile_grid((unsigned)((M + 3) / 4), (unsigned)T);
   const size_t tile_smem = sizeof(double) * 4 * (kLongM - 1) * 9 * 32;   // elimination records, 4 warps per CTA
-  pr_long_tile<LONG_INIT, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);
+  pr_long_fused<true, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);      // level constants of the initial state + first condensation
   launches.fetch_add(3);
   const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
   e = cudaFuncSetAttribute(pr_long_chain<IRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
   if (e != cudaSuccess) return bail("long-reach chain kernel");
   // one Newton trip of all members on stream cs; the iterate buffers swap roles after it
   auto enqueue_trip = [&](cudaStream_t cs, int graph_driven) {
-    pr_long_tile<LONG_CONDENSE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, cs>>>(q);
-    pr_long_chain<IRR><<<M, 32, chain_smem, cs>>>(q);
-    pr_long_tile<LONG_UPDATE, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, cs>>>(q);
+    pr_long_chain<IRR><<<M, 32, chain_smem, cs>>>(q);                               // solve the chain of tile cells, decide
     pr_long_retire<<<(M + 127) / 128, 128, 0, cs>>>(q);
     pr_long_loop_control<<<1, 1, 0, cs>>>(q, graph_driven);
+    pr_long_fused<false, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, cs>>>(q);     // finish this trip, start the next
     std::swap(q.xh, q.xh_out);
     std::swap(q.xq, q.xq_out);
   };
@@ -709,7 +735,7 @@ int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>&
     for (long long chunk = 0; e == cudaSuccess && chunk * 2 < q.max_trips; ++chunk) {
       enqueue_trip(s, 0);
       enqueue_trip(s, 0);
-      launches.fetch_add(10);
+      launches.fetch_add(8);
       const int k = (int)(chunk & 1);
       e = cudaMemcpyAsync(ws.host_flags + 2 * k, q.n_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
       if (e == cudaSuccess) e = cudaEventRecord(ev[k], s);
@@ -736,6 +762,8 @@ int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>&
 
 #endif  // PR_LONG_DECLARE_ONLY
 
+#ifdef PR_LONG_DECLARE_ONLY   // the dispatcher lives in the library's main unit only: in a pr_long_v*.cu unit it would
+                              // instantiate all five variants next to the one that unit is for
 inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, bool has_irregular, cudaStream_t s,
                           std::atomic<long long>& launches, std::string& err) {
   // IrregularSection nodes: one more set of kernels (compound arithmetic for the trapezoid nodes of a mixed reach).
@@ -749,5 +777,7 @@ inline int long_reach_run(const DevParams& p, bool has_curv, bool has_compound, 
   return has_compound ? long_reach_run_t<true, false, false>(p, s, launches, err)
                       : long_reach_run_t<false, false, false>(p, s, launches, err);
 }
+
+#endif
 
 }  // namespace pr
