@@ -2,4 +2,4 @@
 // reaches of up to 61 nodes.
 #include "pr_ensemble_kernel.cuh"
 
-PR_DEFINE_ENSEMBLE_FAMILY(16, 4, 16)
+PR_DEFINE_ENSEMBLE_FAMILY(16, 4, 16, 0)

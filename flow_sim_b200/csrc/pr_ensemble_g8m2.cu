@@ -2,4 +2,4 @@
 // reaches of up to 15 nodes.
 #include "pr_ensemble_kernel.cuh"
 
-PR_DEFINE_ENSEMBLE_FAMILY(8, 2, 16)
+PR_DEFINE_ENSEMBLE_FAMILY(8, 2, 16, 0)

@@ -611,7 +611,9 @@ inline unsigned persistent_grid(DevParams& q, int members_per_warp, int warps_pe
 template <int G, int M, int W>
 int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
 
-#define PR_DEFINE_ENSEMBLE_FAMILY(G_, M_, W_)                                                                \
+// STATIC_RM_ = 1: one build per roughness-override mode (the headline family: the mode's selects and loads are
+// compiled away); 0: one build that decides at run time (RM = 4) - a third of the instantiations, a few per cent slower.
+#define PR_DEFINE_ENSEMBLE_FAMILY(G_, M_, W_, STATIC_RM_)                                                    \
   namespace pr {                                                                                             \
   template <bool CURV, int RM, bool EXACT, bool GST>                                                         \
   static int launch_y_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                      \
@@ -642,11 +644,15 @@ int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
   }                                                                                                          \
   template <bool CURV>                                                                                       \
   static int launch_rm_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                     \
-    switch (rough_mode(p.geo)) {                                                                             \
-      case 0: return launch_one_##G_##_##M_<CURV, 0>(p, s);                                                  \
-      case 1: return launch_one_##G_##_##M_<CURV, 1>(p, s);                                                  \
-      case 2: return launch_one_##G_##_##M_<CURV, 2>(p, s);                                                  \
-      default: return launch_one_##G_##_##M_<CURV, 3>(p, s);                                                 \
+    if constexpr (!(STATIC_RM_)) {                                                                           \
+      return launch_one_##G_##_##M_<CURV, 4>(p, s);                                                          \
+    } else {                                                                                                 \
+      switch (rough_mode(p.geo)) {                                                                           \
+        case 0: return launch_one_##G_##_##M_<CURV, 0>(p, s);                                                \
+        case 1: return launch_one_##G_##_##M_<CURV, 1>(p, s);                                                \
+        case 2: return launch_one_##G_##_##M_<CURV, 2>(p, s);                                                \
+        default: return launch_one_##G_##_##M_<CURV, 3>(p, s);                                               \
+      }                                                                                                      \
     }                                                                                                        \
   }                                                                                                          \
   template <>                                                                                                \

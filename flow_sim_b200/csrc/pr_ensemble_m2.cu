@@ -1,4 +1,4 @@
 // pr_ensemble_m2.cu - instantiations of the fused ensemble kernel with 2 node(s) per lane (12 warps per CTA).
 #include "pr_ensemble_kernel.cuh"
 
-PR_DEFINE_ENSEMBLE_FAMILY(32, 2, 16)
+PR_DEFINE_ENSEMBLE_FAMILY(32, 2, 16, 0)

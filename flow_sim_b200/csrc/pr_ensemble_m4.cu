@@ -4,7 +4,7 @@
 #ifndef PR_W4
 #define PR_W4 16
 #endif
-PR_DEFINE_ENSEMBLE_FAMILY(32, 4, PR_W4)
+PR_DEFINE_ENSEMBLE_FAMILY(32, 4, PR_W4, 1)
 
 #ifdef PR_VARIANT_SHIM   // tuning builds (tools/ab_build.sh): this family alone, loaded through PR_M4_VARIANT
 extern "C" int pr_variant_launch_m4(const pr::DevParams* p, int curv, cudaStream_t s) {
