@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(128) pr_derived_kernel(const __grid_constant__
     double A, T;
     if (irregular) {             // IrregularSection.properties (cross_section.py:247-327): area and geometric top width
       double P;
-      irr_properties(p.raw.irr_x + poly_off, p.raw.irr_z + poly_off, 0, poly_n - 1, hw, A, P, T);
+      IrrTab tab;
+      if (irr_tab_get(p.raw, nd, tab)) irr_tab_eval(tab, irr_tab_interval(tab, hw), hw, 0, A, P, &T);
+      else irr_properties(p.raw.irr_x + poly_off, p.raw.irr_z + poly_off, 0, poly_n - 1, hw, A, P, T);
     } else if (d <= hb) {        // rectangle / simple trapezoid / compound in bank (h_bank staged as 1e300 otherwise)
       T = b + m2 * d;
       A = (b + T) / 2.0 * d;
@@ -213,7 +215,10 @@ __device__ __forceinline__ double normal_flow_residual(const NormalDepthParams& 
     const double nm = rg.om ? rg.nm : p.raw.nm[nd];
     const double nl = rg.ofp ? rg.nfp : p.raw.nl[nd], nr = rg.ofp ? rg.nfp : p.raw.nr[nd];
     IrrSec sec;
-    irr_section(p.raw.irr_x + off, p.raw.irr_z + off, n, hw, p.raw.irr_left[nd], p.raw.irr_right[nd], nl, nm, nr, sec);
+    IrrTab tab;
+    int runs;
+    if (irr_tab_get(p.raw, nd, tab)) irr_section_tab(tab, hw, nl, nm, nr, sec, runs);
+    else irr_section(p.raw.irr_x + off, p.raw.irr_z + off, n, hw, p.raw.irr_left[nd], p.raw.irr_right[nd], nl, nm, nr, sec);
     return Qt - sec.K * sqrt(S0);
   }
   NodeVals nv;

@@ -60,6 +60,13 @@ struct DevGeom {
   // IrregularSection nodes (pr_irregular.cuh): CSR polylines and composite-roughness limits, or nullptr
   const int* irr_offset;
   const double *irr_x, *irr_z, *irr_left, *irr_right;
+  // stage tables of the IrregularSection nodes, built on the device once per call (pr_irregular.cuh, pr_irr_build_tables):
+  // breakpoints = the distinct vertex elevations of a section; per interval the polynomials of area, wetted perimeter
+  // and top width of the whole section and of its three roughness sub-sections.  Stored at the node's irr_offset.
+  const int* irr_tab_n;        // [N] number of breakpoints (0: no table - the node pass scans the polyline)
+  const double* irr_tab_z;     // [points] breakpoints, ascending
+  const double* irr_tab_c;     // [points][kIrrTabCols] coefficients of the interval above breakpoint k
+  const int* irr_tab_runs;     // [points] wetted sub-channels (runs of >= 2 submerged points) in that interval
 };
 
 struct DevParams {

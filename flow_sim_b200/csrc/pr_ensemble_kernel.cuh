@@ -661,28 +661,28 @@ int launch_ensemble_family(const DevParams& p, bool curv, cudaStream_t s);
   }                                                                                                          \
   }
 
-// IrregularSection reaches of up to 249 nodes: one build per nodes-per-lane count and curvature setting (run-time
-// roughness mode, every boundary type, 32 lanes per member).
-template <int M>
+// IrregularSection reaches of up to 249 nodes: one build per (lanes per member, nodes per lane) and curvature setting
+// (run-time roughness mode, every boundary type); 8 and 16 lanes per member pack 4 / 2 short reaches into a warp.
+template <int G, int M>
 int launch_ensemble_irregular(const DevParams& p, bool curv, cudaStream_t s);
 
-#define PR_DEFINE_ENSEMBLE_IRREGULAR(M_, W_)                                                                 \
+#define PR_DEFINE_ENSEMBLE_IRREGULAR(G_, M_, W_)                                                             \
   namespace pr {                                                                                             \
   template <bool CURV>                                                                                       \
-  static int launch_irr_##M_(const DevParams& p, cudaStream_t s) {                                           \
-    constexpr size_t smem = ensemble_smem_bytes<32, M_, W_>();                                               \
+  static int launch_irr_##G_##_##M_(const DevParams& p, cudaStream_t s) {                                    \
+    constexpr size_t smem = ensemble_smem_bytes<G_, M_, W_>();                                               \
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");                                      \
-    auto kern = pr_ensemble_kernel<32, M_, W_, CURV, 4, false, true, true>;                                  \
+    auto kern = pr_ensemble_kernel<G_, M_, W_, CURV, 4, false, true, true>;                                  \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                     \
     DevParams q = p;                                                                                         \
-    const unsigned grid = persistent_grid(q, 1, W_);                                                         \
+    const unsigned grid = persistent_grid(q, 32 / G_, W_);                                                   \
     kern<<<grid, W_ * 32, smem, s>>>(q);                                                                     \
     return (int)cudaGetLastError();                                                                          \
   }                                                                                                          \
   template <>                                                                                                \
-  int launch_ensemble_irregular<M_>(const DevParams& p, bool curv, cudaStream_t s) {                         \
-    return curv ? launch_irr_##M_<true>(p, s) : launch_irr_##M_<false>(p, s);                                \
+  int launch_ensemble_irregular<G_, M_>(const DevParams& p, bool curv, cudaStream_t s) {                     \
+    return curv ? launch_irr_##G_##_##M_<true>(p, s) : launch_irr_##G_##_##M_<false>(p, s);                  \
   }                                                                                                          \
   }
 

@@ -162,6 +162,162 @@ __device__ inline bool irr_split_K(const double* __restrict__ x, const double* _
   return ok;
 }
 
+// ---- stage tables ----------------------------------------------------------------------------------------------
+// Area, wetted perimeter and top width of a polyline are piecewise polynomials of the stage: between two consecutive
+// vertex elevations every segment is either submerged (area linear in hw), cut by the water surface (area quadratic,
+// perimeter and width linear) or dry.  One table per node turns the six polyline scans of a node evaluation
+// (properties at hw and hw -/+ 1e-6, three roughness sub-sections) into one interval search and a few Horner steps.
+// The values agree with the scans to rounding (~1e-16 relative); the reference's finite-difference derivatives are
+// formed from them exactly as from the scanned values.
+constexpr int kIrrTabCols = 22;     // whole section: a0 a1 a2 p0 p1 t0 t1;  left, main, right sub-section: a0 a1 a2 p0 p1
+constexpr int kIrrTabMaxPts = 128;  // larger sections get no table (tab_n = 0) and keep the scanning node pass
+
+// coefficients of the points [lo, hi] (a section of its own, as subsection_props builds it) for zk < hw <= next breakpoint
+__device__ inline void irr_tab_accumulate(const double* x, const double* z, int lo, int hi, double zk, double* c, bool want_t) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, p0 = 0.0, p1 = 0.0, t0 = 0.0, t1 = 0.0;
+  for (int j = lo; j < hi; ++j) {
+    const double za = z[j], zb = z[j + 1], dx = x[j + 1] - x[j], dz = zb - za;
+    const double zl = za < zb ? za : zb, zh = za < zb ? zb : za;
+    if (zh <= zk) {                         // both ends submerged: 0.5 (d_a + d_b) dx, the whole segment wetted
+      a0 += dx * (zk - 0.5 * (za + zb)); a1 += dx;
+      p0 += sqrt(dx * dx + dz * dz);
+      t0 += dx;
+    } else if (zl <= zk) {                  // cut by the water surface at the fraction (hw - zl) / (zh - zl)
+      const double inv = 1.0 / (zh - zl), cc = zk - zl, len = sqrt(dx * dx + dz * dz);
+      const double gq = 0.5 * dx * inv;
+      a0 += gq * cc * cc; a1 += 2.0 * gq * cc; a2 += gq;
+      p0 += len * cc * inv; p1 += len * inv;
+      t0 += dx * cc * inv; t1 += dx * inv;
+    }
+  }
+  c[0] = a0; c[1] = a1; c[2] = a2; c[3] = p0; c[4] = p1;
+  if (want_t) { c[5] = t0; c[6] = t1; }
+}
+
+static __global__ void pr_irr_build_tables(DevGeom g, int N, int* tab_n, double* tab_z, double* tab_c, int* tab_runs) {
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= N) return;
+  tab_n[node] = 0;
+  if (g.kind[node] != PR_XS_IRREGULAR) return;
+  const int off = g.irr_offset[node], n = g.irr_offset[node + 1] - off;
+  if (n < 2 || n > kIrrTabMaxPts) return;
+  const double* x = g.irr_x + off;
+  const double* z = g.irr_z + off;
+  double zz[kIrrTabMaxPts];
+  int nb = 0;
+  for (int i = 0; i < n; ++i) {             // insertion sort of the distinct elevations
+    const double v = z[i];
+    int k = nb;
+    while (k > 0 && zz[k - 1] > v) --k;
+    if (k > 0 && zz[k - 1] == v) continue;
+    for (int m = nb; m > k; --m) zz[m] = zz[m - 1];
+    zz[k] = v; ++nb;
+  }
+  // the three roughness sub-sections: points with x_min <= x <= x_max (get_equivalent_n, cross_section.py:448-470)
+  const double lim_l = g.irr_left[node], lim_r = g.irr_right[node];
+  int lo[3], hi[3];
+  const double xmin[3] = {x[0], lim_l, lim_r}, xmax[3] = {lim_l, lim_r, x[n - 1]};
+  for (int s = 0; s < 3; ++s) {
+    lo[s] = 0; hi[s] = n - 1;
+    while (lo[s] < n && !(x[lo[s]] >= xmin[s])) ++lo[s];
+    while (hi[s] >= 0 && !(x[hi[s]] <= xmax[s])) --hi[s];
+  }
+  for (int k = 0; k < nb; ++k) {
+    const double zk = zz[k];
+    double* c = tab_c + (size_t)(off + k) * kIrrTabCols;
+    tab_z[off + k] = zk;
+    irr_tab_accumulate(x, z, 0, n - 1, zk, c, true);
+    for (int s = 0; s < 3; ++s) {
+      double* cs = c + 7 + 5 * s;
+      if (hi[s] - lo[s] + 1 < 2) { cs[0] = cs[1] = cs[2] = cs[3] = cs[4] = 0.0; }
+      else irr_tab_accumulate(x, z, lo[s], hi[s], zk, cs, false);
+    }
+    int runs = 0;                           // get_subchannels: runs of >= 2 points with z < hw, i.e. z <= zk here
+    for (int i = 0; i < n;) {
+      if (!(z[i] <= zk)) { ++i; continue; }
+      const int st = i;
+      while (i < n && z[i] <= zk) ++i;
+      runs += (i - st >= 2) ? 1 : 0;
+    }
+    tab_runs[off + k] = runs;
+  }
+  tab_n[node] = nb;
+}
+
+struct IrrTab {
+  const double *z, *c;
+  const int* runs;
+  int nb;
+};
+
+__device__ __forceinline__ bool irr_tab_get(const DevGeom& g, int node, IrrTab& t) {
+  t.nb = g.irr_tab_n ? g.irr_tab_n[node] : 0;
+  if (t.nb == 0) return false;
+  const int off = g.irr_offset[node];
+  t.z = g.irr_tab_z + off; t.c = g.irr_tab_c + (size_t)off * kIrrTabCols; t.runs = g.irr_tab_runs + off;
+  return true;
+}
+
+// interval of a stage: the largest k with z_k < hw (a point AT the water level is dry, as in properties), -1 = dry section
+__device__ __forceinline__ int irr_tab_interval(const IrrTab& t, double hw) {
+  int lo = 0, hi = t.nb;                    // first k with z_k >= hw
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t.z[mid] < hw) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+// sec: 0 whole section, 1 / 2 / 3 left / main / right roughness sub-section
+__device__ __forceinline__ void irr_tab_eval(const IrrTab& t, int k, double hw, int sec, double& A, double& P, double* T) {
+  if (k < 0) { A = 0.0; P = 0.0; if (T) *T = 0.0; return; }
+  const double u = hw - t.z[k];
+  const double* c = t.c + (size_t)k * kIrrTabCols + (sec == 0 ? 0 : 7 + 5 * (sec - 1));
+  A = c[0] + u * (c[1] + u * c[2]);
+  P = c[3] + u * c[4];
+  if (T) *T = c[5] + u * c[6];
+}
+
+__device__ __forceinline__ double irr_pow23(double v) { const double c = cbrt(v); return c * c; }     // v^(2/3), v >= 0
+
+// irr_section from the node's stage table
+__device__ inline void irr_section_tab(const IrrTab& t, double hw, double nl, double nm, double nr, IrrSec& s, int& runs) {
+  const double dh = 1e-6;
+  const int k = irr_tab_interval(t, hw);
+  const int k1 = (k >= 0 && hw - dh > t.z[k]) ? k : irr_tab_interval(t, hw - dh);
+  const int k2 = (k >= 0 && (k + 1 >= t.nb || !(hw + dh > t.z[k + 1]))) ? k : irr_tab_interval(t, hw + dh);
+  double P1, P2;
+  irr_tab_eval(t, k, hw, 0, s.A, s.P, &s.T);
+  irr_tab_eval(t, k1, hw - dh, 0, s.A1, P1, nullptr);
+  irr_tab_eval(t, k2, hw + dh, 0, s.A2, P2, nullptr);
+  runs = k >= 0 ? t.runs[k] : 0;
+  s.R = s.P > 0.0 ? s.A / s.P : 0.0;
+  const double R1 = P1 > 0.0 ? s.A1 / P1 : 0.0, R2 = P2 > 0.0 ? s.A2 / P2 : 0.0;
+  const double R23 = irr_pow23(s.R);
+  s.n_eq = nm;
+  if (s.A > 0.0 && s.P > 0.0) {             // get_equivalent_n (:441-500)
+    double sum15 = 0.0;
+    const double nv[3] = {nl, nm, nr};
+#pragma unroll
+    for (int sec = 1; sec <= 3; ++sec) {
+      double As, Ps;
+      irr_tab_eval(t, k, hw, sec, As, Ps, nullptr);
+      if (As > 0.0 && Ps > 0.0) {
+        const double Ks = As * irr_pow23(As / Ps) / nv[sec - 1];
+        sum15 += Ks * sqrt(Ks);
+      }
+    }
+    const double K_total = irr_pow23(sum15);
+    if (K_total > 0.0) s.n_eq = (s.A * R23) / K_total;
+  }
+  s.K = 0.0; s.dKA = 0.0;
+  s.dRA = (s.A2 - s.A1) == 0.0 ? 0.0 : (R2 - R1) / (s.A2 - s.A1);
+  if (s.A > 0.0) {
+    s.K = s.A * R23 / s.n_eq;
+    s.dKA = (R23 + s.A * (2. / 3.) * (R23 / s.R) * s.dRA) / s.n_eq;
+  }
+}
+
 // Everything the scheme needs from an irregular node: the counterpart of node_eval.
 //   T is Solver.dA_dh = the central difference of the area (:534-539), which is what the Jacobian uses.
 //   top_width (optional): the geometric top width of `properties`, which the GVF initial profile uses (channel.py:320).
@@ -178,18 +334,23 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   const double dh = 1e-6;
   const double lim_l = g.irr_left[node], lim_r = g.irr_right[node];
   IrrSec sec;
-  irr_section(x, z, n, hw, lim_l, lim_r, nl, nm, nr, sec);
-  const double A = sec.A, T = sec.T, R = sec.R, A1 = sec.A1, A2 = sec.A2, n_eq = sec.n_eq, dRA = sec.dRA;
-  const double K = sec.K, dKA = sec.dKA;
   // wetted sub-channels (z < hw runs of >= 2 points): with more than one the friction slope and its derivatives take
   // the combined conveyance of the sub-channels; everything else stays with the whole section
   int runs = 0;
-  for (int i = 0; i < n;) {
-    if (!(z[i] < hw)) { ++i; continue; }
-    const int s = i;
-    while (i < n && z[i] < hw) ++i;
-    runs += (i - s >= 2) ? 1 : 0;
+  IrrTab tab;
+  if (irr_tab_get(g, node, tab)) {
+    irr_section_tab(tab, hw, nl, nm, nr, sec, runs);
+  } else {
+    irr_section(x, z, n, hw, lim_l, lim_r, nl, nm, nr, sec);
+    for (int i = 0; i < n;) {
+      if (!(z[i] < hw)) { ++i; continue; }
+      const int s = i;
+      while (i < n && z[i] < hw) ++i;
+      runs += (i - s >= 2) ? 1 : 0;
+    }
   }
+  const double A = sec.A, T = sec.T, R = sec.R, A1 = sec.A1, A2 = sec.A2, n_eq = sec.n_eq, dRA = sec.dRA;
+  const double K = sec.K, dKA = sec.dKA;
   double Kf = K, dKAf = dKA;
   bool refused = false;
   if (runs > 1) refused = !irr_split_K(x, z, n, hw, lim_l, lim_r, nl, nm, nr, Kf, dKAf);

@@ -79,6 +79,15 @@ struct Stage {
     err = cudaMemcpy(d, p, n * sizeof(T), cudaMemcpyHostToDevice);
     return static_cast<const T*>(d);
   }
+  // device scratch that lives as long as the call's staging (freed with it)
+  template <class T>
+  T* scratch(size_t n) {
+    void* d = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d, (n ? n : 1) * sizeof(T));
+    if (err != cudaSuccess) return nullptr;
+    allocs.push_back(d);
+    return static_cast<T*>(d);
+  }
   template <class T>
   T* out(T* p, size_t n) {
     if (!p || !host) return p;
@@ -313,6 +322,7 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
   d.member_nm = st.in(g->member_n_main, M);
   d.member_nfp = st.in(g->member_n_fp, M);
   d.irr_offset = nullptr; d.irr_x = d.irr_z = d.irr_left = d.irr_right = nullptr;
+  d.irr_tab_n = nullptr; d.irr_tab_z = d.irr_tab_c = nullptr; d.irr_tab_runs = nullptr;
   if (g->irr_offset) {                 // IrregularSection polylines (CSR)
     if (!g->irr_x || !g->irr_z || !g->irr_left || !g->irr_right) return fail(PR_ERR_ARG, "geom: irregular-section arrays are incomplete");
     int32_t total = 0;
@@ -322,6 +332,15 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
     d.irr_offset = st.in(g->irr_offset, N + 1);
     d.irr_x = st.in(g->irr_x, (size_t)total); d.irr_z = st.in(g->irr_z, (size_t)total);
     d.irr_left = st.in(g->irr_left, N); d.irr_right = st.in(g->irr_right, N);
+    // stage tables of the polyline sections (one interval search instead of six polyline scans per node evaluation)
+    int* tab_n = st.scratch<int>(N);
+    double* tab_z = st.scratch<double>((size_t)total);
+    double* tab_c = st.scratch<double>((size_t)total * pr::kIrrTabCols);
+    int* tab_runs = st.scratch<int>((size_t)total);
+    if (st.err != cudaSuccess) return fail(PR_ERR_CUDA, "staging: %s", cudaGetErrorString(st.err));
+    pr::pr_irr_build_tables<<<(unsigned)((N + 63) / 64), 64, 0, st.stream>>>(d, (int)N, tab_n, tab_z, tab_c, tab_runs);
+    g_launches.fetch_add(1);
+    d.irr_tab_n = tab_n; d.irr_tab_z = tab_z; d.irr_tab_c = tab_c; d.irr_tab_runs = tab_runs;
   }
   return PR_OK;
 }
@@ -463,11 +482,13 @@ int pr_ensemble_run(const pr_config* cfg, const pr_geom* geom, const pr_bc* upst
   int rc;
   // warps per CTA: one CTA per SM, as many warps as registers (65536 / (32 * regs)) and shared memory allow
   if (has_irregular && lpm != -1 && cells <= 31 * 8) {        // polyline node pass inside the fused kernel
-    const int m = (cells + 30) / 31;
-    if (m <= 1) rc = launch_family(pr::launch_ensemble_irregular<1>(p, has_curv, s));
-    else if (m <= 2) rc = launch_family(pr::launch_ensemble_irregular<2>(p, has_curv, s));
-    else if (m <= 4) rc = launch_family(pr::launch_ensemble_irregular<4>(p, has_curv, s));
-    else rc = launch_family(pr::launch_ensemble_irregular<8>(p, has_curv, s));
+    // short polyline reaches pack 4 / 2 members into a warp (8 / 16 lanes x 2 nodes: up to 15 / 31 nodes)
+    if (fits(8, 2)) rc = launch_family(pr::launch_ensemble_irregular<8, 2>(p, has_curv, s));
+    else if (fits(16, 2)) rc = launch_family(pr::launch_ensemble_irregular<16, 2>(p, has_curv, s));
+    else if (cells <= 31 * 2 && (lpm == 0 || lpm == 32)) rc = launch_family(pr::launch_ensemble_irregular<32, 2>(p, has_curv, s));
+    else if (cells <= 31 * 4 && (lpm == 0 || lpm == 32)) rc = launch_family(pr::launch_ensemble_irregular<32, 4>(p, has_curv, s));
+    else if (lpm == 0 || lpm == 32) rc = launch_family(pr::launch_ensemble_irregular<32, 8>(p, has_curv, s));
+    else return fail(PR_ERR_UNSUPPORTED, "lanes_per_member=%d: no polyline instantiation holds %d nodes", lpm, (int)N);
   } else if (has_irregular) rc = pr::long_reach_run(p, has_curv, true, true, s, g_launches, g_err);   // ... or the tile kernels
   else if (lpm == -1) rc = pr::long_reach_run(p, has_curv, has_compound, false, s, g_launches, g_err);   // forced long-reach path
   else if (fits(8, 1)) rc = launch_family(pr::launch_ensemble_family<8, 1, 16>(p, has_curv, s));
