@@ -417,3 +417,34 @@ def test_solver_run_ensemble_entry_point():
     assert np.array_equal(res["iterations"][0], ref["iters"]) and not res["status"].any()
     with pytest.raises(ValueError, match="unknown member overrides"):
         solver.run_ensemble({"n_bank": [0.1]})
+
+
+def test_member_order_changes_the_schedule_not_the_results():
+    """pr_config.member_order (ABI 7): the persistent kernel hands the members to its warps in the given order; every
+    member's result is bit-identical whatever the order, outputs stay in member order.  Also a launch far smaller than
+    the grid (3 members) and one that leaves a partial last ticket."""
+    from flow_sim_b200.ensemble import EnsembleRunner, to_host
+
+    flat = util.golden_inputs("gerd_calib_m0")
+    M = 1000
+    n_main = 0.020 + 0.040 * np.arange(M) / (M - 1)
+    runner = EnsembleRunner(flat, "cuda:0")
+    base = to_host(runner.roughness_sweep(n_main))                       # descending-n order inside
+    rng = np.random.default_rng(9)
+    import torch
+
+    f_ic = base                                                          # reuse: explicit solve with other orders
+    from flow_sim_b200.runner import gvf_initial_conditions
+    import copy
+
+    f = copy.copy(runner.flat)
+    f.member_n_main = torch.from_numpy(n_main).to("cuda:0")
+    ich, icq, _ = gvf_initial_conditions(f, M, flat.meta["initial_flow"], flat.meta["downstream_depth"], abi.PR_MEM_DEVICE, "cuda:0", None)
+    for order in (None, np.arange(M)[::-1].copy(), rng.permutation(M)):
+        res = to_host(runner.solve(M, member_n_main=n_main, ic_depth=ich, ic_flow=icq,
+                                   member_order=None if order is None else order.astype(np.int32)))
+        for k in ("depth", "flow", "iters", "status"):
+            assert np.array_equal(res[k], base[k]), k
+    small = to_host(runner.roughness_sweep(n_main[:3]))
+    for k in ("depth", "flow", "iters"):
+        assert np.array_equal(small[k], base[k][:3])

@@ -149,3 +149,50 @@ def test_gvf_profile_on_a_reach_too_long_for_the_shared_memory_stage():
     ho, qo, sto = oracle_py.gvf(flat, q0, hd, n_members=M)
     assert np.array_equal(st, sto)
     assert util.max_rel(h, ho) <= 1e-12 and np.array_equal(q, qo)
+
+
+def test_long_path_with_more_members_than_a_grid_dimension_holds():
+    """the tiled path put the members on gridDim.y (limit 65,535), so 65,536 members failed after the whole
+    time loop.  Members now sit on gridDim.x: 65,536 + 3 members of the akbari reach forced onto the tiled path, a few
+    of them against the fused kernel."""
+    flat = util.golden_inputs("akbari")
+    M = 65536 + 3
+    base = np.array(flat.up.series)
+    scale = np.linspace(0.6, 1.4, M)
+    flat.up.series = base[0] + (base - base[0])[None, :] * scale[:, None]
+    out = run_flat(flat, n_members=M, out_mode=abi.PR_OUT_UPSTREAM, lanes=-1)
+    assert not out["status"].any()
+    pick = np.array([0, 1, 65534, 65535, 65536, M - 1])
+    f2 = util.golden_inputs("akbari")
+    f2.up.series = flat.up.series[pick]
+    ref = run_flat(f2, n_members=len(pick), out_mode=abi.PR_OUT_UPSTREAM)
+    util.assert_parity(out["depth"][pick], out["flow"][pick], ref["depth"], ref["flow"], "tiled path, 65,539 members")
+    assert np.array_equal(out["iters"][pick], ref["iters"])
+
+
+def test_two_streams_run_long_reaches_side_by_side():
+    """The long-reach path hands out pooled workspaces instead of holding a process-wide lock: two device-memory runs
+    enqueued on two streams (neither call waits for the GPU) both come out right, and a third run reuses a workspace."""
+    import torch
+
+    from flow_sim_b200.ensemble import EnsembleRunner, to_host
+
+    flat = util.golden_inputs("akbari_long")                 # 2 001 nodes: the tiled path
+    ref = util.golden_outputs("akbari_long")
+    runner = EnsembleRunner(flat, "cuda:0")
+    L = flat.n_levels
+    series = np.tile(np.array(flat.up.series)[None, :], (4, 1))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(s1):
+        a = runner.solve(4, up_series=series, out_mode=abi.PR_OUT_FULL, stream=s1.cuda_stream)
+    with torch.cuda.stream(s2):
+        b = runner.solve(4, up_series=series, out_mode=abi.PR_OUT_FULL, stream=s2.cuda_stream)
+    torch.cuda.synchronize()
+    c = runner.solve(4, up_series=series, out_mode=abi.PR_OUT_FULL)
+    torch.cuda.synchronize()
+    for res in (to_host(a), to_host(b), to_host(c)):
+        assert not res["status"].any()
+        for m in range(4):
+            util.assert_parity(res["depth"][m], res["flow"][m], ref["depth"], ref["flow"], "two streams")
+            assert np.array_equal(res["iters"][m], ref["iters"])
+    assert abi.load_library().pr_long_last_trips() > 0

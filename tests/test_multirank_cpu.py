@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import util
-from flow_sim_b200.ensemble import gather_members, shard_bounds, shard_members
+from flow_sim_b200.ensemble import gather_members, gather_packed, shard_bounds, shard_members
 
 
 def test_shard_bounds_cover_the_ensemble_exactly_once():
@@ -57,8 +57,15 @@ def _worker(rank, world, port, total, layout, out_path):
                                  [1562.5, 3850, 6000, 10000, 14000, 21000], [497.5, 500, 502, 505, 507, 510])
     rmse = gather_members(torch.from_numpy(rm), total, rank, world, layout)
     iters = gather_members(torch.from_numpy(res["iters"].astype(np.int32)), total, rank, world, layout)
+    # the strong-scaling gather of bench.py: RMSE + iteration counts + status + upstream series as ONE message
+    local = dict(rmse=torch.from_numpy(rm), iters=torch.from_numpy(res["iters"].astype(np.int32)),
+                 status=torch.from_numpy(res["status"].astype(np.int32)), depth=torch.from_numpy(res["depth"]),
+                 flow=torch.from_numpy(res["flow"]))
+    packed = gather_packed(local, total, rank, world, layout)
     if rank == 0:
-        np.savez(out_path, rmse=rmse.numpy(), iters=iters.numpy())
+        np.savez(out_path, rmse=rmse.numpy(), iters=iters.numpy(), p_rmse=packed["rmse"].numpy(), p_iters=packed["iters"].numpy(),
+                 p_status=packed["status"].numpy(), p_depth=packed["depth"].numpy(), p_flow=packed["flow"].numpy(),
+                 p_bytes=packed["bytes_per_member"])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -79,3 +86,9 @@ def test_two_rank_gather_equals_single_process(tmp_path, total, layout):
                                 [1562.5, 3850, 6000, 10000, 14000, 21000], [497.5, 500, 502, 505, 507, 510])
     assert np.array_equal(got["rmse"], rm)            # bit-identical: sharding must not change any member
     assert np.array_equal(got["iters"], res["iters"])
+    # the packed gather carries the same bytes: 8 + 4 (L-1) + 4 + 16 L per member
+    L = flat.n_levels
+    assert int(got["p_bytes"]) == 8 + 4 * (L - 1) + 4 + 16 * L == 668
+    assert np.array_equal(got["p_rmse"], rm) and np.array_equal(got["p_iters"], res["iters"])
+    assert np.array_equal(got["p_status"], res["status"])
+    assert np.array_equal(got["p_depth"], res["depth"]) and np.array_equal(got["p_flow"], res["flow"])
