@@ -5,7 +5,7 @@
  * --impl reference leg may load this; the product path never does.
  *
  * Parity status: PINNED.  oracle/make_golden.py runs the live reference (cve-mohd/flow-sim,
- * /root/reference) and tests/test_oracle_vs_golden.py checks this file against those outputs for
+ * /root/reference) and tests/test_oracle_golden.py checks this file against those outputs for
  * configs 1-4 (depth, flow <= 1e-9 relative, identical Newton iteration counts), against per-iteration
  * (J.data, R, delta) captures, and against the reference's two rating-curve CSVs.
  *
