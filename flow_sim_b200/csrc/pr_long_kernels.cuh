@@ -40,6 +40,8 @@ constexpr int kChainMaxK = 64;     // tile cells per lane in the chain kernel ->
 struct LongParams {
   DevParams p;
   const double* geo;   // derived geometry table [F_COUNT][N] (stage_geometry layout, NP = N)
+  const double* geo_tile;  // the same per tile in lane-major order, [T][F_COUNT][kLongM + 1][32]: slot (j, lane) of tile t is
+                           // node t*128 + 4*lane + j, so a warp's load of one field is 256 contiguous bytes
   double *xh, *xq;     // current iterate [M][N] (read)
   double *xh_out, *xq_out;   // next iterate (written by the tile kernel): tiles read their right neighbour's first node, so the
                              // update cannot be done in place
@@ -52,6 +54,8 @@ struct LongParams {
   GateState* gate;                               // [M] gate-controlled rating curve state
   int* n_done;         // [0] members finished so far, [1] Newton trips made
   int T, Kc;
+  int Np;              // row stride of the iterate and of the level constants: N rounded up to a multiple of 4, so that a
+                       // lane's four nodes / cells are always one aligned 32-byte group
   long long max_trips;
   cudaGraphConditionalHandle loop;               // WHILE node of the trip loop (graph-driven runs)
 };
@@ -59,6 +63,19 @@ constexpr int kTileRec = 11;
 
 static __global__ void pr_long_geometry(DevGeom g, int N, double* table) {
   stage_geometry(g, N, N, table, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, [](int i) { return i; });
+}
+
+constexpr int kTileSlots = (kLongM + 1) * 32;     // node slots of a tile in the lane-major table
+
+static __global__ void pr_long_geometry_tiles(const double* __restrict__ table, int N, int T, double* __restrict__ tiles) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)T * F_COUNT * kTileSlots;
+  if (i >= total) return;
+  const int slot = (int)(i % kTileSlots), f = (int)((i / kTileSlots) % F_COUNT), t = (int)(i / ((long long)kTileSlots * F_COUNT));
+  const int lane = slot & 31, j = slot >> 5;
+  int nd = t * kTileCells + lane * kLongM + j;
+  nd = nd < N ? nd : N - 1;
+  tiles[i] = table[(size_t)f * N + nd];
 }
 
 // Device workspace of one long-reach run (iterate, level constants, tile cells: ~7 GB for config 5).  Workspaces are
@@ -247,27 +264,45 @@ __global__ void __launch_bounds__(128, (IRR || CURV || CMP) ? 2 : PR_LONG_CTAS) 
   const int c0 = t * kTileCells + lane * kLongM;        // first cell / node of this lane
   int nc = (N - 1) - c0;
   nc = nc < 0 ? 0 : (nc > kLongM ? kLongM : nc);
-  const double* xh = q.xh + (size_t)m * N;
-  const double* xq = q.xq + (size_t)m * N;
-  double* xh_out = q.xh_out + (size_t)m * N;
-  double* xq_out = q.xq_out + (size_t)m * N;
-  double* pc = q.pc + (size_t)m * 4 * N;
+  const int Np = q.Np;
+  const double* xh = q.xh + (size_t)m * Np;
+  const double* xq = q.xq + (size_t)m * Np;
+  double* xh_out = q.xh_out + (size_t)m * Np;
+  double* xq_out = q.xq_out + (size_t)m * Np;
+  double* pc = q.pc + (size_t)m * 4 * Np;
   // Every global load of this warp's state is issued here, before anything depends on one of them, so the warp pays
   // the DRAM latency once instead of once per dependent group of loads.
   const int act = q.active[m];             // 1 running, 3 last level accepted (its output is still to be written)
   const int conv = FIRST ? 0 : q.conv[m];
   double h[kLongM + 1], qq[kLongM + 1], pcv[kLongM][4];
+  // a lane's four nodes / cells are 32 contiguous, 32-byte aligned bytes (rows are padded to a multiple of 4): vector
+  // accesses, and a warp's access is 1 KB contiguous instead of 32 strided doubles (lanes at the end of the reach take
+  // the scalar path)
+  static_assert(kLongM == 4, "vector access assumes four cells per lane");
+  const bool vec = c0 + kLongM < N;
+  if (vec) {
+    const double4 a = *reinterpret_cast<const double4*>(xh + c0), b = *reinterpret_cast<const double4*>(xq + c0);
+    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = xh[c0 + 4];
+    qq[0] = b.x; qq[1] = b.y; qq[2] = b.z; qq[3] = b.w; qq[4] = xq[c0 + 4];
 #pragma unroll
-  for (int j = 0; j <= kLongM; ++j) {
-    const int nd = c0 + j < N ? c0 + j : N - 1;
-    h[j] = xh[nd];
-    qq[j] = xq[nd];
-  }
+    for (int f = 0; f < 4; ++f) {
+      double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (!FIRST) v = *reinterpret_cast<const double4*>(pc + (size_t)f * Np + c0);
+      pcv[0][f] = v.x; pcv[1][f] = v.y; pcv[2][f] = v.z; pcv[3][f] = v.w;
+    }
+  } else {
 #pragma unroll
-  for (int j = 0; j < kLongM; ++j) {
-    const int c = c0 + j < N - 1 ? c0 + j : N - 2;
+    for (int j = 0; j <= kLongM; ++j) {
+      const int nd = c0 + j < N ? c0 + j : N - 1;
+      h[j] = xh[nd];
+      qq[j] = xq[nd];
+    }
 #pragma unroll
-    for (int f = 0; f < 4; ++f) pcv[j][f] = FIRST ? 0.0 : pc[(size_t)f * N + c];
+    for (int j = 0; j < kLongM; ++j) {
+      const int c = c0 + j < N - 1 ? c0 + j : N - 2;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) pcv[j][f] = FIRST ? 0.0 : pc[(size_t)f * Np + c];
+    }
   }
   double yL1 = 0.0, yL2 = 0.0, yR1 = 0.0, yR2 = 0.0;      // updates of the tile's first node / of the next tile's
   if (!FIRST) {
@@ -282,27 +317,39 @@ __global__ void __launch_bounds__(128, (IRR || CURV || CMP) ? 2 : PR_LONG_CTAS) 
 #define LEL(j, c) elw[((j)*9 + (c)) * 32 + lane]
   NodeVals nv[2];
   // node pass of one node: arithmetic on the derived table, or polyline scans for an IrregularSection node
-  auto eval_node = [&](int nd, double hh, double qv, NodeVals& out) {
-    if (IRR && q.geo[F_KIND * N + nd] == (double)PR_XS_IRREGULAR) node_eval_irregular<DevParams, CURV>(p.geo, nd, hh, qv, rg, p, out, nullptr);
-    else node_eval<CURV, 4, false, DevParams, CMP>(q.geo, N, nd, hh, qv, rg, p, out);
+  const double* tg = q.geo_tile + (size_t)t * F_COUNT * kTileSlots;       // this tile's geometry, slot (j, lane) at j*32 + lane
+  auto eval_node = [&](int j, double hh, double qv, NodeVals& out) {
+    const int nd = c0 + j < N ? c0 + j : N - 1;
+    if (IRR && tg[F_KIND * kTileSlots + j * 32 + lane] == (double)PR_XS_IRREGULAR) node_eval_irregular<DevParams, CURV>(p.geo, nd, hh, qv, rg, p, out, nullptr);
+    else node_eval<CURV, 4, false, DevParams, CMP>(tg, kTileSlots, j * 32 + lane, hh, qv, rg, p, out);
   };
   // One pass over the lane's cells on the state (h, qq): residuals + Jacobian per cell and the Schur condensation into S.
   //   RECORDS: keep the elimination records (U part);  REFRESH: this state is (becomes) the stored level - its level
   //   constants replace the old ones, in memory and in pcv, once the old ones have been used for this cell
+  // the refreshed level constants go back to memory
+  auto store_constants = [&]() {
+    if (vec) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        *reinterpret_cast<double4*>(pc + (size_t)f * Np + c0) = make_double4(pcv[0][f], pcv[1][f], pcv[2][f], pcv[3][f]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kLongM; ++j)
+        if (j < nc) {
+#pragma unroll
+          for (int f = 0; f < 4; ++f) pc[(size_t)f * Np + c0 + j] = pcv[j][f];
+        }
+    }
+  };
   auto pass = [&](const bool records, const bool refresh, Cell& S, double& ss) {
-    eval_node(c0 < N ? c0 : N - 1, h[0], qq[0], nv[0]);
+    eval_node(0, h[0], qq[0], nv[0]);
 #pragma unroll
     for (int j = 0; j < kLongM; ++j) {
-      const int nd = c0 + j + 1 < N ? c0 + j + 1 : N - 1;
-      eval_node(nd, h[j + 1], qq[j + 1], nv[(j + 1) & 1]);
+      eval_node(j + 1, h[j + 1], qq[j + 1], nv[(j + 1) & 1]);
       if (j < nc) {
-        const int c = c0 + j;
         Cell e;
         ss += cell_assemble(nv[j & 1], nv[(j + 1) & 1], p, pcv[j][0], pcv[j][1], pcv[j][2], pcv[j][3], e);
-        if (refresh) {
-          level_constants(nv[j & 1], nv[(j + 1) & 1], p, pcv[j][0], pcv[j][1], pcv[j][2], pcv[j][3]);
-          pc[c] = pcv[j][0]; pc[N + c] = pcv[j][1]; pc[2 * N + c] = pcv[j][2]; pc[3 * N + c] = pcv[j][3];
-        }
+        if (refresh) level_constants(nv[j & 1], nv[(j + 1) & 1], p, pcv[j][0], pcv[j][1], pcv[j][2], pcv[j][3]);
         if (j == 0) S = e;
         else {
           Elim el;
@@ -321,9 +368,11 @@ __global__ void __launch_bounds__(128, (IRR || CURV || CMP) ? 2 : PR_LONG_CTAS) 
   if (FIRST) {
     // level 0: the level constants of the initial state (the cells assembled on the way are not used)
     pass(false, true, S, ss);
+    store_constants();
   } else {
     // ---------------- U: tile interior of trip k-1 with both end nodes known ----------------
     pass(true, conv != 0, S, ss);
+    if (conv) store_constants();
     const int lanes = (N - 1 - t * kTileCells + kLongM - 1) / kLongM;  // lanes of this tile that own cells
     const int Lt = lanes < 32 ? lanes : 32;
     double l1, l2, d11, d12, d21, d22, u1, u2, ra, rb;
@@ -378,11 +427,17 @@ __global__ void __launch_bounds__(128, (IRR || CURV || CMP) ? 2 : PR_LONG_CTAS) 
     if (act == 3) return;            // the member's last level: nothing left to solve
 #pragma unroll
     for (int j = 0; j <= kLongM; ++j) { h[j] += dh[j]; qq[j] += dq[j]; }       // x_k
+    if (vec) {                 // nc == 4
+      *reinterpret_cast<double4*>(xh_out + c0) = make_double4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<double4*>(xq_out + c0) = make_double4(qq[0], qq[1], qq[2], qq[3]);
+      if (last_lane) { xh_out[c0 + kLongM] = h[kLongM]; xq_out[c0 + kLongM] = qq[kLongM]; }     // its cell 3 ends at node N-1
+    } else {
 #pragma unroll
-    for (int j = 0; j <= kLongM; ++j) {
-      if (j < nc || (j == nc && last_lane)) {
-        xh_out[c0 + j] = h[j];
-        xq_out[c0 + j] = qq[j];
+      for (int j = 0; j <= kLongM; ++j) {
+        if (j < nc || (j == nc && last_lane)) {
+          xh_out[c0 + j] = h[j];
+          xq_out[c0 + j] = qq[j];
+        }
       }
     }
     __syncwarp();
@@ -423,8 +478,8 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   const int N = p.N, L = p.L, T = q.T, Kc = q.Kc;
   const int level = q.level[m];
   const int it = q.it[m] + 1;
-  const double* xh = q.xh + (size_t)m * N;
-  const double* xq = q.xq + (size_t)m * N;
+  const double* xh = q.xh + (size_t)m * q.Np;
+  const double* xq = q.xq + (size_t)m * q.Np;
   const Rough rg = load_rough<4>(p.geo, m);
 #define REC(j, c) rec[((j)*10 + (c)) * 32 + lane]
   // ---- per-lane serial condensation of Kc tile cells ----
@@ -564,7 +619,7 @@ static __global__ void pr_long_init_state(const __grid_constant__ LongParams q) 
   if (i >= total) return;
   const int m = (int)(i / p.N), nd = (int)(i % p.N);
   const double h = p.ic_h[(size_t)m * p.ic_stride + nd], qv = p.ic_q[(size_t)m * p.ic_stride + nd];
-  q.xh[i] = h; q.xq[i] = qv;
+  q.xh[(size_t)m * q.Np + nd] = h; q.xq[(size_t)m * q.Np + nd] = qv;
   if (p.out_mode == PR_OUT_FULL) {
     if (p.out_h) p.out_h[(size_t)m * p.L * p.N + nd] = h;
     if (p.out_q) p.out_q[(size_t)m * p.L * p.N + nd] = qv;
@@ -648,11 +703,15 @@ int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>&
   auto dalloc = [&](size_t bytes) -> void* { return ws.get(slot++, bytes, e); };
   double* geo = (double*)dalloc(sizeof(double) * F_COUNT * (size_t)N);
   q.geo = geo;
-  q.xh = (double*)dalloc(sizeof(double) * (size_t)M * N);
-  q.xq = (double*)dalloc(sizeof(double) * (size_t)M * N);
-  q.xh_out = (double*)dalloc(sizeof(double) * (size_t)M * N);
-  q.xq_out = (double*)dalloc(sizeof(double) * (size_t)M * N);
-  q.pc = (double*)dalloc(sizeof(double) * (size_t)M * 4 * N);
+  double* geo_tile = (double*)dalloc(sizeof(double) * F_COUNT * kTileSlots * (size_t)T);
+  q.geo_tile = geo_tile;
+  const int Np = (N + 3) & ~3;
+  q.Np = Np;
+  q.xh = (double*)dalloc(sizeof(double) * (size_t)M * Np);
+  q.xq = (double*)dalloc(sizeof(double) * (size_t)M * Np);
+  q.xh_out = (double*)dalloc(sizeof(double) * (size_t)M * Np);
+  q.xq_out = (double*)dalloc(sizeof(double) * (size_t)M * Np);
+  q.pc = (double*)dalloc(sizeof(double) * (size_t)M * 4 * Np);
   q.tcell = (double*)dalloc(sizeof(double) * (size_t)M * T * kTileRec);
   q.dchain = (double*)dalloc(sizeof(double) * (size_t)M * (T + 1) * 2);
   q.qprev_last = (double*)dalloc(sizeof(double) * M);
@@ -672,12 +731,16 @@ int long_reach_run_t(const DevParams& p, cudaStream_t s, std::atomic<long long>&
   cudaMemsetAsync(q.active, 0, sizeof(int) * M, s);
 
   pr_long_geometry<<<(N + 255) / 256, 256, 0, s>>>(p.geo, N, geo);
+  {
+    const long long cells = (long long)T * F_COUNT * kTileSlots;
+    pr_long_geometry_tiles<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(geo, N, T, geo_tile);
+  }
   const long long total = (long long)M * N;
   pr_long_init_state<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q);
   const dim3 tile_grid((unsigned)((M + 3) / 4), (unsigned)T);
   const size_t tile_smem = sizeof(double) * 4 * (kLongM - 1) * 9 * 32;   // elimination records, 4 warps per CTA
   pr_long_fused<true, CMP, CURV, IRR><<<tile_grid, 128, tile_smem, s>>>(q);      // level constants of the initial state + first condensation
-  launches.fetch_add(3);
+  launches.fetch_add(4);
   const size_t chain_smem = sizeof(double) * (size_t)(Kc > 1 ? Kc - 1 : 1) * 10 * 32;
   e = cudaFuncSetAttribute(pr_long_chain<IRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem);
   if (e != cudaSuccess) return bail("long-reach chain kernel");

@@ -196,3 +196,21 @@ def test_two_streams_run_long_reaches_side_by_side():
             util.assert_parity(res["depth"][m], res["flow"][m], ref["depth"], ref["flow"], "two streams")
             assert np.array_equal(res["iters"][m], ref["iters"])
     assert abi.load_library().pr_long_last_trips() > 0
+
+
+def test_tiled_path_on_a_reach_whose_node_count_is_a_multiple_of_four():
+    """N % 4 == 0 takes the 256-bit state accesses of the tile kernel (and N - 1 = 1999 cells leave a ragged last tile):
+    the vectorised prismatic builder + device normal depth against the oracle, scenarios with different flood peaks."""
+    import oracle_py
+    from flow_sim_b200.cases.akbari_firoozi import build_long_reach_flat, flood_wave_series
+    from flow_sim_b200.runner import normal_depth_initial_conditions
+
+    flat = build_long_reach_flat(n_nodes=2000, n_steps=6)
+    h, q = normal_depth_initial_conditions(flat, 1, flat.meta["initial_flow"])
+    flat.ic_depth, flat.ic_flow = h[0], q[0]
+    flat.up.series = flood_wave_series([120.0, 200.0, 260.0, 300.0, 175.0], flat.n_levels, flat.dt)
+    ora = oracle_py.run(flat, n_members=5, out_mode=abi.PR_OUT_FULL)
+    out = run_flat(flat, n_members=5, out_mode=abi.PR_OUT_FULL)
+    assert not out["status"].any() and not ora["status"].any()
+    util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "2000-node reach")
+    assert np.array_equal(out["iters"], ora["iters"])
