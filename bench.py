@@ -69,48 +69,94 @@ def member_roughness(members: np.ndarray, total: int) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------
 
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU sampled DURING the timed region: NVML queries from a thread of this
+    process (nvidia_ml_py) - an `nvidia-smi -lms` child was seen to stall the running kernel by 3-40 ms at every sample
+    (it enumerates every GPU of the box per query); nvidia-smi is only the fall-back where NVML does not import."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.1):
         self.index = index
-        self.rows = []
+        self.period = period_s
+        self.rows = []            # (time, sm_mhz, max_mhz, reasons set, power_w)
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    def _nvml_loop(self, nv, handle):
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                pw = float(nv.nvmlDeviceGetPowerUsage(handle)) / 1000.0
+                self.rows.append((time.time(), sm, mx, {k for k, bit in names.items() if mask & bit}, pw))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            handle = None
+            try:                                   # the CUDA device's own UUID: right whatever CUDA_VISIBLE_DEVICES says
+                import torch
+
+                handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)).encode())
+            except Exception:
+                handle = None
+            if handle is None:
+                visible = (os.environ.get("CUDA_VISIBLE_DEVICES") or "").split(",")
+                entry = visible[self.index].strip() if self.index < len(visible) else ""
+                if entry.startswith("GPU-"):
+                    handle = nv.nvmlDeviceGetHandleByUUID(entry.encode())
+                else:
+                    handle = nv.nvmlDeviceGetHandleByIndex(int(entry) if entry.isdigit() else self.index)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                  "-lms", "500"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, power = [], [], set(), []
-        for t, line in self.rows:
-            if t < t0 or t > t1 + 0.2:
-                continue
-            parts = [p.strip() for p in line.split(",")]
+            parts = [p.strip() for p in line.strip().split(",")]
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[6]))
+                reasons = {name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6])
+                           if val.lower().startswith("active")}
+                self.rows.append((time.time(), float(parts[0]), float(parts[1]), reasons, float(parts[6])))
             except Exception:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (NVML and nvidia-smi unavailable)"]}
+        time.sleep(0.15)
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.2]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"], "samples": 0, "source": self.source}
+        reasons = set()
+        for r in rows:
+            reasons |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": float(max(r[4] for r in rows)), "source": self.source}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -308,10 +354,23 @@ def run_gpu_arm(args) -> dict | None:
         return step, n_host
 
     def time_steps(step, n_steps: int, warm: int):
+        import gc
+
         for _ in range(warm):
             res = step(None)
         barrier()
         per = {"step": [], "gvf": [], "solve": [], "obj": [], "gather": []}
+        # a generational garbage collection of the interpreter between two launches of a step shows up as GPU idle time
+        # inside the step's events (seen: +40 ms on one step in ten): collect now, not in the timed steps
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(step, n_steps, per)
+        finally:
+            gc.enable()
+
+    def _timed(step, n_steps, per):
+        res = None
         for _ in range(n_steps):
             flush.zero_()                       # L2 flush between timed iterations (not timed)
             barrier()
@@ -361,19 +420,26 @@ def run_gpu_arm(args) -> dict | None:
         return out
 
     def time_e2e(full: bool, n_steps: int):
+        import gc
+
         for _ in range(2):
             step_e2e(full)
         barrier()
         ms = []
-        for _ in range(n_steps):
-            flush.zero_()
-            barrier()
-            a, b = ev(), ev()
-            a.record()
-            step_e2e(full)
-            b.record()
-            barrier()
-            ms.append(a.elapsed_time(b))
+        gc.collect()
+        gc.disable()                     # (see time_steps)
+        try:
+            for _ in range(n_steps):
+                flush.zero_()
+                barrier()
+                a, b = ev(), ev()
+                a.record()
+                step_e2e(full)
+                b.record()
+                barrier()
+                ms.append(a.elapsed_time(b))
+        finally:
+            gc.enable()
         tot = max_over_ranks(sum(ms))
         return node_steps_per_step * n_steps / (tot * 1e-3), tot / n_steps
 
