@@ -398,10 +398,10 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
 }
 
 // Out-of-line entry for kernels with many node-pass call sites (the fused ensemble kernel): one copy of the scans.
-template <bool CURV>
+template <bool CURV, class KP = DevParams>
 __device__ __noinline__ void node_eval_irregular_call(const DevGeom& g, int node, double h, double Q, const Rough& rg,
-                                                      const DevParams& k, NodeVals& o, NodeConv* kc) {
-  node_eval_irregular<DevParams, CURV>(g, node, h, Q, rg, k, o, kc);
+                                                      const KP& k, NodeVals& o, NodeConv* kc, double* top_width = nullptr) {
+  node_eval_irregular<KP, CURV>(g, node, h, Q, rg, k, o, kc, top_width);
 }
 
 }  // namespace pr

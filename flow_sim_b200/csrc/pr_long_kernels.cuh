@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128, (IRR || CURV || CMP) ? 2 : PR_LONG_CTAS) 
   const double* tg = q.geo_tile + (size_t)t * F_COUNT * kTileSlots;       // this tile's geometry, slot (j, lane) at j*32 + lane
   auto eval_node = [&](int j, double hh, double qv, NodeVals& out) {
     const int nd = c0 + j < N ? c0 + j : N - 1;
-    if (IRR && tg[F_KIND * kTileSlots + j * 32 + lane] == (double)PR_XS_IRREGULAR) node_eval_irregular<DevParams, CURV>(p.geo, nd, hh, qv, rg, p, out, nullptr);
+    if (IRR && tg[F_KIND * kTileSlots + j * 32 + lane] == (double)PR_XS_IRREGULAR) node_eval_irregular_call<CURV>(p.geo, nd, hh, qv, rg, p, out, nullptr);     // out of line: ten call sites
     else node_eval<CURV, 4, false, DevParams, CMP>(tg, kTileSlots, j * 32 + lane, hh, qv, rg, p, out);
   };
   // One pass over the lane's cells on the state (h, qq): residuals + Jacobian per cell and the Schur condensation into S.
@@ -514,13 +514,13 @@ __global__ void __launch_bounds__(32) pr_long_chain(const __grid_constant__ Long
   const double hyd_dn = p.dn.series ? p.dn.series[(size_t)m * p.dn.series_stride + level] : 0.0;
   if (lane == 0) {
     NodeVals nvb; NodeConv kc;
-    if (IRR && q.geo[F_KIND * N] == (double)PR_XS_IRREGULAR) node_eval_irregular(p.geo, 0, xh[0], xq[0], rg, p, nvb, &kc);
+    if (IRR && q.geo[F_KIND * N] == (double)PR_XS_IRREGULAR) node_eval_irregular_call<false>(p.geo, 0, xh[0], xq[0], rg, p, nvb, &kc);
     else node_eval<false, 4, true>(q.geo, N, 0, xh[0], xq[0], rg, p, nvb, &kc);
     U = bc_eval<false>(p.up, m, level, hyd_up, xh[0], xq[0], 0.0, 0.0, p.dt, p.g, kc, nvb.T);
   }
   if (lane == Lc) {
     NodeVals nvb; NodeConv kc;
-    if (IRR && q.geo[F_KIND * N + N - 1] == (double)PR_XS_IRREGULAR) node_eval_irregular(p.geo, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
+    if (IRR && q.geo[F_KIND * N + N - 1] == (double)PR_XS_IRREGULAR) node_eval_irregular_call<false>(p.geo, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
     else node_eval<false, 4, true>(q.geo, N, N - 1, xh[N - 1], xq[N - 1], rg, p, nvb, &kc);
     D = bc_eval<true>(p.dn, m, level, hyd_dn, xh[N - 1], xq[N - 1], q.qprev_last[m], q.stage_prev[m], p.dt, p.g, kc, nvb.T, &q.gate[m]);
   }
