@@ -448,3 +448,18 @@ def test_member_order_changes_the_schedule_not_the_results():
     small = to_host(runner.roughness_sweep(n_main[:3]))
     for k in ("depth", "flow", "iters"):
         assert np.array_equal(small[k], base[k][:3])
+
+
+def test_pinned_result_buffers_equal_plain_copies():
+    from flow_sim_b200.ensemble import EnsembleRunner, PinnedResults, to_host
+
+    flat = util.golden_inputs("gerd_calib_m0")
+    runner = EnsembleRunner(flat, "cuda:0")
+    res = runner.roughness_sweep(np.linspace(0.02, 0.06, 40))
+    plain = to_host(res)
+    pinned = PinnedResults()
+    for _ in range(2):                      # second call reuses the buffers
+        got = pinned.fetch(res, keys=("depth", "flow", "iters", "status"))
+        assert set(got) == {"depth", "flow", "iters", "status"}
+        for k in got:
+            assert np.array_equal(got[k], plain[k]), k
