@@ -74,3 +74,23 @@ def test_prepared_call_rejects_inconsistent_member_arrays():
     flat.up.series = np.zeros((2, flat.n_levels))
     with pytest.raises(ValueError):
         PreparedCall(flat, 3)
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    """No CPU fallback: where no CUDA device is visible a well-formed call comes back PR_ERR_CUDA with the runtime's
+    message, from the ABI and (as PreissmannLibraryError) from the solver object."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is visible")
+    lib = abi.load_library()
+    flat = util.golden_inputs("example")
+    call = PreparedCall(flat, 1)
+    assert lib.pr_ensemble_run(*call.args(), None) == abi.PR_ERR_CUDA
+    assert lib.pr_last_error()
+    from flow_sim_b200.cases import build_example
+
+    solver, kw = build_example()
+    with pytest.raises(abi.PreissmannLibraryError):
+        solver.run(verbose=0, **kw)
+    assert lib.pr_long_last_trips() == -1
