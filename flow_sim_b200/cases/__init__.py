@@ -4,3 +4,4 @@ from .akbari_firoozi import build as build_akbari
 from .example import build as build_example
 from .gerd_roseires import build as build_gerd
 from .irregular import build as build_irregular
+from .irregular import build_mixed

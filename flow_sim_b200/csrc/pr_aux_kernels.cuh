@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(128) pr_derived_kernel(const __grid_constant__
     if (irregular) {             // IrregularSection.properties (cross_section.py:247-327): area and geometric top width
       double P;
       IrrTab tab;
-      if (irr_tab_get(p.raw, nd, tab)) irr_tab_eval(tab, irr_tab_interval(tab, hw), hw, 0, A, P, &T);
+      int k = 0;
+      if (irr_tab_get(p.raw, nd, tab) && !irr_tab_tie(tab, k = irr_tab_interval(tab, hw), hw)) irr_tab_eval(tab, k, hw, 0, A, P, &T);
       else irr_properties(p.raw.irr_x + poly_off, p.raw.irr_z + poly_off, 0, poly_n - 1, hw, A, P, T);
     } else if (d <= hb) {        // rectangle / simple trapezoid / compound in bank (h_bank staged as 1e300 otherwise)
       T = b + m2 * d;
@@ -217,8 +218,8 @@ __device__ __forceinline__ double normal_flow_residual(const NormalDepthParams& 
     IrrSec sec;
     IrrTab tab;
     int runs;
-    if (irr_tab_get(p.raw, nd, tab)) irr_section_tab(tab, hw, nl, nm, nr, sec, runs);
-    else irr_section(p.raw.irr_x + off, p.raw.irr_z + off, n, hw, p.raw.irr_left[nd], p.raw.irr_right[nd], nl, nm, nr, sec);
+    if (!(irr_tab_get(p.raw, nd, tab) && irr_section_tab(tab, hw, nl, nm, nr, sec, runs)))
+      irr_section(p.raw.irr_x + off, p.raw.irr_z + off, n, hw, p.raw.irr_left[nd], p.raw.irr_right[nd], nl, nm, nr, sec);
     return Qt - sec.K * sqrt(S0);
   }
   NodeVals nv;

@@ -268,6 +268,13 @@ __device__ __forceinline__ int irr_tab_interval(const IrrTab& t, double hw) {
   return lo - 1;
 }
 
+// A vertex exactly AT the stage: the reference's properties() adds an intersection point only beside a vertex strictly
+// above the water (cross_section.py:292,300), so with z == hw the segments between that vertex and its wet neighbours
+// drop out of area, perimeter and width - a jump at one stage value that the polynomial pieces do not have.  It is hit
+// in practice (an initial depth of 2.0 over a survey with round elevations), so such stages go to the scans.
+// k = irr_tab_interval(t, hw).
+__device__ __forceinline__ bool irr_tab_tie(const IrrTab& t, int k, double hw) { return k + 1 < t.nb && t.z[k + 1] == hw; }
+
 // sec: 0 whole section, 1 / 2 / 3 left / main / right roughness sub-section
 __device__ __forceinline__ void irr_tab_eval(const IrrTab& t, int k, double hw, int sec, double& A, double& P, double* T) {
   if (k < 0) { A = 0.0; P = 0.0; if (T) *T = 0.0; return; }
@@ -280,12 +287,14 @@ __device__ __forceinline__ void irr_tab_eval(const IrrTab& t, int k, double hw, 
 
 __device__ __forceinline__ double irr_pow23(double v) { const double c = cbrt(v); return c * c; }     // v^(2/3), v >= 0
 
-// irr_section from the node's stage table
-__device__ inline void irr_section_tab(const IrrTab& t, double hw, double nl, double nm, double nr, IrrSec& s, int& runs) {
+// irr_section from the node's stage table; false = one of the three stages sits exactly on a vertex elevation (see
+// irr_tab_tie): nothing is written, the caller scans
+__device__ inline bool irr_section_tab(const IrrTab& t, double hw, double nl, double nm, double nr, IrrSec& s, int& runs) {
   const double dh = 1e-6;
   const int k = irr_tab_interval(t, hw);
   const int k1 = (k >= 0 && hw - dh > t.z[k]) ? k : irr_tab_interval(t, hw - dh);
   const int k2 = (k >= 0 && (k + 1 >= t.nb || !(hw + dh > t.z[k + 1]))) ? k : irr_tab_interval(t, hw + dh);
+  if (irr_tab_tie(t, k, hw) || irr_tab_tie(t, k1, hw - dh) || irr_tab_tie(t, k2, hw + dh)) return false;
   double P1, P2;
   irr_tab_eval(t, k, hw, 0, s.A, s.P, &s.T);
   irr_tab_eval(t, k1, hw - dh, 0, s.A1, P1, nullptr);
@@ -316,6 +325,7 @@ __device__ inline void irr_section_tab(const IrrTab& t, double hw, double nl, do
     s.K = s.A * R23 / s.n_eq;
     s.dKA = (R23 + s.A * (2. / 3.) * (R23 / s.R) * s.dRA) / s.n_eq;
   }
+  return true;
 }
 
 // Everything the scheme needs from an irregular node: the counterpart of node_eval.
@@ -338,9 +348,7 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   // the combined conveyance of the sub-channels; everything else stays with the whole section
   int runs = 0;
   IrrTab tab;
-  if (irr_tab_get(g, node, tab)) {
-    irr_section_tab(tab, hw, nl, nm, nr, sec, runs);
-  } else {
+  if (!(irr_tab_get(g, node, tab) && irr_section_tab(tab, hw, nl, nm, nr, sec, runs))) {
     irr_section(x, z, n, hw, lim_l, lim_r, nl, nm, nr, sec);
     for (int i = 0; i < n;) {
       if (!(z[i] < hw)) { ++i; continue; }

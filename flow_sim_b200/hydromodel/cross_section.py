@@ -94,6 +94,22 @@ class TrapezoidalSection(CrossSection):
     def area(self, hw):
         return self.properties(hw)[0]
 
+    def z_at(self, x):
+        """Bed elevation at lateral station ``x`` of the section centred on 0 (cross_section.py:795-849) - what the
+        blend of a trapezoid with a polyline samples.  Outside a rectangle's bed the elevation is +inf."""
+        x = float(x)
+        half = self.b_main / 2.0
+        if self._is_rect:
+            return self.z_bed if -half < x < half else np.inf
+        if self._is_compound and not (self.left_fp_limit <= x <= self.right_fp_limit):
+            # floodplain bed at bank level, then the outer wall at 1 : m_fp
+            beyond = (self.left_fp_limit - self.b_fp_left) - x if x < self.left_fp_limit \
+                else x - (self.right_fp_limit + self.b_fp_right)
+            return self.z_bank if beyond <= 0 else self.z_bank + beyond / self.m_fp
+        if -half <= x <= half:
+            return self.z_bed
+        return self.z_bed + ((x - half) if x > half else (-x - half)) / self.m_main
+
     def wetted_perimeter(self, hw):
         return self.properties(hw)[1]
 
@@ -402,7 +418,8 @@ class IrregularSection(CrossSection):
 
 
 def interpolate_cross_section(xs1, xs2, dist1, dist2):
-    """Distance-weighted blend of two trapezoidal sections (cross_section.py:857-930).  Returns xs1 / xs2
+    """Distance-weighted blend of two sections (cross_section.py:857-969): two trapezoids give a trapezoid, a polyline
+    on either side gives a polyline on the union of the lateral stations.  Returns xs1 / xs2
     themselves when the location coincides with one of them."""
     total = dist1 + dist2
     if total < 1e-9 or dist1 < 1e-9:
@@ -414,8 +431,6 @@ def interpolate_cross_section(xs1, xs2, dist1, dist2):
     slope = None if (xs1.bed_slope is None or xs2.bed_slope is None) else mix(xs1.bed_slope, xs2.bed_slope)
     if not (isinstance(xs1, TrapezoidalSection) and isinstance(xs2, TrapezoidalSection)):
         # a polyline on either side: blend bed elevations on the union of the lateral stations (cross_section.py:933-969)
-        if not all(hasattr(s, "z_at") for s in (xs1, xs2)):
-            raise NotImplementedError("interpolation between a TrapezoidalSection and an IrregularSection")
         stations = [s.x for s in (xs1, xs2) if isinstance(s, IrregularSection)]
         grid = np.union1d(stations[0], stations[1]) if len(stations) == 2 else stations[0]
         bed = lambda s: np.array([s.z_at(v) for v in grid], dtype=float)

@@ -36,7 +36,7 @@ def calib_n(m: int) -> float:
 # one release scenario (a member of a gate-state ensemble): lower pool, jammed gates, narrower blend buffer
 RELEASE_SCENARIO = dict(initial_roseires_level=486.2, rating_kwargs=dict(jammed_spillways=2, jammed_sluice_gates=1, buffer=0.3))
 
-CASES = ["example", "akbari", "gerd_full", "akbari_long", "storage_general", "gerd_release", "gerd_gated", "gerd_gated_full", "irregular", "irregular_curved", "irregular_pocket"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
+CASES = ["example", "akbari", "gerd_full", "akbari_long", "storage_general", "gerd_release", "gerd_gated", "gerd_gated_full", "irregular", "irregular_curved", "irregular_pocket", "mixed_sections"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
 
 
 def build(case: str):
@@ -67,6 +67,8 @@ def build(case: str):
     if case == "irregular_pocket":   # split flow the reference survives: a side pocket behind a ridge (75 of 117
         # node-levels run on the multi-sub-channel conveyance, cross_section.py:374-439)
         return rh.build_irregular(pocket=True)
+    if case == "mixed_sections":     # compound trapezoid upstream, polyline downstream, blended node by node (cross_section.py:933-969)
+        return rh.build_mixed()
     if case == "gerd_gated_full":   # config 3 (curvature, 16 days) with gate control: dozens of open/close cycles
         return rh.build_gerd(calibration=False, rating_kwargs=dict(smooth=False))
     if case == "gerd_full":

@@ -333,3 +333,32 @@ def build_irregular(levee: bool = False, curved: bool = False, pocket: bool = Fa
         ch.set_cross_sections([0.0, L], [sec(S0 * L, 0.0), sec(0.0, 1.0)])
     solver = PreissmannSolver(channel=ch, theta=0.6, time_step=dt, spatial_step=1000.0, simulation_time=8 * dt)
     return solver, dict(tolerance=1e-6, max_iter=60)
+
+
+def build_mixed():
+    """A reach that starts on a compound TrapezoidalSection and ends on a surveyed polyline: every interior node is the
+    reference's blend of the two (cross_section.py:933-969 - the trapezoid sampled through z_at, :795-849, on the
+    polyline's stations), so node 0 is a trapezoid and nodes 1.. are IrregularSections."""
+    setup_reference()
+    from math import pi, sin
+
+    from src.hydromodel.boundary import Boundary
+    from src.hydromodel.channel import Channel
+    from src.hydromodel.cross_section import IrregularSection, TrapezoidalSection
+    from src.hydromodel.hydrograph import Hydrograph
+    from src.hydromodel.preissmann import PreissmannSolver
+
+    L, S0, dt = 12000.0, 0.0005, 1800
+    wave = lambda t: 60 + 40 * sin(pi * min(t, 6 * dt) / (6 * dt)) ** 2
+    us = Boundary("flow_hydrograph", chainage=0, bed_level=S0 * L, initial_depth=2.0, hydrograph=Hydrograph(function=wave))
+    ds = Boundary("fixed_depth", chainage=L, bed_level=0.0, initial_depth=2.0)
+    ch = Channel(upstream_boundary=us, downstream_boundary=ds, initial_flow=60.0, roughness=0.03, width=30.0,
+                 interpolation_method="linear")
+    head = TrapezoidalSection(z_bed=S0 * L, b_main=12.0, m_main=2.0, n_main=0.03, z_bank=S0 * L + 2.4, b_fp_left=6.0,
+                              b_fp_right=9.0, m_fp=3.0, n_left=0.05, n_right=0.06, bed_slope=S0)
+    tail = IrregularSection(x=np.array([-25, -15, -11, -5, 5, 11, 15, 25.0]), z=np.array([6, 3.0, 1.2, 0.0, 0.1, 1.5, 3.2, 6.0]),
+                            n=0.03, bed_slope=S0)
+    tail.set_roughness_para((0.05, 0.03, 0.06, -11.0, 11.0))
+    ch.set_cross_sections([0.0, L], [head, tail])
+    solver = PreissmannSolver(channel=ch, theta=0.6, time_step=dt, spatial_step=1000.0, simulation_time=8 * dt)
+    return solver, dict(tolerance=1e-6, max_iter=60)

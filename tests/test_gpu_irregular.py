@@ -203,6 +203,30 @@ def test_mirror_solver_run_with_polyline_sections():
     assert np.array_equal(pocket.iterations, ref["iters"])
 
 
+@pytest.mark.parametrize("lanes", [0, 8, 16, 32])
+def test_reach_from_a_trapezoid_to_a_polyline(lanes):
+    """Node 0 a compound trapezoid, the other nodes the reference's blend of it with a polyline (cross_section.py:795-849,
+    933-969): the flat inputs against the reference run (tests/golden/mixed_sections.*), in every packing; then through
+    the mirror API, derived arrays from the device for both node kinds."""
+    flat = util.golden_inputs("mixed_sections")
+    ref = util.golden_outputs("mixed_sections")
+    assert flat.geom["kind"][0] != flat.geom["kind"][1]
+    out = run_flat(flat, lanes=lanes)
+    assert np.array_equal(out["iters"][0], ref["iters"])
+    util.assert_parity(out["depth"][0], out["flow"][0], ref["depth"], ref["flow"], f"mixed_sections, lanes={lanes}")
+    if lanes == 0:
+        from flow_sim_b200.cases import build_mixed
+
+        solver, kw = build_mixed()
+        solver.run(verbose=0, **kw)
+        util.assert_parity(solver.depth, solver.flow, ref["depth"], ref["flow"], "mirror run, mixed_sections")
+        assert np.array_equal(solver.iterations, ref["iters"])
+        sections = solver.channel.xs_at_node
+        area = np.array([[sections[i].area(solver.depth[k, i] + sections[i].z_min) for i in range(len(sections))]
+                         for k in range(solver.depth.shape[0])])
+        assert np.allclose(solver.area, area, rtol=1e-12, atol=0)
+
+
 def test_general_storage_with_head_losses_behind_a_polyline_node():
     """Area curve + outflow curve + head losses (friction over the reservoir length uses the polyline node's
     conveyance, composite n and dA/dh) - the downstream boundary of the storage_general case on the polyline reach."""

@@ -8,7 +8,7 @@ import pytest
 
 import util
 from flow_sim_b200 import abi, hydromodel
-from flow_sim_b200.cases import build_akbari, build_example, build_gerd, build_irregular
+from flow_sim_b200.cases import build_akbari, build_example, build_gerd, build_irregular, build_mixed
 from flow_sim_b200.cases import akbari_firoozi, gerd_roseires
 from flow_sim_b200.flatten import flatten_solver, load_flat, save_flat
 
@@ -44,6 +44,7 @@ def _same_flat(a, b):
     ("irregular_levee", lambda: build_irregular(bar=True)),
     ("irregular_curved", lambda: build_irregular(curved=True)),
     ("irregular_pocket", lambda: build_irregular(pocket=True)),
+    ("mixed_sections", lambda: build_mixed()),      # trapezoid blended with a polyline (cross_section.py:795-849, 933-969)
 ])
 def test_case_builders_reproduce_reference_inputs(case, builder):
     solver, kw = builder()
@@ -119,6 +120,29 @@ def test_split_flow_conveyance_equals_the_reference():
         assert len(xs.get_subchannels(h + xs.z_min)) == int(nsub)
         assert (xs.friction_slope(h, Q), xs.dSf_dA(h, Q), xs.dSf_dQ(h, Q)) == (Sf, dSfA, dSfQ), (node, h)
         assert (xs.conveyance(h + xs.z_min), xs.dK_dA(h + xs.z_min)) == (K, dKA)
+
+
+def test_trapezoid_bed_profile_and_mixed_blend_equal_the_reference():
+    """`TrapezoidalSection.z_at` (cross_section.py:795-849) and the blend of a trapezoid with a polyline
+    (`interpolate_cross_section`, :933-969, either order, three weights) against the live reference's values
+    (tests/golden/trapezoid_z_at_probe.npz, oracle/make_probes.py) - bit for bit."""
+    fx = np.load(f"{util.GOLD}/trapezoid_z_at_probe.npz")
+    T, I = hydromodel.TrapezoidalSection, hydromodel.IrregularSection
+    shapes = dict(rect=T(z_bed=1.5, b_main=12.0, m_main=0.0, n_main=0.03), simple=T(z_bed=1.5, b_main=12.0, m_main=2.0, n_main=0.03),
+                  compound=T(z_bed=1.5, b_main=12.0, m_main=2.0, n_main=0.03, z_bank=3.9, b_fp_left=6.0, b_fp_right=9.0, m_fp=3.0,
+                             n_left=0.05, n_right=0.06, bed_slope=5e-4))
+    for name, xs in shapes.items():
+        assert np.array_equal(np.array([xs.z_at(v) for v in fx["grid"]]), fx[f"z_{name}"]), name
+    assert np.isinf(fx["z_rect"]).any() and (fx["z_compound"] == 3.9).any()
+    poly = I(x=np.array([-25, -15, -11, -5, 5, 11, 15, 25.0]), z=np.array([6, 3.0, 1.2, 0.0, 0.1, 1.5, 3.2, 6.0]), n=0.03, bed_slope=5e-4)
+    poly.set_roughness_para((0.05, 0.03, 0.06, -11.0, 11.0))
+    for j, (d1, d2) in enumerate(fx["blend_dists"]):
+        for tag, (a, b) in (("tp", (shapes["compound"], poly)), ("pt", (poly, shapes["compound"]))):
+            s = hydromodel.interpolate_cross_section(a, b, d1, d2)
+            assert isinstance(s, I)
+            assert np.array_equal(s.x, fx[f"blend_{tag}{j}_x"]) and np.array_equal(s.z, fx[f"blend_{tag}{j}_z"]), (tag, j)
+            par = [s.n_left, s.n_main, s.n_right, s.left_fp_limit, s.right_fp_limit, s.bed_slope, s.curvature]
+            assert np.array_equal(np.array(par, dtype=np.float64), fx[f"blend_{tag}{j}_par"]), (tag, j)
 
 
 def test_flat_roundtrip(tmp_path):

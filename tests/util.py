@@ -11,7 +11,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL = 1e-9
 
 CALIB_MEMBERS = [0, 8191, 21845, 30000, 36408, 43690, 54321, 65535]
-SMALL_CASES = ["example", "akbari", "storage_general", "gerd_release", "gerd_gated", "irregular", "irregular_curved", "irregular_pocket"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
+SMALL_CASES = ["example", "akbari", "storage_general", "gerd_release", "gerd_gated", "irregular", "irregular_curved", "irregular_pocket", "mixed_sections"] + [f"gerd_calib_m{m}" for m in CALIB_MEMBERS]
 
 
 def calib_n(m):
