@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Differential fuzzing against the LIVE reference (build container only; test infrastructure).
+
+For every seed, `tests/fuzz_cases.random_case` builds one random small reach twice - on the reference's own classes and
+on the mirror API - and this script checks that (1) flattening either object tree gives the same inputs, bit for bit,
+and (2) the C oracle reproduces the reference's run: depth, flow (<= 1e-10 relative; 1e-15 typical, 1e-11 where the
+finite-difference Jacobian of polyline sections amplifies rounding), Newton iteration counts
+(identical) and, where the reference raises, the level it dies in.  `--write` stores the reference's outputs of the
+seeds as the corpus the GPU parity test replays on the box (tests/golden/fuzz_corpus.npz; inputs are rebuilt there from
+the seed on the mirror API and checked against the digest stored here).
+
+    python oracle/fuzz_reference.py --seeds 0:320,1000:1032 [--write] [--jobs 16]      (~5 min on 16 cores)
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+from multiprocessing import Pool
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path[:0] = [HERE, REPO, os.path.join(REPO, "tests")]
+CORPUS = os.path.join(REPO, "tests", "golden", "fuzz_corpus.npz")
+
+
+def one(seed):
+    import fuzz_cases
+    import oracle_py
+    import ref_harness as rh
+    from flow_sim_b200.flatten import flatten_solver
+
+    rh.setup_reference()
+    from types import SimpleNamespace
+
+    from src.hydromodel.boundary import Boundary
+    from src.hydromodel.channel import Channel
+    from src.hydromodel.cross_section import IrregularSection, TrapezoidalSection
+    from src.hydromodel.hydrograph import Hydrograph
+    from src.hydromodel.lumped_storage import LumpedStorage
+    from src.hydromodel.preissmann import PreissmannSolver
+    from src.hydromodel.rating_curve import RatingCurve
+
+    ref_ns = SimpleNamespace(Boundary=Boundary, Channel=Channel, Hydrograph=Hydrograph, LumpedStorage=LumpedStorage,
+                             PreissmannSolver=PreissmannSolver, RatingCurve=RatingCurve, TrapezoidalSection=TrapezoidalSection,
+                             IrregularSection=IrregularSection)
+    d = fuzz_cases.describe(seed)
+    rec = dict(seed=seed, desc=d, problems=[])
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_solver, kw, _ = fuzz_cases.random_case(ref_ns, seed)
+            ref_flat = flatten_solver(ref_solver, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
+    except Exception as e:                      # the reference refuses the configuration at set-up
+        rec["setup_error"] = f"{type(e).__name__}: {e}"
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                s, kw, _ = fuzz_cases.random_case(fuzz_cases.mirror_namespace(), seed)
+                flatten_solver(s, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
+            rec["problems"].append("the mirror accepts a configuration the reference refuses: " + rec["setup_error"])
+        except Exception:
+            pass
+        return rec
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mir_solver, kw, _ = fuzz_cases.random_case(fuzz_cases.mirror_namespace(), seed)
+            mir_flat = flatten_solver(mir_solver, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
+    except Exception as e:
+        rec["problems"].append(f"mirror set-up failed: {type(e).__name__}: {e}")
+        return rec
+    rec["digest"] = fuzz_cases.flat_digest(ref_flat)
+    if fuzz_cases.flat_digest(mir_flat) != rec["digest"]:
+        rec["problems"].append("flattened inputs differ between the reference objects and the mirror objects")
+    failed, msg = False, ""
+    try:
+        res = rh.run_and_record(ref_solver, kw)
+    except Exception as e:
+        failed, msg = True, f"{type(e).__name__}: {e}"
+        res = dict(depth=np.array(ref_solver.depth), flow=np.array(ref_solver.flow), iters=np.zeros(0, np.int32))
+    rec["ref_failed"], rec["ref_message"] = failed, msg[:120]
+    rec["ref_fail_level"] = int(ref_solver.time_level) if failed else 0
+    o = oracle_py.run(ref_flat, 1)
+    rec["oracle_status"], rec["oracle_fail_level"] = int(o["status"][0]), int(o["fail_level"][0])
+    good = rec["ref_fail_level"] if failed else res["depth"].shape[0]          # levels [0, good) are comparable
+    if failed != (rec["oracle_status"] != 0):
+        rec["problems"].append(f"reference {'raised' if failed else 'finished'} ({msg[:60]}), oracle status {rec['oracle_status']}")
+    elif failed and rec["oracle_fail_level"] != rec["ref_fail_level"]:
+        rec["problems"].append(f"reference died in level {rec['ref_fail_level']}, oracle in level {rec['oracle_fail_level']}")
+    else:
+        dh = np.abs(o["depth"][0][:good] - res["depth"][:good]) / np.abs(res["depth"][:good])
+        dq = np.abs(o["flow"][0][:good] - res["flow"][:good]) / np.maximum(np.abs(res["flow"][:good]), 1e-3)
+        rec["max_rel"] = float(max(dh.max(initial=0.0), dq.max(initial=0.0)))
+        if not (rec["max_rel"] <= 1e-10):
+            rec["problems"].append(f"oracle deviates from the reference by {rec['max_rel']:.3g}")
+        if not failed and not np.array_equal(o["iters"][0], res["iters"]):
+            rec["problems"].append(f"iteration counts differ: oracle {o['iters'][0].tolist()} reference {res['iters'].tolist()}")
+    rec["depth"], rec["flow"], rec["iters"] = res["depth"][:good], res["flow"][:good], res["iters"]
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", default="0:32")
+    ap.add_argument("--jobs", type=int, default=min(16, os.cpu_count() or 1))
+    ap.add_argument("--write", action="store_true")
+    a = ap.parse_args()
+    seeds = [s for part in a.seeds.split(",") for s in range(*(int(v) for v in part.split(":")))]
+    with Pool(a.jobs, maxtasksperchild=4) as pool:
+        recs = pool.map(one, sorted(seeds, key=lambda s: -s), chunksize=1)        # the long reaches (seeds >= 1000) first
+    recs.sort(key=lambda r: r["seed"])
+    bad = 0
+    corpus = {}
+    for r in recs:
+        d = r["desc"]
+        tag = f"seed {r['seed']:4d} {d['family']:22s} up={d['up']:16s} down={d['down']:16s} ic={d['ic']:12s} N={d['n_cells'] + 1:3d}"
+        if "setup_error" in r:
+            print(tag, "| reference refuses:", r["setup_error"][:70])
+        else:
+            state = f"raises in level {r['ref_fail_level']} ({r['ref_message'][:40]})" if r["ref_failed"] else f"iters {int(r['iters'].sum())}"
+            print(tag, "|", state, "| max rel", f"{r.get('max_rel', float('nan')):.2g}")
+        for p in r["problems"]:
+            bad += 1
+            print("      PROBLEM:", p)
+        if "digest" in r and not r["problems"]:
+            s = r["seed"]
+            corpus[f"s{s}_depth"], corpus[f"s{s}_flow"], corpus[f"s{s}_iters"] = r["depth"], r["flow"], r["iters"]
+            corpus[f"s{s}_fail_level"] = np.int32(r["ref_fail_level"])
+            corpus[f"s{s}_digest"] = np.array(r["digest"])
+    print(f"{len(recs)} seeds, {bad} problems, {len([k for k in corpus if k.endswith('_digest')])} in the corpus")
+    if a.write:
+        corpus["refused"] = np.array([r["seed"] for r in recs if "setup_error" in r and not r["problems"]], dtype=np.int32)
+        corpus["seeds"] = np.array(sorted(int(k[1:-7]) for k in corpus if k.endswith("_digest")), dtype=np.int32)
+        np.savez_compressed(CORPUS, **corpus)
+        print("wrote", CORPUS, os.path.getsize(CORPUS), "bytes")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,94 @@
+"""Differential fuzz corpus: 320 random small reaches and 32 of 274..484 nodes - the tiled long-reach path -
+(tests/fuzz_cases.py) that the LIVE reference ran in the build container
+(oracle/fuzz_reference.py --seeds 0:320,1000:1032 --write -> tests/golden/fuzz_corpus.npz: its depth / flow / Newton
+iteration counts, or the level it raised in).  The inputs are rebuilt here from the seed on the mirror API and must
+hash to the digest of the inputs flattened from the reference's own objects; then the oracle (CPU) and the device path
+(GPU, through the C ABI) replay every case."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+import fuzz_cases
+import util
+from flow_sim_b200.flatten import flatten_solver
+
+CORPUS = np.load(f"{util.GOLD}/fuzz_corpus.npz")
+SEEDS = [int(s) for s in CORPUS["seeds"]]
+
+
+def _inputs(seed):
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver, kw, d = fuzz_cases.random_case(fuzz_cases.mirror_namespace(), seed)
+        flat = flatten_solver(solver, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
+    assert fuzz_cases.flat_digest(flat) == str(CORPUS[f"s{seed}_digest"]), f"seed {seed}: inputs differ from the reference's"
+    return flat, d
+
+
+def _check(seed, d, out, what, rtol, iters_exact=True):
+    """One replayed case against the reference's record: the same fate (finished / died in the same level), depth and
+    flow of every level the reference completed, identical iteration counts."""
+    fail_level = int(CORPUS[f"s{seed}_fail_level"])
+    tag = f"{what}, seed {seed} ({d['family']}, up {d['up']}, down {d['down']}, ic {d['ic']})"
+    depth, flow = CORPUS[f"s{seed}_depth"], CORPUS[f"s{seed}_flow"]
+    if fail_level:
+        assert out["status"][0] != 0 and int(out["fail_level"][0]) == fail_level, \
+            f"{tag}: the reference raised in level {fail_level}, got status {out['status'][0]} level {out['fail_level'][0]}"
+    else:
+        assert out["status"][0] == 0, f"{tag}: the reference finished, got status {out['status'][0]} in level {out['fail_level'][0]}"
+        if iters_exact:
+            assert np.array_equal(out["iters"][0], CORPUS[f"s{seed}_iters"]), f"{tag}: iteration counts"
+    good = depth.shape[0]
+    util.assert_parity(out["depth"][0][:good], out["flow"][0][:good], depth, flow, tag, rtol=rtol)
+
+
+def test_corpus_covers_the_configuration_space():
+    fam, down, up, ic, fate = set(), set(), set(), set(), [0, 0]
+    for s in SEEDS:
+        d = fuzz_cases.describe(s)
+        fam.add(d["family"]); down.add(d["down"]); up.add(d["up"]); ic.add(d["ic"])
+        fate[int(CORPUS[f"s{s}_fail_level"]) != 0] += 1
+    assert fam == set(fuzz_cases.FAMILIES) and down == set(fuzz_cases.DOWNSTREAM) and up == set(fuzz_cases.UPSTREAM)
+    assert ic == {"linear", "GVF_equation", "steady-state"}
+    assert fate[0] >= 100 and fate[1] >= 50          # runs the reference finishes, and runs it dies in
+
+
+def test_mirror_refuses_what_the_reference_refuses():
+    for seed in CORPUS["refused"]:
+        with pytest.raises(Exception), contextlib.redirect_stdout(io.StringIO()):
+            solver, kw, _ = fuzz_cases.random_case(fuzz_cases.mirror_namespace(), int(seed))
+            flatten_solver(solver, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
+
+
+def test_oracle_replays_the_corpus():
+    import oracle_py
+
+    for seed in SEEDS:
+        flat, d = _inputs(seed)
+        _check(seed, d, oracle_py.run(flat, 1), "oracle", rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_device_replays_the_corpus():
+    """Every case through the C ABI.  Iteration counts must be the reference's except at a near tie of the convergence
+    test in the oracle's own record (util.assert_iteration_parity)."""
+    import oracle_py
+    from flow_sim_b200.abi import PreissmannLibraryError
+    from flow_sim_b200.runner import run_flat
+
+    flips = 0
+    for seed in SEEDS:
+        flat, d = _inputs(seed)
+        try:        # the family the library picks, and every packing that holds the reach (others are refused loudly)
+            out = run_flat(flat, lanes=(0, 8, 16, 32)[seed % 4])
+        except PreissmannLibraryError as e:
+            assert "instantiation holds" in str(e)
+            out = run_flat(flat)
+        if int(CORPUS[f"s{seed}_fail_level"]) == 0 and out["status"][0] == 0 and \
+                not np.array_equal(out["iters"][0], CORPUS[f"s{seed}_iters"]):
+            ora = oracle_py.run(flat, 1, trace_prev_error=True)
+            flips += util.assert_iteration_parity(out, ora, flat.tol, f"device, seed {seed}")
+            continue
+        _check(seed, d, out, "device", rtol=util.RTOL)
+    assert flips <= 2
