@@ -21,7 +21,7 @@ def mirror_namespace():
 
 FAMILIES = ["width", "simple", "rect_sections", "compound", "polyline", "trapezoid_to_polyline", "polyline_to_trapezoid",
             "compound_to_simple"]
-DOWNSTREAM = ["fixed_depth", "normal_depth", "rating_curve", "stage_hydrograph", "storage"]
+DOWNSTREAM = ["fixed_depth", "normal_depth", "rating_curve", "stage_hydrograph", "storage"]       # + "storage_general", drawn late
 UPSTREAM = ["flow_hydrograph", "flow_hydrograph", "flow_hydrograph", "stage_hydrograph"]
 LONG_SEEDS = 1000      # seeds from here on build reaches of 274..484 nodes
 
@@ -53,6 +53,13 @@ def describe(seed):
         d["ic"] = "linear" if rng.uniform() < 0.5 else d["ic"]
     d["curved"] = bool(rng.uniform() < 0.3) and d["family"] != "width" and d["n_cells"] >= 12     # centre-line curvature slope
     d["rating"] = ["power", "polynomial"][int(rng.integers(2))]
+    # later additions draw last, so that the earlier draws of a seed stay what they were
+    v = rng.uniform(0.0, 1.0, 4)
+    if d["down"] == "storage" and v[0] < 0.6:        # general lumped storage: area curve, outflow curve, head losses
+        d["down"] = "storage_general"
+    d["storage"] = dict(slope=float(0.02 + 0.08 * v[1]), losses=bool(v[2] < 0.6), k_q=float(0.5 * v[3]))
+    if d["up"] == "flow_hydrograph" and v[3] > 0.85:
+        d["up"] = ["fixed_depth", "normal_depth"][int(v[2] < 0.5)]
     return d
 
 
@@ -101,6 +108,8 @@ def random_case(ns, seed):
 
     if d["up"] == "flow_hydrograph":
         up = ns.Boundary("flow_hydrograph", chainage=0, bed_level=S0 * L, initial_depth=d["depth0"], hydrograph=ns.Hydrograph(function=wave))
+    elif d["up"] in ("fixed_depth", "normal_depth"):
+        up = ns.Boundary(d["up"], chainage=0, bed_level=S0 * L, initial_depth=d["depth0"])
     else:
         up = ns.Boundary("stage_hydrograph", chainage=0, bed_level=S0 * L, initial_depth=d["depth0"], hydrograph=ns.Hydrograph(function=stage_up))
     if d["down"] == "rating_curve":
@@ -112,6 +121,15 @@ def random_case(ns, seed):
         down = ns.Boundary("rating_curve", chainage=L, bed_level=0.0, initial_depth=d["depth0"], rating_curve=rc)
     elif d["down"] == "stage_hydrograph":
         down = ns.Boundary("stage_hydrograph", chainage=L, bed_level=0.0, initial_depth=d["depth0"], hydrograph=ns.Hydrograph(function=stage_down))
+    elif d["down"] == "storage_general":
+        down = ns.Boundary("fixed_depth", chainage=L, bed_level=0.0, initial_depth=d["depth0"])
+        ls = ns.LumpedStorage(surface_area=4.0e5, min_stage=d["depth0"], solution_boundaries=(0, 100))
+        stages = np.arange(0.0, 42.0, 2.0)
+        ls.set_area_curve(np.column_stack([stages, 4.0e5 * (1.0 + d["storage"]["slope"] * stages)]), alpha=1.0, beta=0.0)
+        rc = ns.RatingCurve()
+        rc.set("polynomial", a=0.1 * d["q_base"] / d["depth0"] ** 2, b=0.6 * d["q_base"] / d["depth0"], c=0.0)
+        ls.rating_curve, ls.capture_losses, ls.reservoir_length, ls.K_q = rc, d["storage"]["losses"], 1500.0, d["storage"]["k_q"]
+        down.set_lumped_storage(ls)
     elif d["down"] == "storage":
         down = ns.Boundary("fixed_depth", chainage=L, bed_level=0.0, initial_depth=d["depth0"])
         down.set_lumped_storage(ns.LumpedStorage(surface_area=4.0e5, min_stage=d["depth0"], solution_boundaries=(0, 100)))

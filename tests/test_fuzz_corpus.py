@@ -49,7 +49,8 @@ def test_corpus_covers_the_configuration_space():
         d = fuzz_cases.describe(s)
         fam.add(d["family"]); down.add(d["down"]); up.add(d["up"]); ic.add(d["ic"])
         fate[int(CORPUS[f"s{s}_fail_level"]) != 0] += 1
-    assert fam == set(fuzz_cases.FAMILIES) and down == set(fuzz_cases.DOWNSTREAM) and up == set(fuzz_cases.UPSTREAM)
+    assert fam == set(fuzz_cases.FAMILIES) and down == set(fuzz_cases.DOWNSTREAM) | {"storage_general"}
+    assert up == set(fuzz_cases.UPSTREAM) | {"fixed_depth", "normal_depth"}
     assert ic == {"linear", "GVF_equation", "steady-state"}
     assert fate[0] >= 100 and fate[1] >= 50          # runs the reference finishes, and runs it dies in
 
@@ -110,7 +111,8 @@ def test_device_ensembles_on_corpus_configurations():
         flat.member_n_main = d["n_main"] * rng.uniform(0.7, 1.4, M)
         if seed % 2:
             flat.member_n_fp = d["n_fp"] * rng.uniform(0.7, 1.4, M)
-        flat.up.series = flat.up.series[None, :] * (1.0 + (0.1 if d["up"] == "flow_hydrograph" else 0.01) * rng.uniform(-1, 1, (M, 1)))
+        if flat.up.series is not None:          # (a fixed-depth / normal-depth upstream end has no series)
+            flat.up.series = flat.up.series[None, :] * (1.0 + (0.1 if d["up"] == "flow_hydrograph" else 0.01) * rng.uniform(-1, 1, (M, 1)))
         ora = oracle_py.run(flat, M, trace_prev_error=True)
         try:
             out = run_flat(flat, n_members=M, lanes=(0, 8, 16, 32)[(seed // 3) % 4])
