@@ -30,7 +30,7 @@ __device__ __forceinline__ double gvf_slope(const double* sg, int NP, int node, 
   NodeVals nv;
   if (p.geo.irr_offset && sg[F_KIND * NP + node] == (double)PR_XS_IRREGULAR) {
     double top;
-    node_eval_irregular_call<false, GvfParams>(p.geo, node, h_in, Q, rg, p, nv, nullptr, &top);     // out of line
+    node_eval_irregular_call<CURV, GvfParams>(p.geo, node, h_in, Q, rg, p, nv, nullptr, &top);      // out of line
     nv.T = top;                                   // the profile uses the geometric top width, not dA/dh
   } else {
     node_eval<CURV, RM, false, GvfParams>(sg, NP, node, h_in, Q, rg, p, nv);

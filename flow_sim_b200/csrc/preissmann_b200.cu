@@ -332,7 +332,10 @@ int stage_geom(const pr_config& cfg, const pr_geom* g, Stage& st, pr::DevGeom& d
     d.irr_offset = st.in(g->irr_offset, N + 1);
     d.irr_x = st.in(g->irr_x, (size_t)total); d.irr_z = st.in(g->irr_z, (size_t)total);
     d.irr_left = st.in(g->irr_left, N); d.irr_right = st.in(g->irr_right, N);
-    // stage tables of the polyline sections (one interval search instead of six polyline scans per node evaluation)
+    // stage tables of the polyline sections (one interval search instead of six polyline scans per node evaluation);
+    // PR_IRR_NO_TABLES=1 keeps the scanning node pass (A/B and debugging)
+    static const bool no_tables = std::getenv("PR_IRR_NO_TABLES") != nullptr;
+    if (no_tables) return PR_OK;
     int* tab_n = st.scratch<int>(N);
     double* tab_z = st.scratch<double>((size_t)total);
     double* tab_c = st.scratch<double>((size_t)total * pr::kIrrTabCols);

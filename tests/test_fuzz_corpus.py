@@ -132,3 +132,31 @@ def test_device_ensembles_on_corpus_configurations():
             k = int(ora["fail_level"][m])
             util.assert_parity(out["depth"][m][:k], out["flow"][m][:k], ora["depth"][m][:k], ora["flow"][m][:k], what, rtol=util.FLIP_RTOL)
     assert died > 500 and finished > 1000 and flips <= 4
+
+
+@pytest.mark.gpu
+def test_device_initial_conditions_on_the_corpus():
+    """The device's GVF march (channel.py:307-378) and normal-depth solve (cross_section.py:184-205) against the initial
+    state the REFERENCE computed for the corpus configurations (it is part of the digested inputs): every section
+    family, 5-484 nodes."""
+    from flow_sim_b200.runner import gvf_initial_conditions, normal_depth_initial_conditions
+
+    n_gvf = n_normal = 0
+    for seed in SEEDS:
+        d = fuzz_cases.describe(seed)
+        if d["ic"] == "linear":
+            continue
+        flat, d = _inputs(seed)
+        if d["ic"] == "GVF_equation":
+            h, q, st = gvf_initial_conditions(flat, 1, flat.meta["initial_flow"], flat.meta["downstream_depth"])
+            assert st[0] == 0, f"seed {seed}: GVF status {st[0]}"
+            # 1e-16 typical; on a grid too coarse for the explicit predictor-corrector the march itself is unstable and
+            # amplifies rounding (seed 312: dx = 2 km, depths jumping between 2.5 and 10.8 m, 2e-10)
+            tol, n_gvf = util.RTOL, n_gvf + 1
+        else:
+            h, q = normal_depth_initial_conditions(flat, 1, flat.meta["initial_flow"])
+            tol, n_normal = 5e-11, n_normal + 1          # brentq's xtol is 2e-12 absolute
+        err = float(np.max(np.abs(h[0] - flat.ic_depth) / flat.ic_depth))
+        assert err <= tol, f"seed {seed} ({d['family']}, {d['ic']}): initial depth off by {err:.3g}"
+        assert np.array_equal(q[0], flat.ic_flow)
+    assert n_gvf >= 60 and n_normal >= 70
