@@ -24,6 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 sys.path[:0] = [HERE, REPO, os.path.join(REPO, "tests")]
 CORPUS = os.path.join(REPO, "tests", "golden", "fuzz_corpus.npz")
+DERIVED = ("area", "top_width", "froude_number", "wave_celerity")
 
 
 def one(seed):
@@ -98,6 +99,8 @@ def one(seed):
         if not failed and not np.array_equal(o["iters"][0], res["iters"]):
             rec["problems"].append(f"iteration counts differ: oracle {o['iters'][0].tolist()} reference {res['iters'].tolist()}")
     rec["depth"], rec["flow"], rec["iters"] = res["depth"][:good], res["flow"][:good], res["iters"]
+    if not failed and seed % 4 == 0:          # Solver.prepare_results (solver.py:65-98) of every fourth finished run
+        rec["derived"] = {k: np.array(getattr(ref_solver, k), dtype=np.float64) for k in DERIVED}
     return rec
 
 
@@ -131,6 +134,8 @@ def main():
             corpus[f"s{s}_depth"], corpus[f"s{s}_flow"], corpus[f"s{s}_iters"] = r["depth"], r["flow"], r["iters"]
             corpus[f"s{s}_fail_level"] = np.int32(r["ref_fail_level"])
             corpus[f"s{s}_digest"] = np.array(r["digest"])
+            for k, v in r.get("derived", {}).items():
+                corpus[f"s{s}_{k}"] = v
     print(f"{len(recs)} seeds, {bad} problems, {len([k for k in corpus if k.endswith('_digest')])} in the corpus")
     if a.write:
         corpus["refused"] = np.array([r["seed"] for r in recs if "setup_error" in r and not r["problems"]], dtype=np.int32)

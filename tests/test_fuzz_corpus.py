@@ -160,3 +160,23 @@ def test_device_initial_conditions_on_the_corpus():
         assert err <= tol, f"seed {seed} ({d['family']}, {d['ic']}): initial depth off by {err:.3g}"
         assert np.array_equal(q[0], flat.ic_flow)
     assert n_gvf >= 60 and n_normal >= 70
+
+
+@pytest.mark.gpu
+def test_device_derived_arrays_on_the_corpus():
+    """pr_derived_results on the reference's own depth / flow against the arrays its Solver.prepare_results made
+    (solver.py:65-98; stored for every fourth finished run): area, geometric top width, Froude number, wave celerity."""
+    from flow_sim_b200.runner import derived_results
+
+    n = 0
+    for seed in SEEDS:
+        if f"s{seed}_area" not in CORPUS.files:
+            continue
+        flat, d = _inputs(seed)
+        got = derived_results(flat, CORPUS[f"s{seed}_depth"][None], CORPUS[f"s{seed}_flow"][None])
+        for k in ("area", "top_width", "froude_number", "wave_celerity"):
+            ref = CORPUS[f"s{seed}_{k}"]
+            err = float(np.max(np.abs(got[k][0] - ref) / np.maximum(np.abs(ref), 1e-12)))
+            assert err <= 1e-12, f"seed {seed} ({d['family']}): {k} off by {err:.3g}"
+        n += 1
+    assert n >= 40
