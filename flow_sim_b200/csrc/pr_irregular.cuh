@@ -401,7 +401,12 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   o.w2 = (k.hth * dSeA) * dAdh;
   o.w3 = k.hth * dSeQ;
   o.w4 = k.th_dx2 * QA;
-  if (kc) { kc->K = K; kc->dKA = dKA; kc->A = A; kc->Sf = Sf; kc->dSfA = dSfA; kc->dSfQ = dSfQ; }
+  if (kc) {
+    // the boundary rows (normal depth; head losses of a lumped storage, lumped_storage.py:58-116 through
+    // hydraulics.Sf(A, Q, n, R)) take the conveyance of the WHOLE section even where the scheme's friction slope splits
+    const double SfW = Q * absQ / (K * K);
+    kc->K = K; kc->dKA = dKA; kc->A = A; kc->Sf = SfW; kc->dSfA = -2 * SfW * (dKA / K); kc->dSfQ = 2 * absQ / (K * K);
+  }
   if (top_width) *top_width = T;
 }
 

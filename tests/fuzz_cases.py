@@ -60,6 +60,9 @@ def describe(seed):
     d["storage"] = dict(slope=float(0.02 + 0.08 * v[1]), losses=bool(v[2] < 0.6), k_q=float(0.5 * v[3]))
     if d["up"] == "flow_hydrograph" and v[3] > 0.85:
         d["up"] = ["fixed_depth", "normal_depth"][int(v[2] < 0.5)]
+    # a side pocket behind a ridge on the right floodplain of the surveyed sections: a second wetted sub-channel at low
+    # stages, i.e. the split-flow conveyance (cross_section.py:329-439)
+    d["pocket"] = bool(rng.uniform() < 0.4) and d["family"] in ("polyline", "trapezoid_to_polyline", "polyline_to_trapezoid")
     return d
 
 
@@ -72,6 +75,9 @@ def _polyline(ns, d, invert, k):
     # node sits on the jump of the reference's properties() (see irr_tab_tie) and the reference's own run then depends
     # on the last bit of the boundary depth (seeds 150 and 178 of an earlier generator)
     z = np.array([7.0, 3.0 + u[(k + 3) % 8], 2.42, 1.0, 0.0, 0.1 * round(3 * u[(k + 4) % 8]), 1.0 + 0.47 * round(2 * u[(k + 5) % 8]), 2.42, 3.5, 7.5])
+    if d["pocket"]:
+        x = np.concatenate([x[:8], [half + 1.5, half + 2.5, half + 4.5, half + 5.5], x[8:]])
+        z = np.concatenate([z[:8], [3.27, 1.93, 1.93, 3.37], z[8:]])
     s = ns.IrregularSection(x=x, z=z + invert, n=d["n_main"], bed_slope=d["slope"])
     s.set_roughness_para((d["n_fp"], d["n_main"], d["n_fp"] * 1.1, -half, half))
     return s
