@@ -237,7 +237,7 @@ def inflow_table(small: bool) -> np.ndarray:
 def build(n_main=None, n_fp=None, calibration=False, with_gerd=True, curvature=None, sim_duration="default",
           initial_roseires_level=INITIAL_ROSEIRES_LEVEL, gerd_level=INITIAL_GERD_LEVEL, time_step=TIME_STEP,
           spatial_step=SPATIAL_STEP, theta=THETA, tolerance=TOLERANCE, jammed_spillways=0, jammed_sluice_gates=0,
-          inflow_hyd_func=None):
+          inflow_hyd_func=None, rating_kwargs=None):
     """model.run() up to the solver construction.  calibration=True reproduces n_calibrate.run_model:
     small inflow hydrograph, duration from the table (32 h), no centre-line curvature."""
     if inflow_hyd_func is not None:
@@ -261,8 +261,8 @@ def build(n_main=None, n_fp=None, calibration=False, with_gerd=True, curvature=N
     up = Boundary(condition="flow_hydrograph", hydrograph=gerd if with_gerd else inflow, chainage=chain[0])
     down = Boundary(initial_depth=initial_roseires_level - bed, bed_level=bed, condition="rating_curve",
                     rating_curve=RoseiresRatingCurve(initial_stage=initial_roseires_level, initial_flow=q0,
-                                                     jammed_sluice_gates=jammed_sluice_gates,
-                                                     jammed_spillways=jammed_spillways),
+                                                     **{**dict(jammed_sluice_gates=jammed_sluice_gates,
+                                                               jammed_spillways=jammed_spillways), **(rating_kwargs or {})}),
                     chainage=chain[-1])
     ch = Channel(initial_flow=q0, upstream_boundary=up, downstream_boundary=down)
     if use_curvature:

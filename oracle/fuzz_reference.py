@@ -9,7 +9,7 @@ and (2) the C oracle reproduces the reference's run: depth, flow (<= 1e-9 relati
 seeds as the corpus the GPU parity test replays on the box (tests/golden/fuzz_corpus.npz; inputs are rebuilt there from
 the seed on the mirror API and checked against the digest stored here).
 
-    python oracle/fuzz_reference.py --seeds 0:320,1000:1032 [--write] [--jobs 16]      (~5 min on 16 cores)
+    python oracle/fuzz_reference.py --seeds 0:320,1000:1032 --gerd 0:16 [--write] [--jobs 16]      (~6 min on 16 cores)
 """
 import argparse
 import contextlib
@@ -70,6 +70,15 @@ def one(seed):
     except Exception as e:
         rec["problems"].append(f"mirror set-up failed: {type(e).__name__}: {e}")
         return rec
+    return compare(rec, ref_solver, kw, ref_flat, mir_flat, seed % 4 == 0)
+
+
+def compare(rec, ref_solver, kw, ref_flat, mir_flat, want_derived):
+    """Run the reference and the oracle on the same inputs; fills rec (problems, outputs)."""
+    import fuzz_cases
+    import oracle_py
+    import ref_harness as rh
+
     rec["digest"] = fuzz_cases.flat_digest(ref_flat)
     if fuzz_cases.flat_digest(mir_flat) != rec["digest"]:
         rec["problems"].append("flattened inputs differ between the reference objects and the mirror objects")
@@ -99,26 +108,50 @@ def one(seed):
         if not failed and not np.array_equal(o["iters"][0], res["iters"]):
             rec["problems"].append(f"iteration counts differ: oracle {o['iters'][0].tolist()} reference {res['iters'].tolist()}")
     rec["depth"], rec["flow"], rec["iters"] = res["depth"][:good], res["flow"][:good], res["iters"]
-    if not failed and seed % 4 == 0:          # Solver.prepare_results (solver.py:65-98) of every fourth finished run
+    if not failed and want_derived:           # Solver.prepare_results (solver.py:65-98) of every fourth finished run
         rec["derived"] = {k: np.array(getattr(ref_solver, k), dtype=np.float64) for k in DERIVED}
     return rec
+
+
+def one_gerd(seed):
+    """A random member / scenario of the headline reach (tests/fuzz_cases.describe_gerd), ~30 s of reference time."""
+    import fuzz_cases
+    import ref_harness as rh
+    from flow_sim_b200.cases import build_gerd
+    from flow_sim_b200.flatten import flatten_solver
+
+    kwargs = fuzz_cases.describe_gerd(seed)
+    rec = dict(seed=seed, gerd=True, problems=[],
+               desc=dict(family="gerd" + ("_curved" if not kwargs["calibration"] else ""), up="gerd_release",
+                         down="roseires" + ("" if kwargs["rating_kwargs"].get("smooth", True) else "_gated"), ic="GVF_equation", n_cells=120))
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_solver, kw = rh.build_gerd(**kwargs)
+        ref_flat = flatten_solver(ref_solver, tolerance=kw["tolerance"])
+        mir_solver, mkw = build_gerd(**kwargs)
+        mir_flat = flatten_solver(mir_solver, tolerance=mkw["tolerance"])
+    return compare(rec, ref_solver, kw, ref_flat, mir_flat, False)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="0:32")
+    ap.add_argument("--gerd", default="", help="seed range of random members / scenarios of the headline reach")
     ap.add_argument("--jobs", type=int, default=min(16, os.cpu_count() or 1))
     ap.add_argument("--write", action="store_true")
     a = ap.parse_args()
-    seeds = [s for part in a.seeds.split(",") for s in range(*(int(v) for v in part.split(":")))]
+    seeds = [s for part in a.seeds.split(",") if part for s in range(*(int(v) for v in part.split(":")))]
+    gerd = [s for part in a.gerd.split(",") if part for s in range(*(int(v) for v in part.split(":")))]
     with Pool(a.jobs, maxtasksperchild=4) as pool:
+        pending = pool.map_async(one_gerd, gerd, chunksize=1)                      # the slow ones first
         recs = pool.map(one, sorted(seeds, key=lambda s: -s), chunksize=1)        # the long reaches (seeds >= 1000) first
+        grecs = pending.get()
     recs.sort(key=lambda r: r["seed"])
+    recs += grecs
     bad = 0
     corpus = {}
     for r in recs:
         d = r["desc"]
-        tag = f"seed {r['seed']:4d} {d['family']:22s} up={d['up']:16s} down={d['down']:16s} ic={d['ic']:12s} N={d['n_cells'] + 1:3d}"
+        tag = f"seed {'g' if r.get('gerd') else ' '}{r['seed']:4d} {d['family']:22s} up={d['up']:16s} down={d['down']:16s} ic={d['ic']:12s} N={d['n_cells'] + 1:3d}"
         if "setup_error" in r:
             print(tag, "| reference refuses:", r["setup_error"][:70])
         else:
@@ -130,7 +163,7 @@ def main():
         if r.get("excluded"):
             print("      excluded from the corpus: ill-conditioned, the oracle is within 1e-9 but not within 1e-10")
         if "digest" in r and not r["problems"] and not r.get("excluded"):
-            s = r["seed"]
+            s = f"g{r['seed']}" if r.get("gerd") else r["seed"]
             corpus[f"s{s}_depth"], corpus[f"s{s}_flow"], corpus[f"s{s}_iters"] = r["depth"], r["flow"], r["iters"]
             corpus[f"s{s}_fail_level"] = np.int32(r["ref_fail_level"])
             corpus[f"s{s}_digest"] = np.array(r["digest"])
@@ -139,7 +172,8 @@ def main():
     print(f"{len(recs)} seeds, {bad} problems, {len([k for k in corpus if k.endswith('_digest')])} in the corpus")
     if a.write:
         corpus["refused"] = np.array([r["seed"] for r in recs if "setup_error" in r and not r["problems"]], dtype=np.int32)
-        corpus["seeds"] = np.array(sorted(int(k[1:-7]) for k in corpus if k.endswith("_digest")), dtype=np.int32)
+        corpus["seeds"] = np.array(sorted(int(k[1:-7]) for k in corpus if k.endswith("_digest") and not k.startswith("sg")), dtype=np.int32)
+        corpus["gerd_seeds"] = np.array(sorted(int(k[2:-7]) for k in corpus if k.endswith("_digest") and k.startswith("sg")), dtype=np.int32)
         np.savez_compressed(CORPUS, **corpus)
         print("wrote", CORPUS, os.path.getsize(CORPUS), "bytes")
     return 1 if bad else 0

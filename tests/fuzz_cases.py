@@ -185,3 +185,23 @@ def flat_digest(flat):
         for f in ("bed_level", "bed_slope", "fixed_depth", "storage_area", "storage_min_stage", "storage_ymin", "storage_ymax"):
             put(getattr(bc, f))
     return h.hexdigest()
+
+
+# ---- the headline reach (cases/gerd_roseires): random members and scenarios -------------------------------------------
+
+def describe_gerd(seed):
+    """Roughness beyond the calibration grid, floodplain overrides, pool levels, jammed gates, blend widths, gate control
+    and (every fourth) the curved centre line: keyword arguments for `build_gerd` on either implementation."""
+    rng = np.random.default_rng(50_000 + seed)
+    kw = dict(n_main=float(rng.uniform(0.018, 0.065)), calibration=True)
+    if rng.uniform() < 0.5:
+        kw["n_fp"] = float(rng.uniform(0.03, 0.12))
+    kw["initial_roseires_level"] = float(np.round(rng.uniform(484.5, 489.0), 2))
+    rk = dict(jammed_spillways=int(rng.integers(0, 3)), jammed_sluice_gates=int(rng.integers(0, 3)),
+              buffer=float(np.round(rng.uniform(0.2, 1.0), 2)))
+    if rng.uniform() < 0.3:
+        rk.update(smooth=False, initially_open=bool(rng.uniform() < 0.5), max_cooldown=int(rng.choice([3600, 7200, 14400])))
+    kw["rating_kwargs"] = rk
+    if seed % 4 == 3:           # config 3's curved centre line, 12 hourly levels
+        kw.update(calibration=False, sim_duration=12 * 3600)
+    return kw

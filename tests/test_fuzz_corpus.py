@@ -1,6 +1,6 @@
 """Differential fuzz corpus: 320 random small reaches and 32 of 274..484 nodes - the tiled long-reach path -
-(tests/fuzz_cases.py) that the LIVE reference ran in the build container
-(oracle/fuzz_reference.py --seeds 0:320,1000:1032 --write -> tests/golden/fuzz_corpus.npz: its depth / flow / Newton
+and 16 random members / scenarios of the headline reach (tests/fuzz_cases.py) that the LIVE reference ran in the build
+container (oracle/fuzz_reference.py --seeds 0:320,1000:1032 --gerd 0:16 --write -> tests/golden/fuzz_corpus.npz: its depth / flow / Newton
 iteration counts, or the level it raised in).  The inputs are rebuilt here from the seed on the mirror API and must
 hash to the digest of the inputs flattened from the reference's own objects; then the oracle (CPU) and the device path
 (GPU, through the C ABI) replay every case."""
@@ -24,6 +24,23 @@ def _inputs(seed):
         flat = flatten_solver(solver, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
     assert fuzz_cases.flat_digest(flat) == str(CORPUS[f"s{seed}_digest"]), f"seed {seed}: inputs differ from the reference's"
     return flat, d
+
+
+GERD_SEEDS = [int(s) for s in CORPUS["gerd_seeds"]]
+
+
+def _gerd_inputs(seed):
+    """A random member / scenario of the headline reach (fuzz_cases.describe_gerd) on the mirror API."""
+    from flow_sim_b200.cases import build_gerd
+
+    kwargs = fuzz_cases.describe_gerd(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver, kw = build_gerd(**kwargs)
+        flat = flatten_solver(solver, tolerance=kw["tolerance"])
+    assert fuzz_cases.flat_digest(flat) == str(CORPUS[f"sg{seed}_digest"]), f"gerd seed {seed}: inputs differ from the reference's"
+    gated = not kwargs["rating_kwargs"].get("smooth", True)
+    return flat, dict(family="gerd" + ("" if kwargs["calibration"] else ", curved"), up="gerd release",
+                      down="roseires" + (", gate control" if gated else ""), ic="GVF_equation")
 
 
 def _check(seed, d, out, what, rtol, iters_exact=True):
@@ -68,6 +85,10 @@ def test_oracle_replays_the_corpus():
     for seed in SEEDS:
         flat, d = _inputs(seed)
         _check(seed, d, oracle_py.run(flat, 1), "oracle", rtol=1e-10)
+    assert len(GERD_SEEDS) >= 12
+    for seed in GERD_SEEDS:
+        flat, d = _gerd_inputs(seed)
+        _check(f"g{seed}", d, oracle_py.run(flat, 1), "oracle", rtol=1e-10)
 
 
 @pytest.mark.gpu
@@ -92,6 +113,14 @@ def test_device_replays_the_corpus():
             flips += util.assert_iteration_parity(out, ora, flat.tol, f"device, seed {seed}")
             continue
         _check(seed, d, out, "device", rtol=util.RTOL)
+    for seed in GERD_SEEDS:             # the headline reach: roughness off the grid, floodplain overrides, gate control
+        flat, d = _gerd_inputs(seed)
+        out = run_flat(flat)
+        if not np.array_equal(out["iters"][0], CORPUS[f"sg{seed}_iters"]):
+            ora = oracle_py.run(flat, 1, trace_prev_error=True)
+            flips += util.assert_iteration_parity(out, ora, flat.tol, f"device, gerd seed {seed}")
+            continue
+        _check(f"g{seed}", d, out, "device", rtol=util.RTOL)
     assert flips <= 2
 
 
