@@ -6,7 +6,7 @@
 // One wetted sub-channel (get_subchannels, :329-372) takes the base-class formulas the reference falls back to
 // (:374-439 -> :114-141).  Two or more (a bar or a ridge splitting the flow): every sub-channel is evaluated as a
 // section of its own and the conveyances are combined, K = (sum K_j^1.5)^(2/3), exactly as the reference does
-// (irr_split_K below; a sub-channel of more than kIrrSubMax points is refused: NaN, PR_STATUS_NAN).
+// (irr_split_K below; the sub-channels are views of the parent's points, PolySub - no copy, no size limit).
 #pragma once
 #include "pr_device.cuh"
 
@@ -16,47 +16,87 @@ namespace pr {
 // get_equivalent_n's subsection_props builds, :448-470).  The two np.sum reductions are reproduced in numpy's
 // pairwise order (8 interleaved accumulators up to 128 terms): the reference differentiates A and R by central
 // differences with dh = 1e-6, which amplifies a last-bit difference in A a million times.
-__device__ inline void irr_properties(const double* __restrict__ x, const double* __restrict__ z, int lo, int hi,
-                                      double hw, double& A_out, double& P_out, double& T_out) {
+// The scans read a polyline through a view: the arrays themselves, or one wetted sub-channel of them - its submerged
+// points [0, n_in) preceded / followed by a point on the water surface (what get_subchannels builds, :340-370) -
+// without copying it.  One view type for both, so that the scans are compiled once.
+struct PolySub {
+  const double* x;          // first submerged point of the sub-channel
+  const double* z;
+  int n_in;                 // submerged points
+  bool has_l, has_r;
+  double xl, xr, hw;        // stations of the water-surface points, their elevation
+  __device__ __forceinline__ double X(int k) const { const int j = k - (has_l ? 1 : 0); return j < 0 ? xl : (j >= n_in ? xr : x[j]); }
+  __device__ __forceinline__ double Z(int k) const { const int j = k - (has_l ? 1 : 0); return (j < 0 || j >= n_in) ? hw : z[j]; }
+  __device__ __forceinline__ int size() const { return n_in + (has_l ? 1 : 0) + (has_r ? 1 : 0); }
+};
+
+static __device__ __noinline__ void irr_properties(const PolySub& pl, int lo, int hi, double hw, double& A_out, double& P_out, double& T_out) {
   A_out = 0.0; P_out = 0.0; T_out = 0.0;
   const int n = hi - lo + 1;
   if (n <= 0) return;
-  x += lo; z += lo;
-  double z_min = z[0];
-  for (int i = 1; i < n; ++i) z_min = z[i] < z_min ? z[i] : z_min;
+  auto x = [&](int i) { return pl.X(lo + i); };
+  auto z = [&](int i) { return pl.Z(lo + i); };
+  double z_min = z(0);
+  for (int i = 1; i < n; ++i) { const double zi = z(i); z_min = zi < z_min ? zi : z_min; }
   if (hw <= z_min) return;
   double A_total = 0.0, P_total = 0.0, T_total = 0.0;
   int i = 0;
   while (i < n) {
-    if (hw - z[i] > 0.0) {
+    if (hw - z(i) > 0.0) {
       const int i0 = i;
-      while (i + 1 < n && hw - z[i + 1] > 0.0) i += 1;
+      while (i + 1 < n && hw - z(i + 1) > 0.0) i += 1;
       const int iN = i;
-      const bool has_l = i0 > 0 && z[i0 - 1] > hw, has_r = iN < n - 1 && z[iN + 1] > hw;
+      const bool has_l = i0 > 0 && z(i0 - 1) > hw, has_r = iN < n - 1 && z(iN + 1) > hw;
       double xl = 0.0, xr = 0.0;
-      if (has_l) { const double z0 = z[i0 - 1], z1 = z[i0], x0 = x[i0 - 1], x1 = x[i0]; xl = x0 + (hw - z0) / (z1 - z0) * (x1 - x0); }
-      if (has_r) { const double z0 = z[iN], z1 = z[iN + 1], x0 = x[iN], x1 = x[iN + 1]; xr = x0 + (hw - z0) / (z1 - z0) * (x1 - x0); }
+      if (has_l) { const double z0 = z(i0 - 1), z1 = z(i0), x0 = x(i0 - 1), x1 = x(i0); xl = x0 + (hw - z0) / (z1 - z0) * (x1 - x0); }
+      if (has_r) { const double z0 = z(iN), z1 = z(iN + 1), x0 = x(iN), x1 = x(iN + 1); xr = x0 + (hw - z0) / (z1 - z0) * (x1 - x0); }
       const int m = (iN - i0 + 1) + (has_l ? 1 : 0) + (has_r ? 1 : 0), nt = m - 1;
       // point k of the wetted polyline (intersection points carry z = hw)
-      auto px = [&](int k) { const int j = k - (has_l ? 1 : 0); return j < 0 ? xl : (j > iN - i0 ? xr : x[i0 + j]); };
-      auto pz = [&](int k) { const int j = k - (has_l ? 1 : 0); return (j < 0 || j > iN - i0) ? hw : z[i0 + j]; };
+      auto px = [&](int k) { const int j = k - (has_l ? 1 : 0); return j < 0 ? xl : (j > iN - i0 ? xr : x(i0 + j)); };
+      auto pz = [&](int k) { const int j = k - (has_l ? 1 : 0); return (j < 0 || j > iN - i0) ? hw : z(i0 + j); };
       auto term = [&](int k, double& ta, double& tp) {
         const double xa = px(k), xb = px(k + 1), za = pz(k), zb = pz(k + 1);
         const double d0 = fmax(hw - za, 0.0), d1 = fmax(hw - zb, 0.0), dx = xb - xa, dz = zb - za;
         ta = 0.5 * (d0 + d1) * dx;
         tp = sqrt(dx * dx + dz * dz);
       };
+      // np.sum of terms [k0, k0 + cnt), cnt <= 128: numpy's pairwise_sum block (8 interleaved accumulators from 8 terms on)
+      auto block = [&](int k0, int cnt, double& sa, double& sp) {
+        sa = 0.0; sp = 0.0;
+        if (cnt < 8) {
+          for (int k = 0; k < cnt; ++k) { double ta, tp; term(k0 + k, ta, tp); sa += ta; sp += tp; }
+        } else {
+          double ra[8], rp[8];
+          for (int k = 0; k < 8; ++k) term(k0 + k, ra[k], rp[k]);
+          const int nb = cnt - (cnt % 8);
+          for (int k = 8; k < nb; ++k) { double ta, tp; term(k0 + k, ta, tp); ra[k & 7] += ta; rp[k & 7] += tp; }
+          sa = ((ra[0] + ra[1]) + (ra[2] + ra[3])) + ((ra[4] + ra[5]) + (ra[6] + ra[7]));
+          sp = ((rp[0] + rp[1]) + (rp[2] + rp[3])) + ((rp[4] + rp[5]) + (rp[6] + rp[7]));
+          for (int k = nb; k < cnt; ++k) { double ta, tp; term(k0 + k, ta, tp); sa += ta; sp += tp; }
+        }
+      };
       double sa = 0.0, sp = 0.0;
-      if (nt < 8) {
-        for (int k = 0; k < nt; ++k) { double ta, tp; term(k, ta, tp); sa += ta; sp += tp; }
-      } else {                                   // numpy pairwise sum, block of <= 128 terms
-        double ra[8], rp[8];
-        for (int k = 0; k < 8; ++k) term(k, ra[k], rp[k]);
-        const int nb = nt - (nt % 8);
-        for (int k = 8; k < nb; ++k) { double ta, tp; term(k, ta, tp); ra[k & 7] += ta; rp[k & 7] += tp; }
-        sa = ((ra[0] + ra[1]) + (ra[2] + ra[3])) + ((ra[4] + ra[5]) + (ra[6] + ra[7]));
-        sp = ((rp[0] + rp[1]) + (rp[2] + rp[3])) + ((rp[4] + rp[5]) + (rp[6] + rp[7]));
-        for (int k = nb; k < nt; ++k) { double ta, tp; term(k, ta, tp); sa += ta; sp += tp; }
+      if (nt <= 128) {
+        block(0, nt, sa, sp);
+      } else {
+        // beyond 128 terms numpy halves recursively: sum(a[:n2]) + sum(a[n2:]), n2 = n/2 rounded down to a multiple of 8.
+        // The same tree, walked with a small explicit stack (depth <= log2(nt / 64)).
+        constexpr int kDepth = 10;
+        int lo_s[kDepth], n_s[kDepth], st_s[kDepth];
+        double acc_a[kDepth], acc_p[kDepth];
+        int top = 0;
+        lo_s[0] = 0; n_s[0] = nt; st_s[0] = 0;
+        while (top >= 0) {
+          int n2 = n_s[top] / 2;
+          n2 -= n2 % 8;
+          if (st_s[top] == 0) {
+            if (n_s[top] <= 128 || top + 1 >= kDepth) { block(lo_s[top], n_s[top], sa, sp); --top; }   // (depth 10: 64k terms)
+            else { st_s[top] = 1; lo_s[top + 1] = lo_s[top]; n_s[top + 1] = n2; st_s[top + 1] = 0; ++top; }
+          } else if (st_s[top] == 1) {            // the left half is in (sa, sp)
+            acc_a[top] = sa; acc_p[top] = sp;
+            st_s[top] = 2; lo_s[top + 1] = lo_s[top] + n2; n_s[top + 1] = n_s[top] - n2; st_s[top + 1] = 0; ++top;
+          } else { sa = acc_a[top] + sa; sp = acc_p[top] + sp; --top; }
+        }
       }
       A_total += sa; P_total += sp; T_total += px(m - 1) - px(0);
     }
@@ -66,13 +106,13 @@ __device__ inline void irr_properties(const double* __restrict__ x, const double
 }
 
 // conveyance of the points with x_min <= x <= x_max (subsection_props, :448-470)
-__device__ inline double irr_sub_K(const double* x, const double* z, int n, double hw, double x_min, double x_max, double n_value) {
+__device__ inline double irr_sub_K(const PolySub& pl, int n, double hw, double x_min, double x_max, double n_value) {
   int lo = 0, hi = n - 1;
-  while (lo < n && !(x[lo] >= x_min)) ++lo;
-  while (hi >= 0 && !(x[hi] <= x_max)) --hi;
+  while (lo < n && !(pl.X(lo) >= x_min)) ++lo;
+  while (hi >= 0 && !(pl.X(hi) <= x_max)) --hi;
   if (hi - lo + 1 < 2) return 0.0;
   double A, P, T;
-  irr_properties(x, z, lo, hi, hw, A, P, T);
+  irr_properties(pl, lo, hi, hw, A, P, T);
   if (A <= 0.0 || P <= 0.0) return 0.0;
   return A * pow(A / P, 2.0 / 3.0) / n_value;                 // hydraulics.conveyance (hydraulics.py:15-26)
 }
@@ -85,21 +125,21 @@ struct IrrSec {
   double n_eq, dRA, K, dKA;
 };
 
-__device__ inline void irr_section(const double* x, const double* z, int n, double hw, double lim_l, double lim_r,
+static __device__ __noinline__ void irr_section(const PolySub& pl, int n, double hw, double lim_l, double lim_r,
                                    double nl, double nm, double nr, IrrSec& s) {
   const double dh = 1e-6;
   double P1, T1, P2, T2;
-  irr_properties(x, z, 0, n - 1, hw, s.A, s.P, s.T);
-  irr_properties(x, z, 0, n - 1, hw - dh, s.A1, P1, T1);
-  irr_properties(x, z, 0, n - 1, hw + dh, s.A2, P2, T2);
+  irr_properties(pl, 0, n - 1, hw, s.A, s.P, s.T);
+  irr_properties(pl, 0, n - 1, hw - dh, s.A1, P1, T1);
+  irr_properties(pl, 0, n - 1, hw + dh, s.A2, P2, T2);
   s.R = s.P > 0.0 ? s.A / s.P : 0.0;
   const double R1 = P1 > 0.0 ? s.A1 / P1 : 0.0, R2 = P2 > 0.0 ? s.A2 / P2 : 0.0;
   // get_equivalent_n (:441-500)
   s.n_eq = nm;
   if (s.A > 0.0 && s.P > 0.0) {
-    const double Kl = irr_sub_K(x, z, n, hw, x[0], lim_l, nl);
-    const double Km = irr_sub_K(x, z, n, hw, lim_l, lim_r, nm);
-    const double Kr = irr_sub_K(x, z, n, hw, lim_r, x[n - 1], nr);
+    const double Kl = irr_sub_K(pl, n, hw, pl.X(0), lim_l, nl);
+    const double Km = irr_sub_K(pl, n, hw, lim_l, lim_r, nm);
+    const double Kr = irr_sub_K(pl, n, hw, lim_r, pl.X(n - 1), nr);
     const double K_total = pow(pow(Kl, 1.5) + pow(Km, 1.5) + pow(Kr, 1.5), 2.0 / 3.0);
     if (K_total > 0.0) s.n_eq = (s.A * pow(s.R, 2.0 / 3.0)) / K_total;
   }
@@ -110,6 +150,14 @@ __device__ inline void irr_section(const double* x, const double* z, int n, doub
     s.K = s.A * pow(s.R, 2.0 / 3.0) / s.n_eq;
     s.dKA = (pow(s.R, 2.0 / 3.0) + s.A * 2. / 3. * pow(s.R, 2.0 / 3.0 - 1.0) * s.dRA) / s.n_eq;
   }
+}
+
+__device__ inline void irr_section(const double* x, const double* z, int n, double hw, double lim_l, double lim_r,
+                                   double nl, double nm, double nr, IrrSec& s) {
+  irr_section(PolySub{x, z, n, false, false, 0.0, 0.0, hw}, n, hw, lim_l, lim_r, nl, nm, nr, s);
+}
+__device__ inline void irr_properties(const double* x, const double* z, int lo, int hi, double hw, double& A, double& P, double& T) {
+  irr_properties(PolySub{x, z, hi + 1, false, false, 0.0, 0.0, hw}, lo, hi, hw, A, P, T);
 }
 
 // numpy.interp(x, [xp0, xp1], [fp0, fp1]) as get_subchannels calls it (:357,361).  On the LEFT edge of a sub-channel
@@ -130,36 +178,30 @@ __device__ inline double irr_np_interp2(double x, double xp0, double xp1, double
   return r;
 }
 
-constexpr int kIrrSubMax = 64;      // points of one wetted sub-channel, its two water-surface points included
-
 // Split flow (IrregularSection.friction_slope / dSf_dA / dSf_dQ with several sub-channels, :374-439): each run of
 // >= 2 submerged points plus the points where it meets the water surface becomes a section of its own with the
 // parent's roughness limits and values; K_eq = (sum K_j^1.5)^(2/3), dK_eq/dA = 2/3 (sum K_j^1.5)^(-1/3) sum 1.5 K_j^0.5 dK_j/dA_j.
-__device__ inline bool irr_split_K(const double* __restrict__ x, const double* __restrict__ z, int n, double hw,
+// The sub-channel is a view of the parent's points (PolySub), whatever its size.
+__device__ inline void irr_split_K(const double* __restrict__ x, const double* __restrict__ z, int n, double hw,
                                    double lim_l, double lim_r, double nl, double nm, double nr, double& K_eq,
                                    double& dKA_eq) {
   double K_sum = 0.0, dK_sum = 0.0;
-  double lx[kIrrSubMax], lz[kIrrSubMax];
-  bool ok = true;
   for (int i = 0; i < n;) {
     if (!(z[i] < hw)) { ++i; continue; }
     const int start = i;
     while (i < n && z[i] < hw) ++i;
     const int end = i;
     if (end - start < 2) continue;
-    if (end - start + 2 > kIrrSubMax) { ok = false; continue; }
-    int m = 0;
-    if (start > 0 && z[start - 1] > hw) { lx[m] = irr_np_interp2(hw, z[start - 1], z[start], x[start - 1], x[start]); lz[m] = hw; ++m; }
-    for (int k = start; k < end; ++k) { lx[m] = x[k]; lz[m] = z[k]; ++m; }
-    if (end < n && z[end - 1] < hw && z[end] > hw) { lx[m] = irr_np_interp2(hw, z[end - 1], z[end], x[end - 1], x[end]); lz[m] = hw; ++m; }
+    PolySub sub_pl{x + start, z + start, end - start, false, false, 0.0, 0.0, hw};
+    if (start > 0 && z[start - 1] > hw) { sub_pl.has_l = true; sub_pl.xl = irr_np_interp2(hw, z[start - 1], z[start], x[start - 1], x[start]); }
+    if (end < n && z[end - 1] < hw && z[end] > hw) { sub_pl.has_r = true; sub_pl.xr = irr_np_interp2(hw, z[end - 1], z[end], x[end - 1], x[end]); }
     IrrSec sub;
-    irr_section(lx, lz, m, hw, lim_l, lim_r, nl, nm, nr, sub);
+    irr_section(sub_pl, sub_pl.size(), hw, lim_l, lim_r, nl, nm, nr, sub);
     K_sum += pow(sub.K, 1.5);
     dK_sum += 1.5 * pow(sub.K, 0.5) * sub.dKA;
   }
   K_eq = pow(K_sum, 2.0 / 3.0);
   dKA_eq = (2.0 / 3.0) * pow(K_sum, -1.0 / 3.0) * dK_sum;
-  return ok;
 }
 
 // ---- stage tables ----------------------------------------------------------------------------------------------
@@ -360,11 +402,9 @@ __device__ inline void node_eval_irregular(const DevGeom& g, int node, double h,
   const double A = sec.A, T = sec.T, R = sec.R, A1 = sec.A1, A2 = sec.A2, n_eq = sec.n_eq, dRA = sec.dRA;
   const double K = sec.K, dKA = sec.dKA;
   double Kf = K, dKAf = dKA;
-  bool refused = false;
-  if (runs > 1) refused = !irr_split_K(x, z, n, hw, lim_l, lim_r, nl, nm, nr, Kf, dKAf);
+  if (runs > 1) irr_split_K(x, z, n, hw, lim_l, lim_r, nl, nm, nr, Kf, dKAf);
   const double absQ = fabs(Q);
-  double Sf = Q * absQ / (Kf * Kf);                            // hydraulics.Sf (hydraulics.py:42-57)
-  if (refused) Sf = nan("");
+  const double Sf = Q * absQ / (Kf * Kf);                      // hydraulics.Sf (hydraulics.py:42-57)
   const double dSfA = -2 * Sf * (dKAf / Kf), dSfQ = 2 * absQ / (Kf * Kf);
   const double dAdh = (A2 - A1) / (2 * dh);
   double Se = Sf, dSeA = dSfA, dSeQ = dSfQ;

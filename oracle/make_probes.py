@@ -6,6 +6,8 @@ copy oracle/_ref/pyref exists) -> small fixtures under tests/golden/:
   `ref_harness.build_irregular(pocket=True)` at (node, depth, flow) probe points, 114 of the 252 with several wetted
   sub-channels (cross_section.py:329-439).  The probe points are kept when the fixture already exists (values are
   re-evaluated, so `--check` proves the committed numbers are the reference's), else drawn with a fixed seed.
+* irregular_dense_probe.npz - the same quantities for a 201-point version of one of those sections (sub-channels of
+  ~100 points, no stage table on the device).
 * trapezoid_z_at_probe.npz - `TrapezoidalSection.z_at` (cross_section.py:795-849) of a rectangle, a simple and a compound
   trapezoid on a lateral grid, and the blend of a compound trapezoid with a polyline (`interpolate_cross_section`,
   :933-969) at three weights.
@@ -50,6 +52,37 @@ def pocket_rows():
     return dict(rows=np.array(rows, dtype=np.float64), columns=np.array(COLUMNS))
 
 
+def densify(x, z, k):
+    """Every segment of a polyline cut into k equal pieces (the same shape, k times the points)."""
+    t = np.linspace(0.0, 1.0, k, endpoint=False)
+    xs = np.concatenate([x[:-1, None] + (x[1:] - x[:-1])[:, None] * t[None, :], x[-1:, None]], axis=None)
+    zs = np.concatenate([z[:-1, None] + (z[1:] - z[:-1])[:, None] * t[None, :], z[-1:, None]], axis=None)
+    return xs, zs
+
+
+def dense_rows():
+    """The side-pocket section of node 7 with 20 points per segment (201 points: beyond the device's stage tables, and
+    sub-channels of ~100 points): the same quantities as pocket_rows on a fixed stage / flow grid."""
+    import ref_harness as rh
+
+    solver, _ = rh.build_irregular(pocket=True)
+    rh.setup_reference()
+    from src.hydromodel.cross_section import IrregularSection
+
+    base = solver.channel.xs_at_node[7]
+    x, z = densify(np.asarray(base.x, float), np.asarray(base.z, float), 20)
+    xs = IrregularSection(x=x, z=z, n=base.n_main, bed_slope=base.bed_slope)
+    xs.set_roughness_para(base.get_roughness_para())
+    rows = []
+    for h in np.arange(0.35, 4.4, 0.11):
+        Q = 40.0 + 17.0 * h
+        hw = h + xs.z_min
+        rows.append([7, h, Q, len(xs.get_subchannels(hw)), xs.friction_slope(h, Q), xs.dSf_dA(h, Q), xs.dSf_dQ(h, Q),
+                     xs.conveyance(hw), xs.dK_dA(hw), xs.area(hw), xs.dA_dh(hw)])
+    return dict(rows=np.array(rows, dtype=np.float64), columns=np.array(COLUMNS), x=x, z=z,
+                roughness=np.array(base.get_roughness_para(), dtype=np.float64))
+
+
 def z_at_rows():
     import ref_harness as rh
 
@@ -79,7 +112,8 @@ def z_at_rows():
 
 def main():
     check = "--check" in sys.argv[1:]
-    for name, make in (("irregular_pocket_probe.npz", pocket_rows), ("trapezoid_z_at_probe.npz", z_at_rows)):
+    for name, make in (("irregular_pocket_probe.npz", pocket_rows), ("irregular_dense_probe.npz", dense_rows),
+                       ("trapezoid_z_at_probe.npz", z_at_rows)):
         data = make()
         path = os.path.join(GOLD, name)
         if check:

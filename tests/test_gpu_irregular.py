@@ -273,3 +273,23 @@ def test_long_polyline_reach_on_the_tile_kernels():
     assert np.array_equal(out["status"], ora["status"]) and out["status"][0] == 0
     util.assert_parity(out["depth"], out["flow"], ora["depth"], ora["flow"], "N=301 polyline reach")
     assert np.array_equal(out["iters"], ora["iters"])
+
+
+@pytest.mark.parametrize("k,lanes", [(6, 0), (6, -1), (20, 0), (20, -1)])
+def test_dense_polylines_with_split_flow(k, lanes):
+    """The side-pocket reach with every polyline segment cut into k pieces: k = 6 keeps the sections within the stage
+    tables (<= 128 points), k = 20 gives 221-381 points per section - no table, sums of more than 128 terms (numpy's
+    recursive pairwise order) and wetted sub-channels of ~100 points (views of the parent's points, no size limit).
+    Fused and tiled path against the oracle, which the live reference pins on such a section
+    (tests/golden/irregular_dense_probe.npz)."""
+    import oracle_py
+
+    flat = util.golden_inputs("irregular_pocket")
+    util.densify_polylines(flat, k)
+    assert int(np.diff(flat.geom["irr_offset"]).max()) > (300 if k == 20 else 100)
+    M = 5
+    flat.member_n_main = np.linspace(0.026, 0.034, M)
+    ora = oracle_py.run(flat, M, trace_prev_error=True)
+    out = run_flat(flat, n_members=M, lanes=lanes)
+    assert np.array_equal(out["status"], ora["status"]) and not ora["status"].any()
+    util.assert_iteration_parity(out, ora, flat.tol, f"dense polylines x{k}, lanes={lanes}")

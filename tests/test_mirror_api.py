@@ -122,6 +122,34 @@ def test_split_flow_conveyance_equals_the_reference():
         assert (xs.conveyance(h + xs.z_min), xs.dK_dA(h + xs.z_min)) == (K, dKA)
 
 
+def _dense_pocket_case(k):
+    """The side-pocket reach with every polyline segment cut into k pieces (util.densify_polylines)."""
+    flat = util.golden_inputs("irregular_pocket")
+    util.densify_polylines(flat, k)
+    return flat
+
+
+def test_split_flow_on_dense_polylines_equals_the_reference():
+    """A 381-point version of a side-pocket section (tests/golden/irregular_dense_probe.npz, oracle/make_probes.py):
+    sums of more than 128 terms take numpy's recursive pairwise order, sub-channels hold ~100 points.  Oracle and mirror
+    against the live reference's values - bit for bit."""
+    import oracle_py
+
+    fx = np.load(f"{util.GOLD}/irregular_dense_probe.npz")
+    rows = fx["rows"]
+    assert (rows[:, 3] > 1).sum() >= 5 and len(fx["x"]) > 300
+    par = fx["roughness"]
+    xs = hydromodel.IrregularSection(x=fx["x"], z=fx["z"], n=par[1], bed_slope=5e-4)
+    xs.set_roughness_para(tuple(par))
+    flat = util.golden_inputs("irregular_pocket")
+    util.replace_polyline(flat, 7, fx["x"], fx["z"], par[3], par[4])
+    for node, h, Q, nsub, Sf, dSfA, dSfQ, K, dKA, A, dAdh in rows:
+        got = oracle_py.section_probe(flat, 7, h, Q)
+        assert (got["Sf"], got["dSf_dA"], got["dSf_dQ"]) == (Sf, dSfA, dSfQ), h
+        assert (xs.friction_slope(h, Q), xs.dSf_dA(h, Q), xs.dSf_dQ(h, Q)) == (Sf, dSfA, dSfQ), h
+        assert len(xs.get_subchannels(h + xs.z_min)) == int(nsub)
+
+
 def test_trapezoid_bed_profile_and_mixed_blend_equal_the_reference():
     """`TrapezoidalSection.z_at` (cross_section.py:795-849) and the blend of a trapezoid with a polyline
     (`interpolate_cross_section`, :933-969, either order, three weights) against the live reference's values

@@ -95,3 +95,30 @@ def release_ensemble():
     flat.ic_depth = np.stack([a.ic_depth, b.ic_depth])
     flat.ic_flow = np.stack([a.ic_flow, b.ic_flow])
     return flat, [golden_outputs("gerd_release"), golden_outputs("gerd_calib_m0")]
+
+
+def replace_polyline(flat, node, x, z, lim_l, lim_r):
+    """Swap the polyline of one IrregularSection node of flattened inputs (CSR arrays of flat.geom)."""
+    g = flat.geom
+    off = g["irr_offset"]
+    xs = [g["irr_x"][off[i]:off[i + 1]] for i in range(flat.n_nodes)]
+    zs = [g["irr_z"][off[i]:off[i + 1]] for i in range(flat.n_nodes)]
+    xs[node], zs[node] = np.asarray(x, np.float64), np.asarray(z, np.float64)
+    g["irr_x"], g["irr_z"] = np.concatenate(xs), np.concatenate(zs)
+    g["irr_offset"] = np.concatenate([[0], np.cumsum([len(p) for p in xs])]).astype(np.int32)
+    g["irr_left"], g["irr_right"], g["z_bed"] = g["irr_left"].copy(), g["irr_right"].copy(), g["z_bed"].copy()
+    g["irr_left"][node], g["irr_right"][node], g["z_bed"][node] = lim_l, lim_r, float(np.min(z))
+
+
+def densify_polylines(flat, k):
+    """Every segment of every polyline of flattened inputs cut into k equal pieces: the same shapes, k times the points."""
+    g = flat.geom
+    off = g["irr_offset"].copy()
+    t = np.linspace(0.0, 1.0, k, endpoint=False)
+    for i in range(flat.n_nodes):
+        x, z = g["irr_x"][g["irr_offset"][i]:g["irr_offset"][i + 1]], g["irr_z"][g["irr_offset"][i]:g["irr_offset"][i + 1]]
+        if len(x) < 2:
+            continue
+        xd = np.concatenate([x[:-1, None] + (x[1:] - x[:-1])[:, None] * t[None, :], x[-1:, None]], axis=None)
+        zd = np.concatenate([z[:-1, None] + (z[1:] - z[:-1])[:, None] * t[None, :], z[-1:, None]], axis=None)
+        replace_polyline(flat, i, xd, zd, g["irr_left"][i], g["irr_right"][i])
