@@ -135,6 +135,16 @@ __device__ __forceinline__ double fast_rcbrt(double x) {  // x^(-1/3), x > 0 wit
   return fma(r, e * fma(e, 2.0 / 9.0, 1.0 / 3.0), r);
 }
 
+// A node that an update has left dry (depth <= 0) ends the member at its next residual evaluation: the reference clamps
+// the depth to zero (cross_section.py:628-632: A = P = R = T = 0) and dies of the zero conveyance that follows.  The
+// node pass leaves the depth unclamped - and a depth below -b / (2 sqrt(1 + m^2)) makes A and P both negative, their
+// ratio positive, so that a member the reference has lost could run on (1 member in ~8,000 of the device fuzz,
+// tools/fuzz_device.py) - so the UPDATE turns such a depth into NaN: an integer test on the high word (depths below
+// 2^-1022 * 2^20 count as dry), no FP64-pipe work (a clamp in the node pass cost the headline kernel 1.8 %).
+__device__ __forceinline__ double poison_dry(double h) {
+  return __double2hiint(h) <= 0 ? __longlong_as_double(0x7ff8000000000000LL) : h;
+}
+
 // ---- per-node geometry staged in shared memory (SoA: field f of slot idx at sg[f*NP + idx]) -----------
 
 enum GeoField {
@@ -248,7 +258,7 @@ __device__ __forceinline__ void node_eval(const double* __restrict__ sg, const i
 #define GEO(f) sg[(f)*NP + idx]
   const double z = GEO(F_Z), b = GEO(F_B);
   const double hw = z + h;        // Solver.water_level_at
-  const double d = hw - z;        // depth = max(0, hw - z_bed); a dry node (d <= 0) ends in status NaN
+  const double d = hw - z;        // depth = max(0, hw - z_bed) in the reference; a dry node ends the member: poison_dry()
   // Branch-free section geometry: the in-bank (simple trapezoid; a rectangle is m = 0) and the over-bank
   // expressions are both evaluated and selected, so that the whole node pass is straight-line code the
   // scheduler can interleave with its neighbours.  Non-compound sections are staged with h_bank = 1e300.

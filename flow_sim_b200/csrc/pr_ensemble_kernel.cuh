@@ -557,7 +557,7 @@ pr_ensemble_kernel(const __grid_constant__ DevParams p) {
     if (__any_sync(kFull, active && converged)) refresh_level_constants();
     if (active) {
 #pragma unroll
-      for (int j = 0; j < M; ++j) { h[j] += dh[j]; q[j] += dq[j]; }     // unknowns += delta
+      for (int j = 0; j < M; ++j) { h[j] = poison_dry(h[j] + dh[j]); q[j] += dq[j]; }     // unknowns += delta
       if (converged) {
         level += 1; it = 0;
         if (level >= L) active = false;

@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(128, (IRR || CURV || CMP) ? 2 : PR_LONG_CTAS) 
     }
     if (act == 3) return;            // the member's last level: nothing left to solve
 #pragma unroll
-    for (int j = 0; j <= kLongM; ++j) { h[j] += dh[j]; qq[j] += dq[j]; }       // x_k
+    for (int j = 0; j <= kLongM; ++j) { h[j] = poison_dry(h[j] + dh[j]); qq[j] += dq[j]; }       // x_k
     if (vec) {                 // nc == 4
       *reinterpret_cast<double4*>(xh_out + c0) = make_double4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<double4*>(xq_out + c0) = make_double4(qq[0], qq[1], qq[2], qq[3]);
