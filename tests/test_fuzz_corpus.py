@@ -244,3 +244,28 @@ def test_device_roughness_sweeps_on_corpus_configurations():
             flips += util.assert_iteration_parity(res, ora, flat.tol, what, members=ok)
             n += len(ok)
     assert n >= 200 and flips <= 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,lanes", [(411, 32), (544, 0)])
+def test_members_the_reference_loses_stay_lost(seed, lanes):
+    """Two ensembles of tools/fuzz_device.py: every member leaves a node dry in level 1 - the reference (and the
+    oracle) clamps the depth to zero and dies of the zero conveyance - yet one member used to run on to the end on the
+    device, because a depth below -b / (2 sqrt(1 + m^2)) makes A and P both negative and their ratio positive
+    (`poison_dry`, pr_device.cuh)."""
+    import oracle_py
+    from flow_sim_b200.runner import run_flat
+
+    d = fuzz_cases.describe(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        solver, kw, _ = fuzz_cases.random_case(fuzz_cases.mirror_namespace(), seed)
+        flat = flatten_solver(solver, tolerance=kw["tolerance"], max_iter=kw["max_iter"])
+    rng = np.random.default_rng(30_000 + seed)
+    M = 13
+    flat.member_n_main = d["n_main"] * rng.uniform(0.7, 1.4, M)
+    flat.member_n_fp = d["n_fp"] * rng.uniform(0.7, 1.4, M) if seed % 2 else None
+    ora = oracle_py.run(flat, M)
+    assert np.all(ora["status"] != 0) and np.all(ora["fail_level"] == 1)
+    out = run_flat(flat, n_members=M, lanes=lanes)
+    assert np.array_equal(out["status"], ora["status"]) and np.array_equal(out["fail_level"], ora["fail_level"])
+    assert np.all(np.isnan(out["depth"][:, 1:]))
