@@ -22,6 +22,7 @@ sys.path[:0] = [REPO, os.path.join(REPO, "tests"), os.path.join(REPO, "oracle")]
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", default="320:900")
+    ap.add_argument("--gerd", default="", help="seed range of random members / scenarios of the headline reach")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import fuzz_cases
@@ -31,7 +32,7 @@ def main():
     from flow_sim_b200.flatten import flatten_solver
     from flow_sim_b200.runner import run_flat
 
-    seeds = [s for part in a.seeds.split(",") for s in range(*(int(v) for v in part.split(":")))]
+    seeds = [s for part in a.seeds.split(",") if part for s in range(*(int(v) for v in part.split(":")))]
     problems, n_run, n_refused, n_members = [], 0, 0, 0
     for seed in seeds:
         if a.out and seed % 50 == 0:        # progress survives a time-out
@@ -71,7 +72,34 @@ def main():
                         util.assert_iteration_parity(out, ora, flat.tol, "x", members=ok)
                     except AssertionError as e:
                         problems.append(dict(tag, what=str(e)[:300]))
-    rep = dict(seeds=a.seeds, launches=n_run, members=n_members, refused_at_setup=n_refused, problems=problems)
+    # random members / scenarios of the headline reach (fuzz_cases.describe_gerd): single runs on the fused and on the
+    # tiled path, and a 16-member roughness ensemble on each scenario
+    from flow_sim_b200.cases import build_gerd
+
+    for seed in [s for part in a.gerd.split(",") if part for s in range(*(int(v) for v in part.split(":")))]:
+        kwargs = fuzz_cases.describe_gerd(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            solver, kw = build_gerd(**kwargs)
+            flat = flatten_solver(solver, tolerance=kw["tolerance"])
+        rng = np.random.default_rng(40_000 + seed)
+        for M, lanes in ((1, 0), (1, -1), (16, 0)):
+            if M > 1:
+                flat.member_n_main = rng.uniform(0.018, 0.065, M)
+                flat.member_n_fp = rng.uniform(0.03, 0.12, M) if seed % 2 else None
+            ora = oracle_py.run(flat, M, trace_prev_error=True)
+            out = run_flat(flat, n_members=M, lanes=lanes)
+            n_run += 1
+            n_members += M
+            tag = dict(seed=f"g{seed}", M=M, lanes=lanes, scenario={k: v for k, v in kwargs.items() if k != "n_main"})
+            if not np.array_equal(out["status"], ora["status"]) or not np.array_equal(out["fail_level"], ora["fail_level"]):
+                problems.append(dict(tag, what="fate differs", got=out["status"].tolist(), oracle=ora["status"].tolist()))
+                continue
+            ok = np.nonzero(ora["status"] == 0)[0]
+            try:
+                util.assert_iteration_parity(out, ora, flat.tol, "x", members=ok)
+            except AssertionError as e:
+                problems.append(dict(tag, what=str(e)[:300]))
+    rep = dict(seeds=a.seeds, gerd=a.gerd, launches=n_run, members=n_members, refused_at_setup=n_refused, problems=problems)
     print(json.dumps(rep, indent=1)[:6000])
     if a.out:
         json.dump(rep, open(a.out, "w"), indent=1)
