@@ -105,9 +105,10 @@ def test_packed_warp_kernels_at_scale(case):
     assert 0.4 * M < ok.sum() < M
     # identical iteration counts except at near ties of the convergence test (tests/util.py: NEAR_TIE).  This random
     # ensemble is a stress test - half of its members fail, and the survivors include near-critical flows on which the
-    # unpivoted block elimination of the packed kernels loses digits: measured worst member 1.2e-9 (akbari, 16 lanes x
-    # 2 nodes; every other member < 6e-12, and 2e-14 with one node per lane), so it is held to 5e-9, not 1e-9
-    flips = util.assert_iteration_parity(out, ora, flat.tol, f"{case} x {M}", members=np.nonzero(ok)[0], rtol=5e-9)
+    # unpivoted block elimination of the packed kernels loses digits: measured worst member 2.1e-10 (akbari, 16 lanes x
+    # 2 nodes; 99.9 % of the members < 4e-12, and 2e-14 with one node per lane; a compensated determinant in the local
+    # condensation does not change it - it is the conditioning of the elimination order, not its rounding)
+    flips = util.assert_iteration_parity(out, ora, flat.tol, f"{case} x {M}", members=np.nonzero(ok)[0])
     err = np.max(np.abs(out["depth"][ok] - ora["depth"][ok]) / np.abs(ora["depth"][ok]), axis=1)
     assert (err <= util.RTOL).mean() >= 0.999
     assert flips <= 2, f"{flips} members with a near-tie flip among {int(ok.sum())}"
